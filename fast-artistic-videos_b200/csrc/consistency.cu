@@ -1,0 +1,290 @@
+// consistency.cu -- forward/backward-flow occlusion test on the GPU.
+//   a-11 checkConsistency          consistencyChecker/consistencyChecker.cpp:80-134
+//   a-12 computeCorners + normalize + avg    consistencyChecker.cpp:39-78, CMatrix.h:721-736,1245-1251,
+//        filters CFilter.h:600-611 (taps), :1499-1578 (mirror borders), :1417-1464 (IIR)
+//
+// The reference evaluates hard thresholds with a mix of float and double arithmetic (:110-125).  The
+// kernels below mirror that mix operation by operation with explicit round-to-nearest intrinsics (no
+// FMA contraction), so the {0,255} mask is BIT-IDENTICAL to the reference binary's PGM.  The work is a
+// 2-plane gather + one byte store per pixel: HBM-bound, 4 pixels per thread, 16-byte flow1 loads.
+//
+// The motion-edge branch (:129-132) assigns MOTION_BOUNDARIE_VALUE = 255 (:12) to pixels that are
+// already 255 and is therefore not evaluated (no observable effect).
+#include "fav_common.cuh"
+
+namespace fav {
+
+__device__ __forceinline__ float lerp_mixed(float alpha, float v0, float v1) {
+  // (1.0 - alpha) * v0 + alpha * v1   with 1.0 a double literal: double*float -> double; alpha*v1 in float
+  double a = __dmul_rn(__dsub_rn(1.0, (double)alpha), (double)v0);
+  float b = __fmul_rn(alpha, v1);
+  return (float)__dadd_rn(a, (double)b);
+}
+
+__device__ __forceinline__ uint8_t check_pixel(const float *__restrict__ f2u, const float *__restrict__ f2v,
+                                               float u2, float v2, int ax, int ay, int W, int H,
+                                               const float *__restrict__ structure, float structureAvg) {
+  float bx = __fadd_rn((float)ax, u2);  // :101
+  float by = __fadd_rn((float)ay, v2);
+  int x1 = (int)floorf(bx), y1 = (int)floorf(by);  // :103-104
+  int x2 = x1 + 1, y2 = y1 + 1;
+  if (x1 < 0 || x2 >= W || y1 < 0 || y2 >= H) return 0;  // :107-108
+  float alphaX = __fsub_rn(bx, (float)x1), alphaY = __fsub_rn(by, (float)y1);  // :109
+  int64_t i11 = (int64_t)y1 * W + x1, i21 = i11 + 1, i12 = i11 + W, i22 = i12 + 1;
+  float a = lerp_mixed(alphaX, __ldg(f2u + i11), __ldg(f2u + i21));  // :110
+  float b = lerp_mixed(alphaX, __ldg(f2u + i12), __ldg(f2u + i22));
+  float u = lerp_mixed(alphaY, a, b);
+  a = lerp_mixed(alphaX, __ldg(f2v + i11), __ldg(f2v + i21));
+  b = lerp_mixed(alphaX, __ldg(f2v + i12), __ldg(f2v + i22));
+  float v = lerp_mixed(alphaY, a, b);
+  float cx = __fadd_rn(bx, u), cy = __fadd_rn(by, v);  // :116-117
+  float structureTerm = 0.f;
+  if (structure) {  // :122-123
+    float s = __fsub_rn(__fdiv_rn(structureAvg, 2.0f), __ldg(structure + (int64_t)ay * W + ax));
+    structureTerm = __fmul_rn(__fdiv_rn(4.0f, structureAvg), fmaxf(0.0f, s));
+  }
+  float ex = __fsub_rn(cx, (float)ax), ey = __fsub_rn(cy, (float)ay);
+  float lhs = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+  float mag = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(u2, u2), __fmul_rn(v2, v2)), __fmul_rn(u, u)),
+                        __fmul_rn(v, v));
+  double rhs = __dadd_rn(__dadd_rn(__dmul_rn(0.01, (double)mag), (double)structureTerm), (double)0.5f);  // :124
+  return ((double)lhs >= rhs) ? 0 : 255;
+}
+
+__global__ void __launch_bounds__(256) consistency_kernel(const float *__restrict__ f1u, const float *__restrict__ f1v,
+                                                          const float *__restrict__ f2u, const float *__restrict__ f2v,
+                                                          const float *__restrict__ structure,
+                                                          const float *__restrict__ avg_dev, float avg_host,
+                                                          uint8_t *__restrict__ rel, float *__restrict__ cert, int W,
+                                                          int H, int vec) {
+  int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * vec;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x0 >= W || y >= H) return;
+  const int64_t o = (int64_t)y * W + x0;
+  float savg = avg_dev ? __ldg(avg_dev) : avg_host;
+  float u2[4], v2[4];
+  if (vec == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4 *>(f1u + o));
+    u2[0] = t.x; u2[1] = t.y; u2[2] = t.z; u2[3] = t.w;
+    t = __ldg(reinterpret_cast<const float4 *>(f1v + o));
+    v2[0] = t.x; v2[1] = t.y; v2[2] = t.z; v2[3] = t.w;
+  } else {
+    u2[0] = f1u[o];
+    v2[0] = f1v[o];
+  }
+  uint8_t r[4];
+  for (int i = 0; i < vec; ++i)
+    r[i] = check_pixel(f2u, f2v, u2[i], v2[i], x0 + i, y, W, H, structure, savg);
+  if (vec == 4) {
+    if (rel) *reinterpret_cast<uchar4 *>(rel + o) = make_uchar4(r[0], r[1], r[2], r[3]);
+    if (cert)
+      *reinterpret_cast<float4 *>(cert + o) =
+          make_float4(r[0] ? 1.f : 0.f, r[1] ? 1.f : 0.f, r[2] ? 1.f : 0.f, r[3] ? 1.f : 0.f);
+  } else {
+    if (rel) rel[o] = r[0];
+    if (cert) cert[o] = r[0] ? 1.f : 0.f;  // image.load(pgm,1): byte/255 (fast_artistic_video.lua:103)
+  }
+}
+
+int launch_consistency(const float *f1u, const float *f1v, const float *f2u, const float *f2v, const float *structure,
+                       const float *avg_dev, float avg_host, uint8_t *rel, float *cert, int W, int H, cudaStream_t st) {
+  auto al = [](const void *p, int a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+  int vec = (W % 4 == 0 && al(f1u, 16) && al(f1v, 16) && (!rel || al(rel, 4)) && (!cert || al(cert, 16))) ? 4 : 1;
+  dim3 block(32, 8), grid(ceil_div(ceil_div(W, vec), 32), ceil_div(H, 8));
+  consistency_kernel<<<grid, block, 0, st>>>(f1u, f1v, f2u, f2v, structure, avg_dev, avg_host, rel, cert, W, H, vec);
+  return post_launch("checkConsistency");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// a-12 computeCorners (4-argument mode).  Stages:
+//   1. per-pixel structure tensor from 3-tap central differences with mirrored borders (fully parallel)
+//   2. Deriche-style IIR along X (one thread per row) then along Y (one thread per column, coalesced)
+//      for dxx, dyy, dxy -- the recurrences are sequential per line, as in the reference
+//   3. smallest eigenvalue (parallel)
+//   4. normalize(0,1) with the reference's `else if` min/max scan and the sequential fp32 avg: both are
+//      order-dependent in the reference, so they are evaluated in reference order by one thread
+//      (exactness over speed: this is a per-flow-pair preprocessing step, not the frame loop).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float deriv3(float m1, float c0, float p1) {
+  // sum over i=-1,0,1 of f[i]*v starting from 0 (CFilter.h:1510-1514): ((0 + -0.5*m1) + 0*c0) + 0.5*p1
+  float s = __fadd_rn(0.f, __fmul_rn(-0.5f, m1));
+  s = __fadd_rn(s, __fmul_rn(0.0f, c0));
+  s = __fadd_rn(s, __fmul_rn(0.5f, p1));
+  return s;
+}
+
+__global__ void __launch_bounds__(256) structure_tensor_kernel(const float *__restrict__ img, int Z, int W, int H,
+                                                               float *__restrict__ dxx, float *__restrict__ dyy,
+                                                               float *__restrict__ dxy) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  int64_t n = (int64_t)W * H, o = (int64_t)y * W + x;
+  // mirrored neighbours: x-1<0 -> -1-(x-1) = 0 ; x+1>=W -> 2W-1-(x+1) = W-1   (CFilter.h:1511-1512)
+  int xm = x - 1 < 0 ? 0 : x - 1, xp = x + 1 >= W ? W - 1 : x + 1;
+  int ym = y - 1 < 0 ? 0 : y - 1, yp = y + 1 >= H ? H - 1 : y + 1;
+  float sxx = 0.f, syy = 0.f, sxy = 0.f;
+  for (int k = 0; k < Z; ++k) {  // consistencyChecker.cpp:55-61
+    const float *p = img + k * n;
+    float c0 = __ldg(p + o);
+    float gx = deriv3(__ldg(p + (int64_t)y * W + xm), c0, __ldg(p + (int64_t)y * W + xp));
+    float gy = deriv3(__ldg(p + (int64_t)ym * W + x), c0, __ldg(p + (int64_t)yp * W + x));
+    sxx = __fadd_rn(sxx, __fmul_rn(gx, gx));
+    syy = __fadd_rn(syy, __fmul_rn(gy, gy));
+    sxy = __fadd_rn(sxy, __fmul_rn(gx, gy));
+  }
+  dxx[o] = sxx; dyy[o] = syy; dxy[o] = sxy;
+}
+
+struct IirC { float k, pm, pp, e2, te; };
+
+// one thread per line; `stride` between consecutive samples of the line, `pitch` between lines.
+// v1 scratch holds the causal pass (CFilter.h:1428-1431), the anti-causal pass (:1432-1435) is fused
+// with the final sum (:1436-1437).  3 matrices per launch via blockIdx.y.
+__global__ void __launch_bounds__(128) iir_kernel(float *__restrict__ m0, float *__restrict__ m1p,
+                                                  float *__restrict__ m2p, float *__restrict__ scratch, int n,
+                                                  int lines, int64_t stride, int64_t pitch, int64_t plane, IirC c) {
+  int line = blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= lines) return;
+  float *m = blockIdx.y == 0 ? m0 : (blockIdx.y == 1 ? m1p : m2p);
+  float *src = m + line * pitch;
+  float *v1 = scratch + blockIdx.y * plane + line * pitch;
+#define S(i) src[(int64_t)(i) * stride]
+#define V1(i) v1[(int64_t)(i) * stride]
+  const float k = c.k, pm = c.pm, pp = c.pp, e2 = c.e2, te = c.te;
+  float a0 = __fmul_rn(__fsub_rn(0.5f, __fmul_rn(k, pm)), S(0));
+  V1(0) = a0;
+  float s_prev = S(0), s_cur = S(1);
+  float a1 = __fadd_rn(__fmul_rn(k, __fadd_rn(s_cur, __fmul_rn(pm, s_prev))), __fmul_rn(__fsub_rn(te, e2), a0));
+  V1(1) = a1;
+  for (int x = 2; x < n; ++x) {
+    s_prev = s_cur;
+    s_cur = S(x);
+    float a = __fsub_rn(__fadd_rn(__fmul_rn(k, __fadd_rn(s_cur, __fmul_rn(pm, s_prev))), __fmul_rn(te, a1)),
+                        __fmul_rn(e2, a0));
+    V1(x) = a;
+    a0 = a1;
+    a1 = a;
+  }
+  // anti-causal
+  float sN1 = S(n - 1);
+  float b0 = __fmul_rn(__fadd_rn(0.5f, __fmul_rn(k, pm)), sN1);                        // v2[n-1]
+  float b1 = __fadd_rn(__fmul_rn(k, __fmul_rn(__fsub_rn(pp, e2), sN1)), __fmul_rn(__fsub_rn(te, e2), b0));  // v2[n-2]
+  float s_p1 = S(n - 2), s_p2 = sN1;  // S(x+1), S(x+2) for x = n-3
+  S(n - 1) = __fadd_rn(V1(n - 1), b0);
+  // S(n-2) is still needed as S(x+1) for x = n-3: it is cached in s_p1
+  S(n - 2) = __fadd_rn(V1(n - 2), b1);
+  for (int x = n - 3; x >= 0; --x) {
+    float sx = S(x);
+    float b = __fsub_rn(__fadd_rn(__fmul_rn(k, __fsub_rn(__fmul_rn(pp, s_p1), __fmul_rn(e2, s_p2))), __fmul_rn(te, b1)),
+                        __fmul_rn(e2, b0));
+    S(x) = __fadd_rn(V1(x), b);
+    s_p2 = s_p1;
+    s_p1 = sx;
+    b0 = b1;
+    b1 = b;
+  }
+#undef S
+#undef V1
+}
+
+__global__ void __launch_bounds__(256) eigen_kernel(const float *__restrict__ dxx, const float *__restrict__ dxy,
+                                                    const float *__restrict__ dyy, float *__restrict__ corners,
+                                                    int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = dxx[i], b = dxy[i], c = dyy[i];
+  float temp = (float)__dmul_rn(0.5, (double)__fadd_rn(a, c));  // :73  0.5*(a+c)
+  float temp2 = __fsub_rn(__fadd_rn(__fmul_rn(temp, temp), __fmul_rn(b, b)), __fmul_rn(a, c));
+  // :75-76  temp - sqrt(temp2): double sqrt, difference formed in double, rounded once (pinned to _ref)
+  corners[i] = (temp2 < 0.0f) ? 0.0f : (float)__dsub_rn((double)temp, __dsqrt_rn((double)temp2));
+}
+
+// reference-order scans (single thread): CMatrix.h:721-736 then CMatrix.h:1245-1251
+__global__ void normalize_scan_kernel(const float *__restrict__ m, int64_t n, float *__restrict__ minmax) {
+  float cmin = 30000.f, cmax = -30000.f;
+  for (int64_t i = 0; i < n; ++i) {
+    float v = m[i];
+    if (v > cmax) cmax = v;
+    else if (v < cmin) cmin = v;
+  }
+  float t = __fsub_rn(cmax, cmin);
+  if (t == 0.f) t = 1.f;
+  else t = __fdiv_rn(1.0f, t);
+  minmax[0] = cmin;
+  minmax[1] = t;
+}
+__global__ void __launch_bounds__(256) normalize_apply_kernel(float *__restrict__ m, int64_t n,
+                                                              const float *__restrict__ minmax) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = __fsub_rn(m[i], minmax[0]);
+  v = __fmul_rn(v, minmax[1]);
+  m[i] = __fadd_rn(v, 0.0f);
+}
+__global__ void avg_scan_kernel(const float *__restrict__ m, int64_t n, float *__restrict__ avg) {
+  float a = 0.f;
+  for (int64_t i = 0; i < n; ++i) a = __fadd_rn(a, m[i]);
+  *avg = __fdiv_rn(a, (float)(int)n);
+}
+
+}  // namespace fav
+
+using namespace fav;
+
+extern "C" {
+
+int fav_consistency_check(const float *flow1, const float *flow2, const float *structure, float structure_avg,
+                          uint8_t *reliable_u8, float *cert_f32, int W, int H, void *stream) {
+  FAV_REQUIRE(flow1 && flow2, "consistencyChecker: null flow");
+  FAV_REQUIRE(reliable_u8 || cert_f32, "consistencyChecker: no output tensor");
+  FAV_REQUIRE(W > 0 && H > 0, "consistencyChecker: empty flow");
+  FAV_TRY(require_device());
+  const int64_t HW = (int64_t)H * W;
+  return launch_consistency(flow1, flow1 + HW, flow2, flow2 + HW, structure, nullptr, structure_avg, reliable_u8,
+                            cert_f32, W, H, (cudaStream_t)stream);
+}
+
+size_t fav_compute_corners_workspace(int Z, int W, int H) {
+  (void)Z;
+  // dxx,dyy,dxy + 3 scratch planes + minmax
+  return (size_t)6 * W * H * sizeof(float) + 256;
+}
+
+int fav_compute_corners(const float *image, int Z, int W, int H, float rho, float *corners, float *avg_out,
+                        void *workspace, void *stream) {
+  FAV_REQUIRE(image && corners && workspace, "computeCorners: null tensor");
+  FAV_REQUIRE(Z > 0 && W >= 3 && H >= 3, "computeCorners: image too small");
+  FAV_TRY(require_device());
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t n = (int64_t)W * H;
+  float *dxx = (float *)workspace, *dyy = dxx + n, *dxy = dyy + n, *scr = dxy + n, *minmax = scr + 3 * n;
+  dim3 b2(32, 8), g2(ceil_div(W, 32), ceil_div(H, 8));
+  structure_tensor_kernel<<<g2, b2, 0, st>>>(image, Z, W, H, dxx, dyy, dxy);
+  FAV_TRY(post_launch("computeCorners.structure"));
+  // coefficients exactly as CFilter.h:1420-1426 (double expressions rounded to float)
+  IirC c;
+  float alpha = (float)(2.5 / (sqrt(3.1415926535897932384626433832795) * (double)rho));
+  float e = (float)exp(-(double)alpha);
+  c.e2 = e * e;
+  c.te = (float)(2.0 * (double)e);
+  c.k = (float)((1.0 - (double)e) * (1.0 - (double)e) / (1.0 + 2.0 * (double)alpha * (double)e - (double)c.e2));
+  c.pm = (float)((double)e * ((double)alpha - 1.0));
+  c.pp = (float)((double)e * ((double)alpha + 1.0));
+  // X: one thread per row (stride 1, pitch W); Y: one thread per column (stride W, pitch 1)
+  iir_kernel<<<dim3(ceil_div(H, 128), 3), 128, 0, st>>>(dxx, dyy, dxy, scr, W, H, 1, W, n, c);
+  FAV_TRY(post_launch("computeCorners.iirX"));
+  iir_kernel<<<dim3(ceil_div(W, 128), 3), 128, 0, st>>>(dxx, dyy, dxy, scr, H, W, W, 1, n, c);
+  FAV_TRY(post_launch("computeCorners.iirY"));
+  eigen_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(dxx, dxy, dyy, corners, n);
+  FAV_TRY(post_launch("computeCorners.eigen"));
+  normalize_scan_kernel<<<1, 1, 0, st>>>(corners, n, minmax);
+  FAV_TRY(post_launch("normalize.scan"));
+  normalize_apply_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(corners, n, minmax);
+  FAV_TRY(post_launch("normalize.apply"));
+  if (avg_out) {
+    avg_scan_kernel<<<1, 1, 0, st>>>(corners, n, avg_out);
+    FAV_TRY(post_launch("avg.scan"));
+  }
+  return FAV_OK;
+}
+}

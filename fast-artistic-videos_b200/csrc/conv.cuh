@@ -1,0 +1,84 @@
+// conv.cuh -- job descriptors shared by the host planner (net.cu) and the convolution kernels.
+#pragma once
+#include "net_layout.cuh"
+
+namespace fav {
+
+constexpr int kMaxTaps = 81;
+constexpr int kMaxSteps = 168;
+constexpr int kMaxRows = 9;
+constexpr int kMaxGroups = 8;
+constexpr int kTileM = 128;  // output pixels per MMA tile = TMEM lanes
+
+// One K=16 step of the implicit GEMM: two K8 "units" (a unit = 8 input channels of one filter tap).
+// a_off16: offset (16-byte units) of the first unit's pixel 0 inside the shared-memory patch stage;
+// lbo16:   distance between the two units (= patch slab pitch when they are adjacent channel blocks,
+//          1 when they are horizontally adjacent taps of an 8-channel input).
+struct KStep {
+  uint16_t a_off16;
+  uint16_t lbo16;
+};
+
+// tcgen05 implicit-GEMM job (one convolution, or one sub-pixel phase of a transposed convolution)
+struct ConvJob {
+  // input operand (hi/lo fp16 planes), addressed in 16-byte units
+  const uint4 *a_hi, *a_lo;
+  int a_Cb, a_slab16;
+  // output grid of this job and its tiling (one tile = 128 consecutive pixels of one output row)
+  int Ho, Wo, tiles_x, ntiles;
+  // patch geometry: storage row of patch row ri in group g for output row y: row_mul*y + grp_row[g][ri]
+  int row_mul;
+  int nseg, seg_src16[2], seg_len16[2], seg_dst16[2];  // bulk-copy segments per (row, cb): src + x0
+  int ngroups, nrows, CbG;
+  int grp_cb0[kMaxGroups];
+  int grp_row[kMaxGroups][kMaxRows];
+  int pslab16;   // patch slab pitch (16-byte units) per (row, cb)
+  int stage16;   // one A stage (hi or lo) in 16-byte units
+  int nchunks, spc;  // weight chunks per group, K16 steps per chunk
+  KStep steps[kMaxSteps];
+  const uint4 *b;  // packed weights: [group][chunk][hi|lo][step][k8 half][Npad] x 16 B
+  int chunk16;     // 2 * spc * 2 * Npad
+  int Npad, Cout;
+  const float *bias;
+  // output placement: raw(y*oy_mul + oy_off, x*ox_mul + ox_off)
+  float *raw;
+  int raw_Cq, raw_Wp;
+  int oy_mul, oy_off, ox_mul, ox_off;
+  // final layer: Tanh -> MulConstant(tanh_c) [-> deprocess] written as fp32 NCHW [3][outH][outW]
+  int final_mode;  // 0 = raw, 1 = net space, 2 = fused vgg.deprocess
+  float *out3;
+  float tanh_c;
+};
+
+// CUDA-core comparator job (debug / bring-up path; same inputs and outputs as ConvJob)
+struct SimtJob {
+  Operand in;
+  int sy, sx;  // input stride
+  int ntaps;
+  int8_t tdy[kMaxTaps], tdx[kMaxTaps];
+  const float *w;  // [tap][Cin_pad][Cout_pad8] fp32
+  int Cin_pad, Cout, Cout_pad8;
+  const float *bias;
+  int Ho, Wo;
+  float *raw;
+  int raw_Cq, raw_Wp;
+  int oy_mul, oy_off, ox_mul, ox_off;
+  int final_mode;
+  float *out3;
+  float tanh_c;
+};
+
+int launch_conv_tc(const ConvJob &job, int num_sms, cudaStream_t st);
+int launch_conv_simt(const SimtJob &job, cudaStream_t st);
+size_t conv_tc_smem_bytes(const ConvJob &job);
+
+// elementwise / reduction kernels of the net (net_kernels.cu)
+int launch_pack_input(const float *in, int Cin, int H, int W, int reflect, const Operand &dst, cudaStream_t st);
+int launch_in_stats(const RawTensor &raw, double *sums /*[2*C]*/, cudaStream_t st);
+int launch_in_finalize(const double *sums, const float *gamma, const float *beta, int C, int64_t count, float eps,
+                       float *mean_scale_beta /*[3*C]*/, cudaStream_t st);
+int launch_in_apply(const RawTensor &raw, const float *mean_scale_beta, int relu, const Operand *skip, int shave,
+                    const Operand &dst, cudaStream_t st);
+int launch_unpack_operand(const Operand &src, float *out_nchw, cudaStream_t st);
+
+}  // namespace fav

@@ -1,0 +1,282 @@
+// conv_plan.hpp -- host-only planning of the tcgen05 implicit-GEMM convolution: filter-tap tables, K-step
+// tables, weight packing and operand geometry.  Pure functions without CUDA runtime calls so that the same
+// code is exercised on the CPU by tests/emu (an emulation of the kernel's addressing) and on the GPU by net.cu.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "conv.cuh"
+
+namespace fav {
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct Unit {  // one K8 unit of a K16 step: filter tap index (or -1 = zero weights) and input channel block
+  int tap, cb;
+};
+
+struct ConvPhase {
+  std::vector<ConvTap> taps;
+  int oy_off = 0, ox_off = 0;
+  // tcgen05 tables (size independent)
+  int kind = 0;  // 0: stride-1 input, Cin_pad >= 16; 1: Cin_pad == 8 (tap pairing); 2: stride-2 parity-split input
+  int dxmin = 0, dxmax = 0;
+  std::vector<int> rows;  // distinct dy, ascending
+  int nrg = 1, nchg = 1, CbG = 1, rows_per_group = 1;
+  int pslab16 = 0, nseg = 1, seg_len16[2] = {0, 0}, seg_dst16[2] = {0, 0};
+  int nchunks = 1, spc = 1;
+  std::vector<KStep> steps;                    // per group
+  std::vector<std::vector<Unit>> units;        // [group][step*2 + u]
+  float *d_w_simt = nullptr;
+  uint4 *d_b_tc = nullptr;
+};
+
+struct ConvDef {
+  std::string name;
+  int cin = 0, cout = 0, k = 0, stride = 1, pad = 0, adj = 0;
+  bool transposed = false;
+  int cin_pad = 0, Cb = 0, Npad = 0, cout_pad8 = 0;
+  int in_stride = 1;  // stride of the input sampling grid (2 for 'd' layers)
+  int out_mul = 1;    // 2 for transposed stride-2 (sub-pixel phases)
+  std::vector<ConvPhase> phases;
+  float *d_bias = nullptr;
+  int pw = -1, pb = -1;  // param indices
+};
+
+// ---- tcgen05 tables for one phase -------------------------------------------------------------------------
+static constexpr int kStageCapBytes = 56 * 1024;  // one A stage (hi + lo)
+static constexpr int kChunkCapBytes = 24 * 1024;
+
+static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
+  ph.rows.clear();
+  ph.dxmin = 1 << 30; ph.dxmax = -(1 << 30);
+  for (auto &t : ph.taps) {
+    if (std::find(ph.rows.begin(), ph.rows.end(), t.dy) == ph.rows.end()) ph.rows.push_back(t.dy);
+    ph.dxmin = std::min(ph.dxmin, t.dx); ph.dxmax = std::max(ph.dxmax, t.dx);
+  }
+  std::sort(ph.rows.begin(), ph.rows.end());
+  std::vector<int> dxs;
+  for (int dx = ph.dxmin; dx <= ph.dxmax; ++dx) dxs.push_back(dx);
+  auto tap_index = [&](int dy, int dx) {
+    for (size_t i = 0; i < ph.taps.size(); ++i)
+      if (ph.taps[i].dy == dy && ph.taps[i].dx == dx) return (int)i;
+    return -1;
+  };
+  const int nrows = (int)ph.rows.size();
+  if (c.in_stride == 2) {
+    if (!(c.k == 3 && c.pad == 1 && c.Cb >= 2 && c.Cb % 2 == 0)) {
+      set_error("conv %s: stride-2 tcgen05 path needs k=3, pad=1, Cin%%16==0", c.name.c_str());
+      return FAV_ERR_UNSUPPORTED;
+    }
+    ph.kind = 2; ph.CbG = 2; ph.nchg = c.Cb / 2; ph.nrg = 1; ph.rows_per_group = nrows;
+    ph.nseg = 2; ph.seg_len16[0] = kTileM + 1; ph.seg_dst16[0] = 0; ph.seg_len16[1] = kTileM; ph.seg_dst16[1] = kTileM + 1;
+    ph.pslab16 = 2 * kTileM + 1;
+  } else if (c.cin_pad == 8) {
+    ph.kind = 1; ph.CbG = 1; ph.nchg = 1; ph.nrg = 1; ph.rows_per_group = nrows;
+    int ntx = (int)dxs.size(), ntx_pad = round_up(ntx, 2);
+    ph.nseg = 1; ph.pslab16 = kTileM + ntx_pad; ph.seg_len16[0] = ph.pslab16; ph.seg_dst16[0] = 0;
+  } else {
+    if (c.Cb % 2) {
+      set_error("conv %s: Cin must be 8 or a multiple of 16 for the tcgen05 path", c.name.c_str());
+      return FAV_ERR_UNSUPPORTED;
+    }
+    ph.kind = 0; ph.CbG = (c.Cb % 4 == 0) ? 4 : 2; ph.nchg = c.Cb / ph.CbG;
+    ph.nseg = 1; ph.pslab16 = kTileM + (ph.dxmax - ph.dxmin); ph.seg_len16[0] = ph.pslab16; ph.seg_dst16[0] = 0;
+    ph.nrg = 0;
+    for (int rg = 1; rg <= nrows; ++rg) {
+      if (nrows % rg) continue;
+      if ((nrows / rg) * ph.CbG * ph.pslab16 * 32 <= kStageCapBytes) { ph.nrg = rg; break; }
+    }
+    if (!ph.nrg) { set_error("conv %s: patch stage too large", c.name.c_str()); return FAV_ERR_UNSUPPORTED; }
+    ph.rows_per_group = nrows / ph.nrg;
+  }
+  if (ph.rows_per_group * ph.CbG * ph.pslab16 * 32 > kStageCapBytes || ph.rows_per_group > kMaxRows ||
+      ph.nrg * ph.nchg > kMaxGroups) {
+    set_error("conv %s: tcgen05 tiling limits exceeded", c.name.c_str());
+    return FAV_ERR_UNSUPPORTED;
+  }
+  // steps of one group (identical for every group) + per-group unit lists
+  ph.steps.clear();
+  const int ngroups = ph.nrg * ph.nchg;
+  ph.units.assign(ngroups, {});
+  for (int ri = 0; ri < ph.rows_per_group; ++ri) {
+    if (ph.kind == 1) {
+      for (int p = 0; p * 2 < (int)dxs.size(); ++p) {
+        ph.steps.push_back(KStep{(uint16_t)(ri * ph.pslab16 + 2 * p), 1});
+        for (int g = 0; g < ngroups; ++g)
+          for (int u = 0; u < 2; ++u) {
+            int di = 2 * p + u;
+            int tap = di < (int)dxs.size() ? tap_index(ph.rows[ri], dxs[di]) : -1;
+            ph.units[g].push_back(Unit{tap, 0});
+          }
+      }
+    } else {
+      for (int dx : dxs) {
+        int xoff = ph.kind == 2 ? (dx == -1 ? 0 : (dx == 0 ? kTileM + 1 : 1)) : dx - ph.dxmin;
+        for (int j = 0; j < ph.CbG / 2; ++j) {
+          ph.steps.push_back(KStep{(uint16_t)((ri * ph.CbG + 2 * j) * ph.pslab16 + xoff), (uint16_t)ph.pslab16});
+          for (int chg = 0; chg < ph.nchg; ++chg)
+            for (int rg = 0; rg < ph.nrg; ++rg) {
+              int g = chg * ph.nrg + rg;
+              int tap = tap_index(ph.rows[rg * ph.rows_per_group + ri], dx);
+              for (int u = 0; u < 2; ++u) ph.units[g].push_back(Unit{tap, chg * ph.CbG + 2 * j + u});
+            }
+        }
+      }
+    }
+  }
+  const int spg = (int)ph.steps.size();
+  if (spg > kMaxSteps) { set_error("conv %s: too many K steps", c.name.c_str()); return FAV_ERR_UNSUPPORTED; }
+  const int step_bytes = 2 * 2 * c.Npad * 16;
+  ph.spc = 1;
+  for (int d = 1; d <= spg; ++d)
+    if (spg % d == 0 && d * step_bytes <= kChunkCapBytes) ph.spc = d;
+  ph.nchunks = spg / ph.spc;
+  return FAV_OK;
+}
+
+static inline uint16_t f2h_bits(float f) {
+  __half h = __float2half_rn(f);
+  uint16_t b;
+  memcpy(&b, &h, 2);
+  return b;
+}
+static inline float h2f_bits(uint16_t b) {
+  __half h;
+  memcpy(&h, &b, 2);
+  return __half2float(h);
+}
+
+static inline float weight_at(const ConvDef &c, const std::vector<float> &w, int co, int ci, int ky, int kx) {
+  if (co >= c.cout || ci >= c.cin) return 0.f;
+  if (c.transposed) return w[(((int64_t)ci * c.cout + co) * c.k + ky) * c.k + kx];
+  return w[(((int64_t)co * c.cin + ci) * c.k + ky) * c.k + kx];
+}
+
+
+// taps of a plain convolution / the 4 sub-pixel phases of a stride-2 transposed convolution
+static inline void build_phases(ConvDef &c) {
+  c.phases.clear();
+  if (!c.transposed) {
+    ConvPhase ph;
+    for (int ky = 0; ky < c.k; ++ky)
+      for (int kx = 0; kx < c.k; ++kx) ph.taps.push_back(ConvTap{ky - c.pad, kx - c.pad, ky, kx});
+    c.phases.push_back(std::move(ph));
+  } else {
+    // out[2y+a, 2x+b]:  oy = 2*iy - pad + ky  =>  2*iy = 2*y + (a + pad - ky)
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        ConvPhase ph;
+        ph.oy_off = a; ph.ox_off = b;
+        for (int ky = 0; ky < c.k; ++ky) {
+          int ny = a + c.pad - ky;
+          if (ny % 2) continue;
+          for (int kx = 0; kx < c.k; ++kx) {
+            int nx = b + c.pad - kx;
+            if (nx % 2) continue;
+            ph.taps.push_back(ConvTap{ny / 2, nx / 2, ky, kx});
+          }
+        }
+        c.phases.push_back(std::move(ph));
+      }
+  }
+}
+
+static inline void init_conv_def(ConvDef &c, const std::string &name, int cin, int cout, int k, int stride, int pad,
+                                 bool tr, int adj) {
+  c.name = name; c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; c.pad = pad; c.transposed = tr; c.adj = adj;
+  c.cin_pad = round_up(cin, 8);
+  c.Cb = c.cin_pad / 8;
+  c.Npad = std::max(16, round_up(cout, 16));
+  c.cout_pad8 = round_up(cout, 8);
+  c.in_stride = (!tr && stride == 2) ? 2 : 1;
+  c.out_mul = (tr && stride == 2) ? 2 : 1;
+}
+
+// packed tcgen05 weights of one phase: [group][chunk][hi|lo][step][k8 half][Npad][8] fp16 (as uint16 bit patterns)
+static inline std::vector<uint16_t> pack_phase_weights(const ConvDef &c, const ConvPhase &ph, const std::vector<float> &w) {
+  const int ngroups = ph.nrg * ph.nchg, spg = (int)ph.steps.size();
+  std::vector<uint16_t> pk((size_t)ngroups * spg * 2 * 2 * c.Npad * 8, 0);
+  for (int g = 0; g < ngroups; ++g)
+    for (int ch = 0; ch < ph.nchunks; ++ch)
+      for (int part = 0; part < 2; ++part)
+        for (int st = 0; st < ph.spc; ++st)
+          for (int u = 0; u < 2; ++u) {
+            const Unit un = ph.units[g][(ch * ph.spc + st) * 2 + u];
+            size_t base = (((((size_t)g * ph.nchunks + ch) * 2 + part) * ph.spc + st) * 2 + u) * c.Npad * 8;
+            if (un.tap < 0) continue;
+            for (int n = 0; n < c.Npad; ++n)
+              for (int i = 0; i < 8; ++i) {
+                float v = weight_at(c, w, n, un.cb * 8 + i, ph.taps[un.tap].ky, ph.taps[un.tap].kx);
+                uint16_t hb = f2h_bits(v);
+                pk[base + (size_t)n * 8 + i] = part == 0 ? hb : f2h_bits(v - h2f_bits(hb));
+              }
+          }
+  return pk;
+}
+
+// geometry of the operand feeding convolution `consumer` (pointers left null)
+static inline Operand operand_geometry(int C, int H, int W, const ConvDef *consumer) {
+  Operand o;
+  o.C = C; o.Cb = round_up(C, 8) / 8; o.H = H; o.W = W;
+  int pad = consumer ? consumer->pad : 0;
+  if (consumer && consumer->transposed) pad = 0;
+  o.padT = o.padL = pad;
+  o.Hs = H + 2 * pad + 2;
+  o.parity = (consumer && consumer->in_stride == 2) ? 1 : 0;
+  o.Ws = pad + round_up(W, kTileM) + pad + 16;
+  if (o.parity) o.Ws2 = round_up((W + 2 * pad + 1) / 2, kTileM) + 8;
+  o.elems16 = (size_t)o.Hs * o.Cb * o.slab16() + 512;
+  return o;
+}
+
+static inline void conv_out_size(const ConvDef &c, int H, int W, int *Ho, int *Wo) {
+  if (c.transposed) {
+    *Ho = (H - 1) * c.stride - 2 * c.pad + c.k + c.adj;
+    *Wo = (W - 1) * c.stride - 2 * c.pad + c.k + c.adj;
+  } else {
+    *Ho = (H + 2 * c.pad - c.k) / c.stride + 1;
+    *Wo = (W + 2 * c.pad - c.k) / c.stride + 1;
+  }
+}
+
+// the device job of one phase (weights / bias / raw pointers filled by the caller)
+static inline int fill_conv_job(const ConvDef &c, const ConvPhase &ph, const Operand &in, ConvJob &j) {
+  int Ho, Wo;
+  conv_out_size(c, in.H, in.W, &Ho, &Wo);
+  const int pHo = c.transposed ? in.H : Ho, pWo = c.transposed ? in.W : Wo;  // phase grid
+  memset(&j, 0, sizeof(j));
+  j.a_hi = reinterpret_cast<const uint4 *>(in.hi); j.a_lo = reinterpret_cast<const uint4 *>(in.lo);
+  j.a_Cb = in.Cb; j.a_slab16 = in.slab16();
+  j.Ho = pHo; j.Wo = pWo; j.tiles_x = ceil_div(pWo, kTileM); j.ntiles = j.tiles_x * pHo;
+  j.row_mul = c.in_stride;
+  j.nseg = ph.nseg;
+  for (int s = 0; s < ph.nseg; ++s) { j.seg_len16[s] = ph.seg_len16[s]; j.seg_dst16[s] = ph.seg_dst16[s]; }
+  if (ph.kind == 2) { j.seg_src16[0] = 0; j.seg_src16[1] = in.Ws2; }
+  else j.seg_src16[0] = in.padL + ph.dxmin;
+  j.ngroups = ph.nrg * ph.nchg; j.nrows = ph.rows_per_group; j.CbG = ph.CbG;
+  for (int chg = 0; chg < ph.nchg; ++chg)
+    for (int rg = 0; rg < ph.nrg; ++rg) {
+      int g = chg * ph.nrg + rg;
+      j.grp_cb0[g] = chg * ph.CbG;
+      for (int ri = 0; ri < ph.rows_per_group; ++ri) j.grp_row[g][ri] = in.padT + ph.rows[rg * ph.rows_per_group + ri];
+    }
+  j.pslab16 = ph.pslab16; j.stage16 = ph.rows_per_group * ph.CbG * ph.pslab16;
+  j.nchunks = ph.nchunks; j.spc = ph.spc;
+  for (size_t i = 0; i < ph.steps.size(); ++i) j.steps[i] = ph.steps[i];
+  j.chunk16 = 2 * ph.spc * 2 * c.Npad; j.Npad = c.Npad; j.Cout = c.cout;
+  j.oy_mul = c.out_mul; j.ox_mul = c.out_mul; j.oy_off = ph.oy_off; j.ox_off = ph.ox_off;
+  // every bulk copy must stay inside the operand allocation
+  int64_t max_row = (int64_t)j.row_mul * (pHo - 1) + in.padT + ph.rows.back();
+  int64_t last16 = ((max_row * in.Cb + in.Cb - 1) * (int64_t)in.slab16()) + j.seg_src16[ph.nseg - 1] +
+                   (int64_t)(j.tiles_x - 1) * kTileM + j.seg_len16[ph.nseg - 1];
+  if (max_row >= in.Hs || last16 > (int64_t)in.elems16) {
+    set_error("conv %s: internal operand bounds error", c.name.c_str());
+    return FAV_ERR_INVALID;
+  }
+  return FAV_OK;
+}
+
+}  // namespace fav

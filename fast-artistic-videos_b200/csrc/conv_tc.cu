@@ -1,0 +1,303 @@
+// conv_tc.cu -- the hot kernel: implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+// Replaces the cuDNN / THNN SpatialConvolution + SpatialFullConvolution calls of the reference net
+// (fast_artistic_video/models_video.lua:80,93,102; fast_artistic_video_core.lua:48-55).
+//
+// GEMM view (per job):  D[128 pixels, Npad couts] += A[128 pixels, K] * B[Npad, K]^T,
+//   K = taps x input channels, walked in K=16 steps (two 8-channel "units" per step).
+// Precision: the reference computes in fp32.  A single fp16/tf32 pass misses the 1e-3 parity bar
+// (measured 1.2e-3..2.7e-3), so every operand is an fp16 pair x = hi + lo and each
+// K step issues three MMAs  hi*hi + lo*hi + hi*lo  (fp32 accumulation in TMEM): ~2^-21 relative error at
+// 1.5x the cost of one TF32 pass.
+//
+// Data movement: the input patch of a tile (all filter rows x a group of channel blocks x 128+halo pixels)
+// is fetched ONCE per tile by 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP, completion on an
+// mbarrier).  Because the operand layout in HBM is already the canonical no-swizzle K-major core-matrix
+// layout (net_layout.cuh), every filter tap reuses the same shared-memory patch: the UMMA matrix descriptor
+// just starts 16 B * dx further.  Weights stream through a ring of pre-packed chunks.
+//
+// Warp roles (224 threads, 1 CTA / SM, persistent over tiles):
+//   warps 0-3  epilogue: tcgen05.ld TMEM -> registers -> +bias -> float4 stores (or tanh/deprocess, last layer)
+//   warp  4    A producer (bulk copies of the patch, all lanes issue)
+//   warp  5    B producer (bulk copies of weight chunks)
+//   warp  6    TMEM allocator + single-thread MMA issuer
+// Pipelines: A stages (kNA) and B slots (kNB) with full/empty mbarriers; TMEM accumulator double-buffered so
+// the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "conv.cuh"
+
+namespace fav {
+
+constexpr int kNA = 2;
+constexpr int kNB = 4;
+constexpr int kTmemCols = 256;
+constexpr int kThreads = 224;
+
+struct __align__(16) TcShared {
+  uint64_t a_full[kNA], a_empty[kNA], b_full[kNB], b_empty[kNB], t_full[2], t_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad_;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && (spin & 255u) == 255u) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();  // ~2 s at 2 GHz
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, no swizzle: canonical layout ((8,m),(8 elems,2)) : ((16 B, SBO), (2 B, LBO))   [cute/atom/mma_traits_sm100.hpp]
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo16, uint32_t sbo16) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16) |
+         ((uint64_t)(sbo16 & 0x3FFF) << 32) | (1ull << 46) /* descriptor version: Blackwell */;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float tc_final_value(float v, int k, int mode, float tanh_c) {
+  float t = tanhf(v) * tanh_c;  // nn.Tanh -> nn.MulConstant(150) (models_video.lua:135-136)
+  if (mode == 2) {              // fused vgg.deprocess (preprocess.lua:70)
+    const float mean[3] = {FAV_MEAN_B, FAV_MEAN_G, FAV_MEAN_R};
+    t = __fdiv_rn(__fadd_rn(t, mean[k]), 255.0f);
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvJob job) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t a_stage_bytes = (uint32_t)job.stage16 * 16u;  // one of hi / lo
+  const uint32_t chunk_bytes = (uint32_t)job.chunk16 * 16u;
+  uint8_t *a_base = smem;                                   // stage s: hi | lo
+  uint8_t *b_base = a_base + kNA * 2 * a_stage_bytes;       // slot s: [hi steps][lo steps]
+  TcShared *sh = reinterpret_cast<TcShared *>(b_base + kNB * chunk_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNA; ++i) { mbar_init(&sh->a_full[i], 1); mbar_init(&sh->a_empty[i], 1); }
+    for (int i = 0; i < kNB; ++i) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], 1); mbar_init(&sh->t_empty[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 6) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  const int ngroups = job.ngroups, nchunks = job.nchunks, spc = job.spc, Npad = job.Npad;
+
+  if (warp == 4) {
+    // ===== A producer: the input patch of each (tile, channel group) =====
+    const int per_row = job.CbG * job.nseg * 2;  // copies per patch row (x2: hi, lo)
+    const int ncopies = job.nrows * per_row;
+    uint32_t stage_tx = 0;
+    for (int s = 0; s < job.nseg; ++s) stage_tx += (uint32_t)job.seg_len16[s] * 16u;
+    stage_tx *= (uint32_t)(job.nrows * job.CbG * 2);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
+      const int y = tile / job.tiles_x, x0 = (tile - y * job.tiles_x) * kTileM;
+      for (int g = 0; g < ngroups; ++g, ++it) {
+        const uint32_t s = it % kNA, ph = (it / kNA) & 1;
+        mbar_wait(&sh->a_empty[s], ph ^ 1);
+        if (lane == 0) mbar_arrive_expect_tx(&sh->a_full[s], stage_tx);
+        __syncwarp();
+        uint8_t *stage = a_base + s * 2 * a_stage_bytes;
+        for (int c = lane; c < ncopies; c += 32) {
+          int ri = c / per_row, r = c - ri * per_row;
+          int cbi = r / (job.nseg * 2);
+          r -= cbi * job.nseg * 2;
+          int seg = r >> 1, part = r & 1;
+          int64_t src16 = ((int64_t)(job.row_mul * y + job.grp_row[g][ri]) * job.a_Cb + job.grp_cb0[g] + cbi) *
+                              job.a_slab16 + job.seg_src16[seg] + x0;
+          const uint4 *src = (part ? job.a_lo : job.a_hi) + src16;
+          uint8_t *dst = stage + part * a_stage_bytes +
+                         (uint32_t)((ri * job.CbG + cbi) * job.pslab16 + job.seg_dst16[seg]) * 16u;
+          bulk_g2s(dst, src, (uint32_t)job.seg_len16[seg] * 16u, &sh->a_full[s]);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===== B producer: weight chunks =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x)
+        for (int g = 0; g < ngroups; ++g)
+          for (int c = 0; c < nchunks; ++c, ++it) {
+            const uint32_t s = it % kNB, ph = (it / kNB) & 1;
+            mbar_wait(&sh->b_empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&sh->b_full[s], chunk_bytes);
+            bulk_g2s(b_base + s * chunk_bytes, job.b + (int64_t)(g * nchunks + c) * job.chunk16, chunk_bytes,
+                     &sh->b_full[s]);
+          }
+    }
+    __syncwarp();
+  } else if (warp == 6) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      uint32_t ita = 0, itb = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x, ++tl) {
+        const uint32_t as = tl & 1, tph = (tl >> 1) & 1;
+        mbar_wait(&sh->t_empty[as], tph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 128u;
+        uint32_t accumulate = 0;
+        for (int g = 0; g < ngroups; ++g, ++ita) {
+          const uint32_t sa = ita % kNA;
+          mbar_wait(&sh->a_full[sa], (ita / kNA) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(a_base + sa * 2 * a_stage_bytes), a_lo = a_hi + a_stage_bytes;
+          for (int c = 0; c < nchunks; ++c, ++itb) {
+            const uint32_t sb = itb % kNB;
+            mbar_wait(&sh->b_full[sb], (itb / kNB) & 1);
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(b_base + sb * chunk_bytes);
+            const uint32_t b_lo = b_hi + (uint32_t)spc * 2u * (uint32_t)Npad * 16u;
+            for (int st = 0; st < spc; ++st) {
+              const KStep ks = job.steps[c * spc + st];
+              const uint32_t aoff = (uint32_t)ks.a_off16 * 16u, boff = (uint32_t)st * 2u * (uint32_t)Npad * 16u;
+              const uint64_t ad_hi = make_desc(a_hi + aoff, ks.lbo16, 8), ad_lo = make_desc(a_lo + aoff, ks.lbo16, 8);
+              const uint64_t bd_hi = make_desc(b_hi + boff, Npad, 8), bd_lo = make_desc(b_lo + boff, Npad, 8);
+              tc_mma_f16(d_tmem, ad_hi, bd_hi, idesc, accumulate);
+              accumulate = 1;
+              tc_mma_f16(d_tmem, ad_lo, bd_hi, idesc, 1);
+              tc_mma_f16(d_tmem, ad_hi, bd_lo, idesc, 1);
+            }
+            tc_commit(&sh->b_empty[sb]);  // frees the weight slot when the MMAs above retire
+          }
+          tc_commit(&sh->a_empty[sa]);  // frees the patch stage
+        }
+        tc_commit(&sh->t_full[as]);  // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps 0..3: TMEM lane = pixel =====
+    uint32_t tl = 0;
+    const int px = warp * 32 + lane;
+    for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x, ++tl) {
+      const int y = tile / job.tiles_x, x = (tile - y * job.tiles_x) * kTileM + px;
+      const uint32_t as = tl & 1, tph = (tl >> 1) & 1;
+      mbar_wait(&sh->t_full[as], tph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 128u;
+      const int yo = y * job.oy_mul + job.oy_off, xo = x * job.ox_mul + job.ox_off;
+      const bool valid = x < job.Wo;
+      for (int c0 = 0; c0 < Npad; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)c0, r);
+        if (job.final_mode == 0) {
+          if (valid) {
+            float4 *rp = reinterpret_cast<float4 *>(job.raw) + (((int64_t)yo * job.raw_Cq + (c0 >> 2)) * job.raw_Wp + xo);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (c0 + 4 * q < job.Cout) {
+                const float4 bq = __ldg(reinterpret_cast<const float4 *>(job.bias + c0) + q);
+                rp[(int64_t)q * job.raw_Wp] =
+                    make_float4(__uint_as_float(r[4 * q]) + bq.x, __uint_as_float(r[4 * q + 1]) + bq.y,
+                                __uint_as_float(r[4 * q + 2]) + bq.z, __uint_as_float(r[4 * q + 3]) + bq.w);
+              }
+            }
+          }
+        } else if (c0 == 0 && valid) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (k < job.Cout)
+              job.out3[((int64_t)k * job.Ho + yo) * job.Wo + xo] =
+                  tc_final_value(__uint_as_float(r[k]) + __ldg(job.bias + k), k, job.final_mode, job.tanh_c);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sh->t_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 6) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
+                 : "memory");
+  }
+}
+
+size_t conv_tc_smem_bytes(const ConvJob &job) {
+  return (size_t)kNA * 2 * job.stage16 * 16 + (size_t)kNB * job.chunk16 * 16 + sizeof(TcShared) + 128;
+}
+
+int launch_conv_tc(const ConvJob &job, int num_sms, cudaStream_t st) {
+  size_t smem = conv_tc_smem_bytes(job);
+  if (smem > 227 * 1024) {
+    set_error("conv_tc: shared memory %zu exceeds 227 KB", smem);
+    return FAV_ERR_UNSUPPORTED;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    FAV_TRY(check_cuda(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                       "cudaFuncSetAttribute(conv_tc)"));
+    attr_set = true;
+  }
+  int grid = job.ntiles < num_sms ? job.ntiles : num_sms;
+  conv_tc_kernel<<<grid, kThreads, smem, st>>>(job);
+  return post_launch("conv_tc");
+}
+
+}  // namespace fav

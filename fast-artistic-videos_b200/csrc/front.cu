@@ -1,0 +1,415 @@
+// front.cu -- the temporal-consistency front end (all HBM-bound, fp32, bit-exact vs oracle/fav_oracle.c):
+//   a-1  nn.BilinearSamplerBDHW forward           stnbdhw/BilinearSamplerBDHW.cu:48-152
+//   a-2  utils.warp_image                         fast_artistic_video/utils.lua:141-149
+//   a-5  utils.min_filter                         fast_artistic_video/utils.lua:161-169
+//   a-6  vgg preprocess / deprocess               fast_artistic_video/preprocess.lua:48-71
+//   a-8  fused 7-channel temporal input           fast_artistic_video_core.lua:161-171
+//   a-9  first-frame input                        fast_artistic_video_core.lua:133-137
+//
+// Design (B200): one thread owns VEC (=4) consecutive output pixels of one row so that the flow,
+// cert and content reads and all stores are 16-byte vector accesses, fully coalesced (the reference
+// kernel maps lanes to x-stride-16 addresses and re-reads the flow once per channel).  The 4
+// bilinear taps are scalar read-only loads; for real optical flow neighbouring lanes gather
+// neighbouring addresses, so they coalesce in L1/L2 and each source sector is fetched from HBM once.
+// All arithmetic uses explicit round-to-nearest intrinsics in the reference's evaluation order (no
+// FMA contraction), which makes the output bit-identical to the CPU restatement.
+#include "fav_common.cuh"
+
+namespace fav {
+
+// ---- shared per-pixel sampling ------------------------------------------------------------------
+struct Sample {
+  int x0, y0;
+  float wx, wy;     // weights of the top-left corner (BilinearSamplerBDHW.cu:21-22)
+  bool tl, tr, bl, br;
+  bool off;         // PAD_PIXEL mode: whole pixel takes the pad value
+  int x1, y1;       // PAD_PIXEL mode: clamped neighbours
+};
+
+__device__ __forceinline__ Sample make_sample(float dy, float dx, int yOut, int xOut, int H, int W,
+                                              int border_mode) {
+  Sample s;
+  float yf = __fadd_rn(dy, (float)yOut);  // BilinearSamplerBDHW.cu:72
+  float xf = __fadd_rn(dx, (float)xOut);  // :73
+  float fy = floorf(yf), fx = floorf(xf);
+  s.y0 = (int)fy;
+  s.x0 = (int)fx;
+  if (border_mode == FAV_BORDER_PER_TAP) {
+    s.wx = __fsub_rn(1.0f, __fsub_rn(xf, (float)s.x0));  // :22
+    s.wy = __fsub_rn(1.0f, __fsub_rn(yf, (float)s.y0));
+    bool xin0 = s.x0 >= 0 && s.x0 <= W - 1, xin1 = s.x0 + 1 >= 0 && s.x0 + 1 <= W - 1;
+    bool yin0 = s.y0 >= 0 && s.y0 <= H - 1, yin1 = s.y0 + 1 >= 0 && s.y0 + 1 <= H - 1;
+    s.tl = xin0 && yin0;  // :92-95
+    s.tr = xin1 && yin0;
+    s.bl = xin0 && yin1;
+    s.br = xin1 && yin1;
+    s.off = false;
+    s.x1 = s.x0 + 1;
+    s.y1 = s.y0 + 1;
+  } else {
+    // image.warp(..., 'bilinear', true, 'pad', 0) (fast_artistic_video/utils.lua:147), see oracle
+    s.off = (yf < 0.f || yf > (float)(H - 1) || xf < 0.f || xf > (float)(W - 1));
+    s.wx = __fsub_rn(xf, (float)s.x0);  // here: fractional parts
+    s.wy = __fsub_rn(yf, (float)s.y0);
+    s.x1 = min(s.x0 + 1, W - 1);
+    s.y1 = min(s.y0 + 1, H - 1);
+    s.tl = s.tr = s.bl = s.br = !s.off;
+  }
+  return s;
+}
+
+__device__ __forceinline__ float sample_plane(const Sample &s, const float *__restrict__ p,
+                                              int64_t sy, int64_t sx, int border_mode) {
+  float vtl = 0.f, vtr = 0.f, vbl = 0.f, vbr = 0.f;
+  if (s.tl) vtl = __ldg(p + (int64_t)s.y0 * sy + (int64_t)s.x0 * sx);
+  if (s.tr) vtr = __ldg(p + (int64_t)s.y0 * sy + (int64_t)s.x1 * sx);
+  if (s.bl) vbl = __ldg(p + (int64_t)s.y1 * sy + (int64_t)s.x0 * sx);
+  if (s.br) vbr = __ldg(p + (int64_t)s.y1 * sy + (int64_t)s.x1 * sx);
+  if (border_mode == FAV_BORDER_PER_TAP) {
+    // BilinearSamplerBDHW.cu:103-106, left to right
+    float omx = __fsub_rn(1.0f, s.wx), omy = __fsub_rn(1.0f, s.wy);
+    float v = __fmul_rn(__fmul_rn(s.wx, s.wy), vtl);
+    v = __fadd_rn(v, __fmul_rn(__fmul_rn(omx, s.wy), vtr));
+    v = __fadd_rn(v, __fmul_rn(__fmul_rn(s.wx, omy), vbl));
+    v = __fadd_rn(v, __fmul_rn(__fmul_rn(omx, omy), vbr));
+    return v;
+  } else {
+    if (s.off) return 0.0f;
+    float omx = __fsub_rn(1.0f, s.wx), omy = __fsub_rn(1.0f, s.wy);
+    float v = __fmul_rn(__fmul_rn(omy, omx), vtl);
+    v = __fadd_rn(v, __fmul_rn(__fmul_rn(omy, s.wx), vtr));
+    v = __fadd_rn(v, __fmul_rn(__fmul_rn(s.wy, omx), vbl));
+    v = __fadd_rn(v, __fmul_rn(__fmul_rn(s.wy, s.wx), vbr));
+    return v;
+  }
+}
+
+// ---- a-1: standalone warp ------------------------------------------------------------------------
+struct Strides4 { int64_t b, c, h, w; };
+
+// generic-stride kernel: one thread per output pixel, channels looped inside (flow read once)
+__global__ void __launch_bounds__(256) warp_generic_kernel(
+    const float *__restrict__ img, Strides4 is, const float *__restrict__ grid, Strides4 gs,
+    float *__restrict__ out, Strides4 os, int C, int Hin, int Win, int Hout, int Wout, int border_mode) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  int b = blockIdx.z;
+  if (x >= Wout || y >= Hout) return;
+  const float *g = grid + b * gs.b + (int64_t)y * gs.h + (int64_t)x * gs.w;
+  Sample s = make_sample(__ldg(g), __ldg(g + gs.c), y, x, Hin, Win, border_mode);
+  for (int c = 0; c < C; ++c)
+    out[b * os.b + c * os.c + (int64_t)y * os.h + (int64_t)x * os.w] =
+        sample_plane(s, img + b * is.b + c * is.c, is.h, is.w, border_mode);
+}
+
+// contiguous-row fast path: 4 pixels / thread, float4 flow loads and float4 stores
+template <int C_STATIC>
+__global__ void __launch_bounds__(256) warp_vec4_kernel(
+    const float *__restrict__ img, Strides4 is, const float *__restrict__ grid, Strides4 gs,
+    float *__restrict__ out, Strides4 os, int C, int Hin, int Win, int Hout, int Wout, int border_mode) {
+  int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  int b = blockIdx.z;
+  if (x4 >= Wout || y >= Hout) return;
+  const float *g = grid + b * gs.b + (int64_t)y * gs.h + x4;
+  float4 dy = __ldg(reinterpret_cast<const float4 *>(g));
+  float4 dx = __ldg(reinterpret_cast<const float4 *>(g + gs.c));
+  Sample s0 = make_sample(dy.x, dx.x, y, x4 + 0, Hin, Win, border_mode);
+  Sample s1 = make_sample(dy.y, dx.y, y, x4 + 1, Hin, Win, border_mode);
+  Sample s2 = make_sample(dy.z, dx.z, y, x4 + 2, Hin, Win, border_mode);
+  Sample s3 = make_sample(dy.w, dx.w, y, x4 + 3, Hin, Win, border_mode);
+  const int Cn = C_STATIC > 0 ? C_STATIC : C;
+#pragma unroll
+  for (int c = 0; c < Cn; ++c) {
+    const float *p = img + b * is.b + c * is.c;
+    float4 v;
+    v.x = sample_plane(s0, p, is.h, 1, border_mode);
+    v.y = sample_plane(s1, p, is.h, 1, border_mode);
+    v.z = sample_plane(s2, p, is.h, 1, border_mode);
+    v.w = sample_plane(s3, p, is.h, 1, border_mode);
+    __stcs(reinterpret_cast<float4 *>(out + b * os.b + c * os.c + (int64_t)y * os.h + x4), v);
+  }
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int launch_warp(const float *img, const int64_t isz[4], const int64_t ist[4], const float *grid,
+                       const int64_t gsz[4], const int64_t gst[4], float *out, const int64_t ost[4],
+                       int border_mode, cudaStream_t st) {
+  // the Lua asserts of BilinearSamplerBDHW:check (BilinearSamplerBDHW.lua:26-42)
+  FAV_REQUIRE(img && grid && out, "BilinearSamplerBDHW: null tensor");
+  FAV_REQUIRE(isz[0] == gsz[0], "BilinearSamplerBDHW: batch mismatch (%lld vs %lld)", (long long)isz[0],
+              (long long)gsz[0]);
+  FAV_REQUIRE(gsz[1] == 2, "BilinearSamplerBDHW: grids:size(2) must be 2 (got %lld)", (long long)gsz[1]);
+  FAV_REQUIRE(border_mode == FAV_BORDER_PER_TAP || border_mode == FAV_BORDER_PAD_PIXEL, "bad border_mode");
+  for (int i = 0; i < 4; ++i) FAV_REQUIRE(isz[i] > 0 && gsz[i] > 0, "BilinearSamplerBDHW: empty tensor");
+  FAV_TRY(require_device());
+  int B = (int)isz[0], C = (int)isz[1], Hin = (int)isz[2], Win = (int)isz[3];
+  int Hout = (int)gsz[2], Wout = (int)gsz[3];
+  Strides4 is{ist[0], ist[1], ist[2], ist[3]}, gs{gst[0], gst[1], gst[2], gst[3]},
+      os{ost[0], ost[1], ost[2], ost[3]};
+  bool vec = is.w == 1 && gs.w == 1 && os.w == 1 && (Wout % 4 == 0) && aligned16(grid) && aligned16(out) &&
+             (gs.b % 4 == 0) && (gs.c % 4 == 0) && (gs.h % 4 == 0) && (os.b % 4 == 0) && (os.c % 4 == 0) &&
+             (os.h % 4 == 0);
+  if (vec) {
+    dim3 block(32, 8), gridDim(ceil_div(Wout / 4, 32), ceil_div(Hout, 8), B);
+    if (C == 3)
+      warp_vec4_kernel<3><<<gridDim, block, 0, st>>>(img, is, grid, gs, out, os, C, Hin, Win, Hout, Wout, border_mode);
+    else if (C == 1)
+      warp_vec4_kernel<1><<<gridDim, block, 0, st>>>(img, is, grid, gs, out, os, C, Hin, Win, Hout, Wout, border_mode);
+    else
+      warp_vec4_kernel<0><<<gridDim, block, 0, st>>>(img, is, grid, gs, out, os, C, Hin, Win, Hout, Wout, border_mode);
+  } else {
+    dim3 block(32, 8), gridDim(ceil_div(Wout, 32), ceil_div(Hout, 8), B);
+    warp_generic_kernel<<<gridDim, block, 0, st>>>(img, is, grid, gs, out, os, C, Hin, Win, Hout, Wout, border_mode);
+  }
+  return post_launch("BilinearSamplerBDHW.updateOutput");
+}
+
+// ---- a-8 / a-9: fused temporal input ---------------------------------------------------------------
+// out7: [7,H,W] fp32.  VEC pixels per thread.
+template <int VEC, bool FIRST>
+__global__ void __launch_bounds__(256) temporal_input_kernel(
+    const float *__restrict__ content, const float *__restrict__ prev, const float *__restrict__ flow,
+    const float *__restrict__ cert, const float *__restrict__ fill, const float *__restrict__ flow_mask,
+    float *__restrict__ out7, int H, int W, int border_mode) {
+  int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x0 >= W || y >= H) return;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t o = (int64_t)y * W + x0;
+  const float mean[3] = {FAV_MEAN_B, FAV_MEAN_G, FAV_MEAN_R};
+  float cont[3][VEC], res[7][VEC];
+  // content planes (R,G,B)
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (VEC == 4) {
+      float4 t = __ldcs(reinterpret_cast<const float4 *>(content + j * HW + o));
+      cont[j][0] = t.x; cont[j][1] = t.y; cont[j][2] = t.z; cont[j][3] = t.w;
+    } else {
+      cont[j][0] = __ldcs(content + j * HW + o);
+    }
+  }
+  float dy[VEC], dx[VEC], c[VEC], fm[VEC];
+  if (!FIRST) {
+    if (VEC == 4) {
+      float4 t = __ldcs(reinterpret_cast<const float4 *>(flow + o));
+      dy[0] = t.x; dy[1] = t.y; dy[2] = t.z; dy[3] = t.w;
+      t = __ldcs(reinterpret_cast<const float4 *>(flow + HW + o));
+      dx[0] = t.x; dx[1] = t.y; dx[2] = t.z; dx[3] = t.w;
+      t = __ldcs(reinterpret_cast<const float4 *>(cert + o));
+      c[0] = t.x; c[1] = t.y; c[2] = t.z; c[3] = t.w;
+      if (flow_mask) {
+        t = __ldcs(reinterpret_cast<const float4 *>(flow_mask + o));
+        fm[0] = t.x; fm[1] = t.y; fm[2] = t.z; fm[3] = t.w;
+      }
+    } else {
+      dy[0] = flow[o]; dx[0] = flow[HW + o]; c[0] = cert[o];
+      if (flow_mask) fm[0] = flow_mask[o];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    // in[k] = 255*content[2-k] - mean[k]   (preprocess.lua:61; core.lua:168)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) res[k][i] = __fsub_rn(__fmul_rn(cont[2 - k][i], 255.0f), mean[k]);
+    if (FIRST) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) res[3 + k][i] = 0.0f;
+      res[6][i] = 0.0f;  // core.lua:135-136: everything "uncertain"
+    } else {
+      Sample s = make_sample(dy[i], dx[i], y, x0 + i, H, W, border_mode);
+      float wr = sample_plane(s, prev, W, 1, border_mode);
+      float wg = sample_plane(s, prev + HW, W, 1, border_mode);
+      float wb = sample_plane(s, prev + 2 * HW, W, 1, border_mode);
+      float wrgb[3] = {wr, wg, wb};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float pre = __fsub_rn(__fmul_rn(wrgb[2 - k], 255.0f), mean[k]);  // core.lua:166
+        res[3 + k][i] = __fmul_rn(pre, c[i]);                              // :167
+      }
+      res[6][i] = flow_mask ? fminf(c[i], fm[i]) : c[i];  // :169 cmin
+    }
+  }
+  if (fill) {  // generate_fill, core.lua:108-117 ('uniform-random' supplies the tensor; 'vgg-mean' = NULL)
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) res[3 + k][i] = __fadd_rn(__ldg(fill + k * HW + o + i), res[3 + k][i]);
+  } else if (!FIRST) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) res[3 + k][i] = __fadd_rn(0.0f, res[3 + k][i]);  // torch.add(zeros, x)
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    if (VEC == 4)
+      *reinterpret_cast<float4 *>(out7 + k * HW + o) = make_float4(res[k][0], res[k][1], res[k][2], res[k][3]);
+    else
+      out7[k * HW + o] = res[k][0];
+  }
+}
+
+int launch_temporal_input(const float *content, const float *prev, const float *flow, const float *cert,
+                          const float *fill, const float *flow_mask, float *out7, int H, int W,
+                          int border_mode, bool first, cudaStream_t st) {
+  bool vec = (W % 4 == 0) && aligned16(content) && aligned16(out7) && (first || (aligned16(flow) && aligned16(cert))) &&
+             (!flow_mask || aligned16(flow_mask));
+  dim3 block(32, 8);
+  if (vec) {
+    dim3 grid(ceil_div(W / 4, 32), ceil_div(H, 8));
+    if (first)
+      temporal_input_kernel<4, true><<<grid, block, 0, st>>>(content, prev, flow, cert, fill, flow_mask, out7, H, W, border_mode);
+    else
+      temporal_input_kernel<4, false><<<grid, block, 0, st>>>(content, prev, flow, cert, fill, flow_mask, out7, H, W, border_mode);
+  } else {
+    dim3 grid(ceil_div(W, 32), ceil_div(H, 8));
+    if (first)
+      temporal_input_kernel<1, true><<<grid, block, 0, st>>>(content, prev, flow, cert, fill, flow_mask, out7, H, W, border_mode);
+    else
+      temporal_input_kernel<1, false><<<grid, block, 0, st>>>(content, prev, flow, cert, fill, flow_mask, out7, H, W, border_mode);
+  }
+  return post_launch(first ? "first_frame_input" : "temporal_input");
+}
+
+// ---- a-5: min filter -------------------------------------------------------------------------------
+// 1 - maxpool_{r x r,s1,p=r/2}(1 - x) == fl(1 - fl(1 - min_window(x))) (rounding is monotone); pad cells
+// are ignored by max-pooling (-inf padding), i.e. +inf for the min.
+#define MF_TX 64
+#define MF_TY 16
+#define MF_MAXP 7
+__global__ void __launch_bounds__(256) min_filter_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                         int H, int W, int r) {
+  __shared__ float tile[MF_TY + 2 * MF_MAXP][MF_TX + 2 * MF_MAXP + 1];
+  __shared__ float rowmin[MF_TY + 2 * MF_MAXP][MF_TX + 1];
+  const int p = r / 2;
+  const int bx = blockIdx.x * MF_TX, by = blockIdx.y * MF_TY;
+  const float *src = in + (int64_t)blockIdx.z * H * W;
+  float *dst = out + (int64_t)blockIdx.z * H * W;
+  const int tw = MF_TX + 2 * p, th = MF_TY + 2 * p;
+  for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
+    int ty = i / tw, tx = i % tw;
+    int gy = by + ty - p, gx = bx + tx - p;
+    tile[ty][tx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(src + (int64_t)gy * W + gx) : INFINITY;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < th * MF_TX; i += blockDim.x) {
+    int ty = i / MF_TX, tx = i % MF_TX;
+    float m = INFINITY;
+    for (int d = 0; d < r; ++d) m = fminf(m, tile[ty][tx + d]);
+    rowmin[ty][tx] = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < MF_TY * MF_TX; i += blockDim.x) {
+    int ty = i / MF_TX, tx = i % MF_TX;
+    int gy = by + ty, gx = bx + tx;
+    if (gy >= H || gx >= W) continue;
+    float m = INFINITY;
+    for (int d = 0; d < r; ++d) m = fminf(m, rowmin[ty + d][tx]);
+    // MulConstant(-1), AddConstant(1), pool, MulConstant(-1), AddConstant(1)  (utils.lua:162-167)
+    float t = __fadd_rn(__fmul_rn(m, -1.0f), 1.0f);
+    dst[(int64_t)gy * W + gx] = __fadd_rn(__fmul_rn(t, -1.0f), 1.0f);
+  }
+}
+
+int launch_min_filter(const float *in, float *out, int n, int H, int W, int r, cudaStream_t st) {
+  dim3 grid(ceil_div(W, MF_TX), ceil_div(H, MF_TY), n);
+  min_filter_kernel<<<grid, 256, 0, st>>>(in, out, H, W, r);
+  return post_launch("min_filter");
+}
+
+// ---- a-6: vgg pre/deprocess ------------------------------------------------------------------------
+template <bool DE>
+__global__ void __launch_bounds__(256) vgg_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t HW,
+                                                  int64_t total_px) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_px) return;
+  int64_t n = i / HW, px = i % HW;
+  const float *src = in + n * 3 * HW + px;
+  float *dst = out + n * 3 * HW + px;
+  const float mean[3] = {FAV_MEAN_B, FAV_MEAN_G, FAV_MEAN_R};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (!DE)
+      dst[k * HW] = __fsub_rn(__fmul_rn(src[(2 - k) * HW], 255.0f), mean[k]);  // preprocess.lua:61
+    else
+      dst[(2 - k) * HW] = __fdiv_rn(__fadd_rn(src[k * HW], mean[k]), 255.0f);  // :70
+  }
+}
+
+}  // namespace fav
+
+using namespace fav;
+
+extern "C" {
+
+int fav_bilinear_sampler_bdhw_update_output(const float *img, const int64_t img_size[4], const int64_t img_stride[4],
+                                            const float *grid, const int64_t grid_size[4],
+                                            const int64_t grid_stride[4], float *out, const int64_t out_stride[4],
+                                            int border_mode, void *stream) {
+  return launch_warp(img, img_size, img_stride, grid, grid_size, grid_stride, out, out_stride, border_mode,
+                     (cudaStream_t)stream);
+}
+
+int fav_bilinear_sampler_bdhw_update_grad_input(void) {
+  // BilinearSamplerBDHW.cu:171-176
+  set_error("error in BilinearSampler.updateGradInput: Not implemented");
+  return FAV_ERR_NOT_IMPLEMENTED;
+}
+int fav_bilinear_sampler_bdhw_update_grad_input_only_grid(void) {
+  // BilinearSamplerBDHW.cu:179-184
+  set_error("error in BilinearSampler.updateGradInput: Not implemented");
+  return FAV_ERR_NOT_IMPLEMENTED;
+}
+
+int fav_warp_image(const float *img, int C, int Hin, int Win, const float *flow, int Hout, int Wout, float *out,
+                   int border_mode, void *stream) {
+  int64_t isz[4] = {1, C, Hin, Win}, ist[4] = {(int64_t)C * Hin * Win, (int64_t)Hin * Win, Win, 1};
+  int64_t gsz[4] = {1, 2, Hout, Wout}, gst[4] = {(int64_t)2 * Hout * Wout, (int64_t)Hout * Wout, Wout, 1};
+  int64_t ost[4] = {(int64_t)C * Hout * Wout, (int64_t)Hout * Wout, Wout, 1};
+  return launch_warp(img, isz, ist, flow, gsz, gst, out, ost, border_mode, (cudaStream_t)stream);
+}
+
+int fav_min_filter(const float *in, float *out, int n, int H, int W, int r, void *stream) {
+  FAV_REQUIRE(in && out, "min_filter: null tensor");
+  FAV_REQUIRE(n > 0 && H > 0 && W > 0, "min_filter: empty tensor");
+  FAV_REQUIRE(r >= 1 && (r & 1) && r / 2 <= MF_MAXP, "min_filter: r must be odd and <= %d", 2 * MF_MAXP + 1);
+  FAV_TRY(require_device());
+  return launch_min_filter(in, out, n, H, W, r, (cudaStream_t)stream);
+}
+
+int fav_vgg_preprocess(const float *in, float *out, int N, int H, int W, void *stream) {
+  FAV_REQUIRE(in && out && N > 0 && H > 0 && W > 0, "vgg.preprocess: img must be N x 3 x H x W");
+  FAV_TRY(require_device());
+  int64_t HW = (int64_t)H * W, total = HW * N;
+  vgg_kernel<false><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, HW, total);
+  return post_launch("vgg.preprocess");
+}
+int fav_vgg_deprocess(const float *in, float *out, int N, int H, int W, void *stream) {
+  FAV_REQUIRE(in && out && N > 0 && H > 0 && W > 0, "vgg.deprocess: img must be N x 3 x H x W");
+  FAV_TRY(require_device());
+  int64_t HW = (int64_t)H * W, total = HW * N;
+  vgg_kernel<true><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, HW, total);
+  return post_launch("vgg.deprocess");
+}
+
+int fav_temporal_input(const float *content, const float *prev, const float *flow, const float *cert,
+                       const float *fill, const float *flow_mask, float *out7, int H, int W, int border_mode,
+                       void *stream) {
+  FAV_REQUIRE(content && prev && flow && cert && out7, "temporal_input: null tensor");
+  FAV_REQUIRE(H > 0 && W > 0, "temporal_input: empty frame");
+  FAV_REQUIRE(border_mode == FAV_BORDER_PER_TAP || border_mode == FAV_BORDER_PAD_PIXEL, "bad border_mode");
+  FAV_TRY(require_device());
+  return launch_temporal_input(content, prev, flow, cert, fill, flow_mask, out7, H, W, border_mode, false,
+                               (cudaStream_t)stream);
+}
+
+int fav_first_frame_input(const float *content, const float *fill, float *out7, int H, int W, void *stream) {
+  FAV_REQUIRE(content && out7, "first_frame_input: null tensor");
+  FAV_REQUIRE(H > 0 && W > 0, "first_frame_input: empty frame");
+  FAV_TRY(require_device());
+  return launch_temporal_input(content, nullptr, nullptr, nullptr, fill, nullptr, out7, H, W, 0, true,
+                               (cudaStream_t)stream);
+}
+}

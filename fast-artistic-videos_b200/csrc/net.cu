@@ -1,0 +1,509 @@
+// net.cu -- host side of the stylization network: arch parser, parameter store, weight repacking, per-size
+// execution plan, forward, run_image / run_next_image.
+//   models_video.build_model              fast_artistic_video/models_video.lua:55-140
+//   build_res_block (reflect-start)       models_video.lua:41-53
+//   lazily inserted reflection padding    train_video.lua:316-325
+//   run_image / run_next_image            fast_artistic_video_core.lua:121-180
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include <cmath>
+#include <cstring>
+
+#include "conv_plan.hpp"
+
+namespace fav {
+
+int launch_temporal_input(const float *content, const float *prev, const float *flow, const float *cert,
+                          const float *fill, const float *flow_mask, float *out7, int H, int W, int border_mode,
+                          bool first, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------
+struct Param {
+  std::string name;
+  int64_t shape[4] = {1, 1, 1, 1};
+  int64_t numel = 0;
+  std::vector<float> host;
+  bool set = false;
+};
+
+struct InDef {
+  std::string name;
+  int C = 0;
+  float *d_gamma = nullptr, *d_beta = nullptr;
+  int pw = -1, pb = -1;
+};
+
+// arch-level program
+struct SpecOp {
+  int kind;  // 0 conv(+in+relu), 1 res block
+  int conv[2] = {-1, -1};
+  int inorm[2] = {-1, -1};
+  bool relu = false, last = false;
+};
+
+struct PlanStep {
+  int kind;  // 0 conv, 1 instance norm (+relu, +skip) -> operand
+  int conv = -1, inorm = -1;
+  int src = -1, dst = -1, skip = -1;
+  int relu = 0;
+  RawTensor raw;
+  std::vector<ConvJob> tc;
+  std::vector<SimtJob> simt;
+  int stats_off = 0;
+  int layer_index = -1;  // arch token index whose output this step completes (for fav_net_layer_output)
+};
+
+struct Plan {
+  int H = 0, W = 0;
+  std::vector<Operand> ops;
+  std::vector<void *> allocs;
+  float *raw_buf = nullptr;
+  double *stats = nullptr;
+  size_t stats_bytes = 0;
+  float *msb = nullptr;
+  float *in7 = nullptr, *out3 = nullptr;  // scratch for run_image / run_next_image
+  std::vector<PlanStep> steps;
+  std::map<int, int> layer_operand;  // arch token index -> operand holding its output
+  ~Plan() {
+    for (void *p : allocs) cudaFree(p);
+  }
+};
+
+}  // namespace fav
+
+using namespace fav;
+
+struct fav_net {
+  std::string arch;
+  float tanh_c = 150.f;
+  int in_dim = 7;
+  int reflect_pad = 0;
+  std::vector<Param> params;
+  std::vector<ConvDef> convs;
+  std::vector<InDef> inorms;
+  std::vector<SpecOp> ops;
+  bool finalized = false;
+  int conv_impl = 0;
+  int num_sms = 148;
+  int device = 0;
+  std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+  std::vector<void *> allocs;
+  ~fav_net() {
+    plans.clear();
+    for (void *p : allocs) cudaFree(p);
+  }
+};
+
+namespace fav {
+
+static int add_param(fav_net *net, const std::string &name, std::initializer_list<int64_t> shape) {
+  Param p;
+  p.name = name;
+  int i = 0;
+  p.numel = 1;
+  for (int64_t s : shape) {
+    p.shape[i++] = s;
+    p.numel *= s;
+  }
+  net->params.push_back(std::move(p));
+  return (int)net->params.size() - 1;
+}
+
+static int add_conv(fav_net *net, const std::string &name, int cin, int cout, int k, int stride, int pad, bool tr,
+                    int adj) {
+  ConvDef c;
+  init_conv_def(c, name, cin, cout, k, stride, pad, tr, adj);
+  build_phases(c);
+  if (tr) c.pw = add_param(net, name + ".weight", {cin, cout, k, k});
+  else c.pw = add_param(net, name + ".weight", {cout, cin, k, k});
+  c.pb = add_param(net, name + ".bias", {cout});
+  net->convs.push_back(std::move(c));
+  return (int)net->convs.size() - 1;
+}
+static int add_in(fav_net *net, const std::string &name, int C) {
+  InDef n;
+  n.name = name; n.C = C;
+  n.pw = add_param(net, name + ".weight", {C});
+  n.pb = add_param(net, name + ".bias", {C});
+  net->inorms.push_back(std::move(n));
+  return (int)net->inorms.size() - 1;
+}
+
+template <class T>
+static int dev_upload(fav_net *net, const std::vector<T> &h, T **out) {
+  void *d = nullptr;
+  FAV_TRY(check_cuda(cudaMalloc(&d, std::max<size_t>(h.size() * sizeof(T), 16)), "cudaMalloc(weights)"));
+  net->allocs.push_back(d);
+  FAV_TRY(check_cuda(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice), "cudaMemcpy(weights)"));
+  *out = (T *)d;
+  return FAV_OK;
+}
+
+static int pack_conv_weights(fav_net *net, ConvDef &c) {
+  const std::vector<float> &w = net->params[c.pw].host;
+  std::vector<float> bias(c.Npad, 0.f);
+  for (int i = 0; i < c.cout; ++i) bias[i] = net->params[c.pb].host[i];
+  FAV_TRY(dev_upload(net, bias, &c.d_bias));
+  for (auto &ph : c.phases) {
+    FAV_TRY(build_phase_tables(c, ph));
+    // CUDA-core comparator layout: [tap][Cin_pad][Cout_pad8]
+    std::vector<float> ws((size_t)ph.taps.size() * c.cin_pad * c.cout_pad8, 0.f);
+    for (size_t t = 0; t < ph.taps.size(); ++t)
+      for (int ci = 0; ci < c.cin; ++ci)
+        for (int co = 0; co < c.cout; ++co)
+          ws[(t * c.cin_pad + ci) * c.cout_pad8 + co] = weight_at(c, w, co, ci, ph.taps[t].ky, ph.taps[t].kx);
+    FAV_TRY(dev_upload(net, ws, &ph.d_w_simt));
+    std::vector<uint16_t> pk = pack_phase_weights(c, ph, w);
+    uint16_t *d = nullptr;
+    FAV_TRY(dev_upload(net, pk, &d));
+    ph.d_b_tc = reinterpret_cast<uint4 *>(d);
+  }
+  return FAV_OK;
+}
+
+// ---- plan ---------------------------------------------------------------------------------------------------
+static int alloc_zero(Plan &pl, void **out, size_t bytes) {
+  FAV_TRY(check_cuda(cudaMalloc(out, bytes), "cudaMalloc(activations)"));
+  pl.allocs.push_back(*out);
+  return check_cuda(cudaMemset(*out, 0, bytes), "cudaMemset(activations)");
+}
+
+// operand feeding convolution `c` (its pad / parity requirements)
+static int make_operand(Plan &pl, int C, int H, int W, const ConvDef *consumer, int *index) {
+  Operand o = operand_geometry(C, H, W, consumer);
+  FAV_TRY(alloc_zero(pl, (void **)&o.hi, o.elems16 * 16));
+  FAV_TRY(alloc_zero(pl, (void **)&o.lo, o.elems16 * 16));
+  pl.ops.push_back(o);
+  *index = (int)pl.ops.size() - 1;
+  return FAV_OK;
+}
+
+static int build_conv_jobs(fav_net *net, Plan &pl, PlanStep &st, const ConvDef &c, bool last, float *out3) {
+  const Operand &in = pl.ops[st.src];
+  for (const ConvPhase &ph : c.phases) {
+    ConvJob j;
+    FAV_TRY(fill_conv_job(c, ph, in, j));
+    j.b = ph.d_b_tc; j.bias = c.d_bias;
+    j.raw = st.raw.p; j.raw_Cq = st.raw.Cq; j.raw_Wp = st.raw.Wp;
+    j.final_mode = last ? 1 : 0; j.out3 = out3; j.tanh_c = net->tanh_c;
+    if (conv_tc_smem_bytes(j) > 227 * 1024) {
+      set_error("conv %s: shared memory budget exceeded", c.name.c_str());
+      return FAV_ERR_UNSUPPORTED;
+    }
+    st.tc.push_back(j);
+
+    SimtJob s;
+    memset(&s, 0, sizeof(s));
+    s.in = in; s.sy = s.sx = c.in_stride; s.ntaps = (int)ph.taps.size();
+    for (int t = 0; t < s.ntaps; ++t) { s.tdy[t] = (int8_t)ph.taps[t].dy; s.tdx[t] = (int8_t)ph.taps[t].dx; }
+    s.w = ph.d_w_simt; s.Cin_pad = c.cin_pad; s.Cout = c.cout; s.Cout_pad8 = c.cout_pad8; s.bias = c.d_bias;
+    s.Ho = j.Ho; s.Wo = j.Wo; s.raw = st.raw.p; s.raw_Cq = st.raw.Cq; s.raw_Wp = st.raw.Wp;
+    s.oy_mul = s.ox_mul = c.out_mul; s.oy_off = ph.oy_off; s.ox_off = ph.ox_off;
+    s.final_mode = last ? 1 : 0; s.out3 = out3; s.tanh_c = net->tanh_c;
+    st.simt.push_back(s);
+  }
+  return FAV_OK;
+}
+
+static int build_plan(fav_net *net, int H, int W, Plan **out) {
+  auto key = std::make_pair(H, W);
+  auto it = net->plans.find(key);
+  if (it != net->plans.end()) { *out = it->second.get(); return FAV_OK; }
+  if (H % 4 || W % 4 || H < 16 || W < 16) {
+    set_error("frame size %dx%d: H and W must be multiples of 4 (reflect-start nets restore the input size only "
+              "then, SURVEY appendix B)", W, H);
+    return FAV_ERR_INVALID;
+  }
+  std::unique_ptr<Plan> pl(new Plan());
+  pl->H = H; pl->W = W;
+  const int R = net->reflect_pad;
+  if (R >= H || R >= W) { set_error("frame smaller than the reflection padding (%d)", R); return FAV_ERR_INVALID; }
+  // pass 1: sizes -> largest raw tensor, stats slots
+  size_t raw_max = 0;
+  int stats_slots = 0;
+  {
+    int h = H + 2 * R, w = W + 2 * R;
+    for (auto &op : net->ops) {
+      int n = op.kind == 1 ? 2 : 1;
+      for (int i = 0; i < n; ++i) {
+        const ConvDef &c = net->convs[op.conv[i]];
+        int ho, wo;
+        conv_out_size(c, h, w, &ho, &wo);
+        raw_max = std::max(raw_max, (size_t)(ho + 2) * round_up(c.cout, 4) * round_up(wo, kTileM));
+        h = ho; w = wo;
+        if (op.inorm[i] >= 0) stats_slots += 2 * c.cout;
+      }
+    }
+  }
+  FAV_TRY(alloc_zero(*pl, (void **)&pl->raw_buf, raw_max * sizeof(float) + 4096));
+  pl->stats_bytes = std::max(1, stats_slots) * sizeof(double);
+  FAV_TRY(alloc_zero(*pl, (void **)&pl->stats, pl->stats_bytes));
+  FAV_TRY(alloc_zero(*pl, (void **)&pl->msb, std::max(1, stats_slots) * 2 * sizeof(float)));
+  FAV_TRY(alloc_zero(*pl, (void **)&pl->in7, (size_t)net->in_dim * H * W * sizeof(float)));
+  FAV_TRY(alloc_zero(*pl, (void **)&pl->out3, (size_t)3 * H * W * sizeof(float)));
+
+  // flat list of convs in execution order, to look up the consumer of each operand
+  std::vector<int> order;
+  for (auto &op : net->ops) { order.push_back(op.conv[0]); if (op.kind == 1) order.push_back(op.conv[1]); }
+  size_t pos = 0;
+  int cur;
+  FAV_TRY(make_operand(*pl, net->in_dim, H + 2 * R, W + 2 * R, &net->convs[order[0]], &cur));
+  int stats_off = 0;
+  for (size_t oi = 0; oi < net->ops.size(); ++oi) {
+    const SpecOp &op = net->ops[oi];
+    const int n = op.kind == 1 ? 2 : 1;
+    const int block_in = cur;
+    for (int i = 0; i < n; ++i, ++pos) {
+      const ConvDef &c = net->convs[op.conv[i]];
+      PlanStep cs;
+      cs.kind = 0; cs.conv = op.conv[i]; cs.src = cur;
+      int ho, wo;
+      conv_out_size(c, pl->ops[cur].H, pl->ops[cur].W, &ho, &wo);
+      cs.raw.p = pl->raw_buf; cs.raw.C = c.cout; cs.raw.Cq = round_up(c.cout, 4) / 4; cs.raw.H = ho; cs.raw.W = wo;
+      cs.raw.Hp = ho + 2; cs.raw.Wp = round_up(wo, kTileM);
+      const bool last = op.last && i == n - 1;
+      FAV_TRY(build_conv_jobs(net, *pl, cs, c, last, nullptr));
+      if (last) { cs.layer_index = (int)oi; pl->steps.push_back(std::move(cs)); break; }
+      RawTensor raw = cs.raw;
+      pl->steps.push_back(std::move(cs));
+      // InstanceNorm (+ReLU) (+skip) -> operand for the next convolution
+      if (op.inorm[i] < 0 || c.cout % 8) {
+        set_error("layer %s: a non-final convolution must be followed by InstanceNormalization (Cout %% 8 == 0)",
+                  c.name.c_str());
+        return FAV_ERR_UNSUPPORTED;
+      }
+      PlanStep ns;
+      ns.kind = 1; ns.inorm = op.inorm[i]; ns.raw = raw; ns.stats_off = stats_off;
+      stats_off += 2 * c.cout;
+      const ConvDef *consumer = pos + 1 < order.size() ? &net->convs[order[pos + 1]] : nullptr;
+      FAV_TRY(make_operand(*pl, c.cout, ho, wo, consumer, &ns.dst));
+      if (op.kind == 1) {
+        ns.relu = i == 0 ? 1 : 0;
+        ns.skip = i == 1 ? block_in : -1;  // ShaveImage(2) of the block input (models_video.lua:47-48)
+      } else {
+        ns.relu = op.relu ? 1 : 0;
+      }
+      cur = ns.dst;
+      if (i == n - 1) { ns.layer_index = (int)oi; pl->layer_operand[(int)oi] = cur; }
+      pl->steps.push_back(std::move(ns));
+    }
+  }
+  *out = pl.get();
+  net->plans[key] = std::move(pl);
+  return FAV_OK;
+}
+
+static int run_plan(fav_net *net, Plan &pl, const float *in7, float *out3, int final_mode, cudaStream_t st) {
+  FAV_TRY(check_cuda(cudaMemsetAsync(pl.stats, 0, pl.stats_bytes, st), "cudaMemsetAsync(stats)"));
+  FAV_TRY(launch_pack_input(in7, net->in_dim, pl.H, pl.W, net->reflect_pad, pl.ops[0], st));
+  for (PlanStep &s : pl.steps) {
+    if (s.kind == 0) {
+      if (net->conv_impl == 0) {
+        for (ConvJob &j : s.tc) {
+          if (j.final_mode) { j.final_mode = final_mode; j.out3 = out3; }
+          FAV_TRY(launch_conv_tc(j, net->num_sms, st));
+        }
+      } else {
+        for (SimtJob &j : s.simt) {
+          if (j.final_mode) { j.final_mode = final_mode; j.out3 = out3; }
+          FAV_TRY(launch_conv_simt(j, st));
+        }
+      }
+    } else {
+      const InDef &n = net->inorms[s.inorm];
+      double *sums = pl.stats + s.stats_off;
+      float *msb = pl.msb + (size_t)s.stats_off * 2;
+      FAV_TRY(launch_in_stats(s.raw, sums, st));
+      // InstanceNormalization.lua:21,39: eps = 1e-5, statistics over H*W of each (n, c)
+      FAV_TRY(launch_in_finalize(sums, n.d_gamma, n.d_beta, n.C, (int64_t)s.raw.H * s.raw.W, 1e-5f, msb, st));
+      FAV_TRY(launch_in_apply(s.raw, msb, s.relu, s.skip >= 0 ? &pl.ops[s.skip] : nullptr, 2, pl.ops[s.dst], st));
+    }
+  }
+  return FAV_OK;
+}
+
+}  // namespace fav
+
+// =============================================================================================================
+extern "C" {
+
+int fav_net_create(const char *arch, const char *padding_type, float tanh_constant, int in_dim, fav_net_t **out) {
+  FAV_REQUIRE(arch && out, "fav_net_create: null argument");
+  FAV_REQUIRE(in_dim >= 1 && in_dim <= 8, "fav_net_create: in_dim must be in [1,8] (video nets use 7, image nets 3)");
+  if (padding_type && strcmp(padding_type, "reflect-start") != 0) {
+    set_error("padding_type '%s' is not supported: the released video models use 'reflect-start' "
+              "(train_video.lua:25)", padding_type);
+    return FAV_ERR_UNSUPPORTED;
+  }
+  std::unique_ptr<fav_net> net(new fav_net());
+  net->arch = arch; net->tanh_c = tanh_constant; net->in_dim = in_dim;
+  // tokenise (models_video.lua:56)
+  std::vector<std::string> toks;
+  {
+    std::string s(arch), cur;
+    for (char ch : s) {
+      if (ch == ',') { toks.push_back(cur); cur.clear(); }
+      else if (ch != ' ') cur.push_back(ch);
+    }
+    if (!cur.empty()) toks.push_back(cur);
+  }
+  FAV_REQUIRE(!toks.empty(), "fav_net_create: empty arch");
+  int prev = in_dim;
+  double scale = 1.0, shrink = 0.0;
+  for (size_t i = 0; i < toks.size(); ++i) {
+    const std::string &v = toks[i];
+    const std::string name = "l" + std::to_string(i);
+    SpecOp op;
+    op.kind = 0; op.relu = true; op.last = (i + 1 == toks.size());
+    bool needs_bn = true;
+    int next = 0;
+    char c0 = v[0];
+    if (c0 == 'c' && v.size() >= 6 && v[2] == 's' && v[4] == '-') {  // cXsY-Z  models_video.lua:65-80
+      int f = v[1] - '0', s = v[3] - '0';
+      next = atoi(v.c_str() + 5);
+      FAV_REQUIRE(f % 2 == 1 && (s == 1 || s == 2) && next > 0, "bad arch token '%s'", v.c_str());
+      op.conv[0] = add_conv(net.get(), name, prev, next, f, s, (f - 1) / 2, false, 0);
+      if (s == 2) scale *= 2;
+    } else if (c0 == 'd') {  // dX  :90-93
+      next = atoi(v.c_str() + 1);
+      FAV_REQUIRE(next > 0, "bad arch token '%s'", v.c_str());
+      op.conv[0] = add_conv(net.get(), name, prev, next, 3, 2, 1, false, 0);
+      scale *= 2;
+    } else if (c0 == 'u') {  // uX  :99-102  SpatialFullConvolution(3,3,2,2,1,1,1,1)
+      next = atoi(v.c_str() + 1);
+      FAV_REQUIRE(next > 0, "bad arch token '%s'", v.c_str());
+      op.conv[0] = add_conv(net.get(), name, prev, next, 3, 2, 1, true, 1);
+      scale /= 2;
+    } else if (c0 == 'R') {  // RX  :109-114
+      next = atoi(v.c_str() + 1);
+      FAV_REQUIRE(next == prev, "residual block R%d needs %d input channels (got %d)", next, next, prev);
+      op.kind = 1;
+      op.conv[0] = add_conv(net.get(), name + ".c1", prev, next, 3, 1, 0, false, 0);
+      op.inorm[0] = add_in(net.get(), name + ".n1", next);
+      op.conv[1] = add_conv(net.get(), name + ".c2", next, next, 3, 1, 0, false, 0);
+      op.inorm[1] = add_in(net.get(), name + ".n2", next);
+      needs_bn = false; op.relu = false;
+      shrink += 4 * scale;
+    } else {
+      set_error("arch token '%s' is not supported by the sm_100a path (supported: cXsY-Z, dX, uX, RX)", v.c_str());
+      return FAV_ERR_UNSUPPORTED;
+    }
+    if (op.last) { needs_bn = false; op.relu = false; }  // :117-120
+    if (needs_bn && op.kind == 0) op.inorm[0] = add_in(net.get(), name + ".n", next);
+    net->ops.push_back(op);
+    prev = next;
+  }
+  FAV_REQUIRE(prev == 3, "the last layer must produce 3 channels (got %d)", prev);
+  FAV_REQUIRE(net->ops.back().kind == 0, "the last arch token must be a convolution");
+  FAV_REQUIRE(shrink == std::floor(shrink) && ((int)shrink) % 2 == 0, "unsupported shrink %f", shrink);
+  net->reflect_pad = (int)shrink / 2;  // train_video.lua:319-324
+  *out = net.release();
+  return FAV_OK;
+}
+
+void fav_net_destroy(fav_net_t *net) { delete net; }
+
+int fav_net_num_params(const fav_net_t *net) { return net ? (int)net->params.size() : 0; }
+
+int fav_net_param_info(const fav_net_t *net, int index, char *name_out, int64_t shape_out[4], int64_t *numel) {
+  FAV_REQUIRE(net && index >= 0 && index < (int)net->params.size(), "fav_net_param_info: bad index");
+  const Param &p = net->params[index];
+  if (name_out) { strncpy(name_out, p.name.c_str(), 63); name_out[63] = 0; }
+  if (shape_out) for (int i = 0; i < 4; ++i) shape_out[i] = p.shape[i];
+  if (numel) *numel = p.numel;
+  return FAV_OK;
+}
+
+int fav_net_set_param(fav_net_t *net, const char *name, const float *host_data, int64_t numel) {
+  FAV_REQUIRE(net && name && host_data, "fav_net_set_param: null argument");
+  FAV_REQUIRE(!net->finalized, "fav_net_set_param: net already finalized");
+  for (Param &p : net->params)
+    if (p.name == name) {
+      FAV_REQUIRE(numel == p.numel, "param %s: expected %lld elements, got %lld", name, (long long)p.numel,
+                  (long long)numel);
+      p.host.assign(host_data, host_data + numel);
+      p.set = true;
+      return FAV_OK;
+    }
+  set_error("fav_net_set_param: unknown parameter '%s'", name);
+  return FAV_ERR_INVALID;
+}
+
+int fav_net_finalize(fav_net_t *net) {
+  FAV_REQUIRE(net, "fav_net_finalize: null net");
+  if (net->finalized) return FAV_OK;
+  for (Param &p : net->params) FAV_REQUIRE(p.set, "fav_net_finalize: parameter %s was never set", p.name.c_str());
+  FAV_TRY(require_device());
+  cudaDeviceProp prop;
+  FAV_TRY(check_cuda(cudaGetDevice(&net->device), "cudaGetDevice"));
+  FAV_TRY(check_cuda(cudaGetDeviceProperties(&prop, net->device), "cudaGetDeviceProperties"));
+  if (prop.major != 10) {
+    set_error("libfav_b200 targets sm_100a (B200); device is sm_%d%d", prop.major, prop.minor);
+    return FAV_ERR_UNSUPPORTED;
+  }
+  net->num_sms = prop.multiProcessorCount;
+  for (ConvDef &c : net->convs) FAV_TRY(pack_conv_weights(net, c));
+  for (InDef &n : net->inorms) {
+    FAV_TRY(dev_upload(net, net->params[n.pw].host, &n.d_gamma));
+    FAV_TRY(dev_upload(net, net->params[n.pb].host, &n.d_beta));
+  }
+  net->finalized = true;
+  return FAV_OK;
+}
+
+int fav_net_set_conv_impl(fav_net_t *net, int impl) {
+  FAV_REQUIRE(net && (impl == 0 || impl == 1), "fav_net_set_conv_impl: impl must be 0 (tcgen05) or 1 (CUDA cores)");
+  net->conv_impl = impl;
+  return FAV_OK;
+}
+
+int fav_net_forward(fav_net_t *net, const float *in7, int H, int W, float *out3, void *stream) {
+  FAV_REQUIRE(net && in7 && out3, "fav_net_forward: null argument");
+  FAV_REQUIRE(net->finalized, "fav_net_forward: call fav_net_finalize first");
+  Plan *pl;
+  FAV_TRY(build_plan(net, H, W, &pl));
+  return run_plan(net, *pl, in7, out3, 1, (cudaStream_t)stream);
+}
+
+int fav_net_layer_output(fav_net_t *net, int index, float *out, int *C, int *Hl, int *Wl, void *stream) {
+  FAV_REQUIRE(net && !net->plans.empty(), "fav_net_layer_output: run a forward first");
+  Plan *pl = net->plans.rbegin()->second.get();
+  auto it = pl->layer_operand.find(index);
+  FAV_REQUIRE(it != pl->layer_operand.end(), "fav_net_layer_output: layer %d has no stored activation", index);
+  const Operand &o = pl->ops[it->second];
+  if (C) *C = o.C;
+  if (Hl) *Hl = o.H;
+  if (Wl) *Wl = o.W;
+  if (!out) return FAV_OK;
+  return launch_unpack_operand(o, out, (cudaStream_t)stream);
+}
+
+int fav_run_image(fav_net_t *net, const float *content, const float *fill, int H, int W, float *out_rgb,
+                  void *stream) {
+  FAV_REQUIRE(net && content && out_rgb, "fav_run_image: null argument");
+  FAV_REQUIRE(net->finalized, "fav_run_image: call fav_net_finalize first");
+  FAV_REQUIRE(net->in_dim == 7, "fav_run_image: video model (7 input channels) required");
+  Plan *pl;
+  FAV_TRY(build_plan(net, H, W, &pl));
+  cudaStream_t st = (cudaStream_t)stream;
+  FAV_TRY(launch_temporal_input(content, nullptr, nullptr, nullptr, fill, nullptr, pl->in7, H, W, 0, true, st));
+  return run_plan(net, *pl, pl->in7, out_rgb, 2, st);  // deprocess fused into the last epilogue (core.lua:149)
+}
+
+int fav_run_next_image(fav_net_t *net, const float *content, const float *prev_rgb, const float *flow,
+                       const float *cert, const float *fill, const float *flow_mask, int H, int W, int border_mode,
+                       float *out_rgb, void *stream) {
+  FAV_REQUIRE(net && content && prev_rgb && flow && cert && out_rgb, "fav_run_next_image: null argument");
+  FAV_REQUIRE(net->finalized, "fav_run_next_image: call fav_net_finalize first");
+  FAV_REQUIRE(net->in_dim == 7, "fav_run_next_image: video model (7 input channels) required");
+  FAV_REQUIRE(border_mode == FAV_BORDER_PER_TAP || border_mode == FAV_BORDER_PAD_PIXEL, "bad border_mode");
+  Plan *pl;
+  FAV_TRY(build_plan(net, H, W, &pl));
+  cudaStream_t st = (cudaStream_t)stream;
+  FAV_TRY(launch_temporal_input(content, prev_rgb, flow, cert, fill, flow_mask, pl->in7, H, W, border_mode, false, st));
+  return run_plan(net, *pl, pl->in7, out_rgb, 2, st);  // core.lua:172-173
+}
+}

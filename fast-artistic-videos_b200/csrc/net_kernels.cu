@@ -1,0 +1,241 @@
+// net_kernels.cu -- HBM-bound kernels of the stylization net + the CUDA-core convolution comparator.
+//   pack_input      : fp32 NCHW net input -> (reflect-padded) fp16 hi/lo operand     train_video.lua:319-324
+//   in_stats        : per-channel sum / sum of squares of a raw conv output         InstanceNormalization.lua:33-53
+//   in_finalize     : mean, gamma/sqrt(var+eps), beta (biased variance, eps 1e-5)
+//   in_apply        : normalise (+ReLU) (+ShaveImage(2) skip add) -> next operand    models_video.lua:41-53,121-130
+//   unpack_operand  : operand -> fp32 NCHW (per-layer parity checks)
+//   conv_simt       : direct convolution on CUDA cores, same I/O as the tcgen05 kernel (bring-up comparator)
+#include "conv.cuh"
+
+namespace fav {
+
+__device__ __forceinline__ void split_store8(const float v[8], uint4 *hi_dst, uint4 *lo_dst) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
+    __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+    __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
+    h[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+    l[i] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+  }
+  *hi_dst = make_uint4(h[0], h[1], h[2], h[3]);
+  *lo_dst = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void load_join8(const uint4 *hi_src, const uint4 *lo_src, float v[8]) {
+  uint4 h = __ldg(hi_src), l = __ldg(lo_src);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __half2float(__ushort_as_half((unsigned short)(hw[i] & 0xffff))) +
+               __half2float(__ushort_as_half((unsigned short)(lw[i] & 0xffff)));
+    v[2 * i + 1] = __half2float(__ushort_as_half((unsigned short)(hw[i] >> 16))) +
+                   __half2float(__ushort_as_half((unsigned short)(lw[i] >> 16)));
+  }
+}
+
+// ---- pack_input --------------------------------------------------------------------------------------
+// in: [Cin][H][W] fp32.  dst logical size = (H+2R) x (W+2R) with R = reflect (nn.SpatialReflectionPadding:
+// index -i for i<0, 2(n-1)-i for i>=n).  One thread per (padded pixel, channel block).
+__global__ void __launch_bounds__(256) pack_input_kernel(const float *__restrict__ in, int Cin, int H, int W, int R,
+                                                         Operand dst) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  int cb = blockIdx.z;
+  if (x >= dst.W) return;
+  int sy = y - R, sx = x - R;
+  sy = sy < 0 ? -sy : (sy >= H ? 2 * (H - 1) - sy : sy);
+  sx = sx < 0 ? -sx : (sx >= W ? 2 * (W - 1) - sx : sx);
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = cb * 8 + i;
+    v[i] = c < Cin ? __ldg(in + ((int64_t)c * H + sy) * W + sx) : 0.f;
+  }
+  int64_t o = dst.off16(dst.padT + y, cb, dst.padL + x);
+  split_store8(v, reinterpret_cast<uint4 *>(dst.hi) + o, reinterpret_cast<uint4 *>(dst.lo) + o);
+}
+
+int launch_pack_input(const float *in, int Cin, int H, int W, int reflect, const Operand &dst, cudaStream_t st) {
+  dim3 grid(ceil_div(dst.W, 256), dst.H, dst.Cb);
+  pack_input_kernel<<<grid, 256, 0, st>>>(in, Cin, H, W, reflect, dst);
+  return post_launch("pack_input");
+}
+
+// ---- in_stats ----------------------------------------------------------------------------------------
+constexpr int kStatRows = 8;
+__global__ void __launch_bounds__(256) in_stats_kernel(RawTensor raw, double *__restrict__ sums) {
+  const int cq = blockIdx.x;
+  const int y0 = blockIdx.y * kStatRows;
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  for (int y = y0; y < min(y0 + kStatRows, raw.H); ++y) {
+    const float4 *row = reinterpret_cast<const float4 *>(raw.p) + raw.off4(y, cq, 0);
+    for (int x = threadIdx.x; x < raw.W; x += 256) {
+      float4 v = __ldg(row + x);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+    }
+  }
+  __shared__ double red[8][8];
+  double d[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { d[i] = s[i]; d[4 + i] = q[i]; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d[i] += __shfl_xor_sync(0xffffffffu, d[i], o);
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][i] = d[i];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    int i = threadIdx.x & 3;
+    int c = cq * 4 + i;
+    if (c < raw.C) atomicAdd(sums + (threadIdx.x < 4 ? c : raw.C + c), t);
+  }
+}
+
+int launch_in_stats(const RawTensor &raw, double *sums, cudaStream_t st) {
+  dim3 grid(raw.Cq, ceil_div(raw.H, kStatRows));
+  in_stats_kernel<<<grid, 256, 0, st>>>(raw, sums);
+  return post_launch("in_stats");
+}
+
+__global__ void in_finalize_kernel(const double *__restrict__ sums, const float *__restrict__ gamma,
+                                   const float *__restrict__ beta, int C, double inv_count, double eps,
+                                   float *__restrict__ msb) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mean = sums[c] * inv_count;
+  double var = sums[C + c] * inv_count - mean * mean;  // biased variance (SpatialBatchNormalization, training mode)
+  if (var < 0) var = 0;
+  double rstd = 1.0 / sqrt(var + eps);
+  msb[c] = (float)mean;
+  msb[C + c] = (float)((double)gamma[c] * rstd);
+  msb[2 * C + c] = beta[c];
+}
+
+int launch_in_finalize(const double *sums, const float *gamma, const float *beta, int C, int64_t count, float eps,
+                       float *msb, cudaStream_t st) {
+  in_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, gamma, beta, C, 1.0 / (double)count, (double)eps, msb);
+  return post_launch("in_finalize");
+}
+
+// ---- in_apply ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const float *__restrict__ msb, int relu,
+                                                       Operand skip, int has_skip, int shave, Operand dst) {
+  int x = blockIdx.x * 128 + threadIdx.x;
+  int y = blockIdx.y, cb = blockIdx.z;
+  if (x >= raw.W) return;
+  const float4 *rp = reinterpret_cast<const float4 *>(raw.p);
+  float4 a = __ldg(rp + raw.off4(y, 2 * cb, x)), b = __ldg(rp + raw.off4(y, 2 * cb + 1, x));
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  const int C = raw.C;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = cb * 8 + i;
+    float t = (v[i] - __ldg(msb + c)) * __ldg(msb + C + c) + __ldg(msb + 2 * C + c);
+    v[i] = relu ? fmaxf(t, 0.f) : t;
+  }
+  if (has_skip) {  // ConcatTable{conv_block, ShaveImage(2)} -> CAddTable (models_video.lua:41-53)
+    float sk[8];
+    int64_t so = skip.off16(skip.padT + y + shave, cb, skip.padL + x + shave);
+    load_join8(reinterpret_cast<const uint4 *>(skip.hi) + so, reinterpret_cast<const uint4 *>(skip.lo) + so, sk);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += sk[i];
+  }
+  int64_t o = dst.off16(dst.padT + y, cb, dst.padL + x);
+  split_store8(v, reinterpret_cast<uint4 *>(dst.hi) + o, reinterpret_cast<uint4 *>(dst.lo) + o);
+}
+
+int launch_in_apply(const RawTensor &raw, const float *msb, int relu, const Operand *skip, int shave,
+                    const Operand &dst, cudaStream_t st) {
+  dim3 grid(ceil_div(raw.W, 128), raw.H, raw.C / 8);
+  Operand sk = skip ? *skip : Operand();
+  in_apply_kernel<<<grid, 128, 0, st>>>(raw, msb, relu, sk, skip ? 1 : 0, shave, dst);
+  return post_launch("in_apply");
+}
+
+// ---- unpack_operand (debug) -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) unpack_kernel(Operand src, float *__restrict__ out) {
+  int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y, cb = blockIdx.z;
+  if (x >= src.W) return;
+  float v[8];
+  int64_t o = src.off16(src.padT + y, cb, src.padL + x);
+  load_join8(reinterpret_cast<const uint4 *>(src.hi) + o, reinterpret_cast<const uint4 *>(src.lo) + o, v);
+  for (int i = 0; i < 8; ++i) {
+    int c = cb * 8 + i;
+    if (c < src.C) out[((int64_t)c * src.H + y) * src.W + x] = v[i];
+  }
+}
+int launch_unpack_operand(const Operand &src, float *out, cudaStream_t st) {
+  dim3 grid(ceil_div(src.W, 128), src.H, src.Cb);
+  unpack_kernel<<<grid, 128, 0, st>>>(src, out);
+  return post_launch("unpack_operand");
+}
+
+// ---- conv_simt: CUDA-core direct convolution (comparator) ---------------------------------------------------
+// block = 128 threads = 128 consecutive output pixels of one row; blockIdx.y = output row; blockIdx.z = group of
+// 8 output channels.  fp32 FMA over (hi + lo) activations and fp32 weights.
+__device__ __forceinline__ float final_value(float v, int k, int mode, float tanh_c) {
+  float t = tanhf(v) * tanh_c;  // nn.Tanh -> nn.MulConstant (models_video.lua:135-136)
+  if (mode == 2) {              // fused vgg.deprocess (preprocess.lua:70)
+    const float mean[3] = {FAV_MEAN_B, FAV_MEAN_G, FAV_MEAN_R};
+    t = __fdiv_rn(__fadd_rn(t, mean[k]), 255.0f);
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ SimtJob j) {
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int y = blockIdx.y;
+  const int co0 = blockIdx.z * 8;
+  if (x >= j.Wo) return;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const uint4 *hi = reinterpret_cast<const uint4 *>(j.in.hi), *lo = reinterpret_cast<const uint4 *>(j.in.lo);
+  for (int t = 0; t < j.ntaps; ++t) {
+    int ys = j.in.padT + j.sy * y + j.tdy[t], xs = j.in.padL + j.sx * x + j.tdx[t];
+    for (int cb = 0; cb < j.in.Cb; ++cb) {
+      float a[8];
+      int64_t o = j.in.off16(ys, cb, xs);
+      load_join8(hi + o, lo + o, a);
+      const float *w = j.w + ((int64_t)t * j.Cin_pad + cb * 8) * j.Cout_pad8 + co0;
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci) {
+        float4 w0 = __ldg(reinterpret_cast<const float4 *>(w + (int64_t)ci * j.Cout_pad8));
+        float4 w1 = __ldg(reinterpret_cast<const float4 *>(w + (int64_t)ci * j.Cout_pad8 + 4));
+        acc[0] = fmaf(a[ci], w0.x, acc[0]); acc[1] = fmaf(a[ci], w0.y, acc[1]);
+        acc[2] = fmaf(a[ci], w0.z, acc[2]); acc[3] = fmaf(a[ci], w0.w, acc[3]);
+        acc[4] = fmaf(a[ci], w1.x, acc[4]); acc[5] = fmaf(a[ci], w1.y, acc[5]);
+        acc[6] = fmaf(a[ci], w1.z, acc[6]); acc[7] = fmaf(a[ci], w1.w, acc[7]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] += (co0 + i < j.Cout) ? __ldg(j.bias + co0 + i) : 0.f;
+  const int yo = y * j.oy_mul + j.oy_off, xo = x * j.ox_mul + j.ox_off;
+  if (j.final_mode == 0) {
+    float4 *rp = reinterpret_cast<float4 *>(j.raw);
+    int64_t o0 = (((int64_t)yo * j.raw_Cq + (co0 >> 2)) * j.raw_Wp + xo);
+    rp[o0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if ((co0 >> 2) + 1 < j.raw_Cq) rp[o0 + j.raw_Wp] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  } else {
+    for (int k = 0; k < 8; ++k)
+      if (co0 + k < j.Cout)
+        j.out3[((int64_t)(co0 + k) * j.Ho + yo) * j.Wo + xo] = final_value(acc[k], co0 + k, j.final_mode, j.tanh_c);
+  }
+}
+
+int launch_conv_simt(const SimtJob &job, cudaStream_t st) {
+  dim3 grid(ceil_div(job.Wo, 128), job.Ho, job.Cout_pad8 / 8);
+  conv_simt_kernel<<<grid, 128, 0, st>>>(job);
+  return post_launch("conv_simt");
+}
+
+}  // namespace fav

@@ -1,0 +1,53 @@
+// net_layout.cuh -- HBM data layouts of the stylization net (fast_artistic_video/models_video.lua:55-140).
+//
+// The reference keeps every activation as fp32 NCHW.  Internally this implementation uses two layouts,
+// both chosen so that the tcgen05 implicit-GEMM convolution needs neither im2col nor swizzled TMA maps:
+//
+//  Operand  activation feeding a convolution, stored as an fp16 PAIR (hi, lo) with x ~= hi + lo
+//           (22 significant bits).  Layout per tensor: [Hs][Cb][Ws][8 channels] -- 16 bytes per
+//           (pixel, channel-block).  A run of consecutive pixels of one channel block is contiguous in
+//           HBM *and* is exactly the canonical no-swizzle K-major UMMA core-matrix layout (8 rows x 16 B),
+//           so a 1-D bulk copy (cp.async.bulk) of a row segment lands MMA-ready in shared memory and a
+//           filter tap is just a +16 B * dx offset of the matrix descriptor's start address.
+//           Zero padding of the convolution is materialised as a zero border (padT/padL + slack).
+//           Inputs of stride-2 convolutions are stored parity-split: [Hs][Cb][2][Ws2][8]
+//           (even x plane, then odd x plane) so that stride-2 taps stay contiguous.
+//  Raw      fp32 convolution output before InstanceNorm: [Ho][Cq][Wp][4 channels] -- 16 bytes per
+//           (pixel, channel-quad); the epilogue thread that owns TMEM lane = pixel writes float4s that are
+//           coalesced across the 32 lanes of a warp.
+#pragma once
+#include "fav_common.cuh"
+
+namespace fav {
+
+struct Operand {
+  __half *hi = nullptr, *lo = nullptr;
+  int C = 0, Cb = 0;        // logical channels, channel blocks of 8 (zero padded)
+  int H = 0, W = 0;         // logical size
+  int padT = 0, padL = 0;   // storage coords of logical (0,0)
+  int Hs = 0, Ws = 0;       // storage rows / pixels per (row, cb) slab (non-parity)
+  int parity = 0, Ws2 = 0;  // parity split: slab = [2][Ws2]
+  size_t elems16 = 0;       // allocation size in 16-byte units (per hi / lo), incl. tail slack
+  __host__ __device__ int slab16() const { return parity ? 2 * Ws2 : Ws; }
+  // offset in 16-byte units of storage pixel (ys, xs) of channel block cb
+  __host__ __device__ int64_t off16(int ys, int cb, int xs) const {
+    int64_t base = ((int64_t)ys * Cb + cb) * slab16();
+    return base + (parity ? (int64_t)(xs & 1) * Ws2 + (xs >> 1) : xs);
+  }
+};
+
+struct RawTensor {
+  float *p = nullptr;
+  int C = 0, Cq = 0;  // channels, channel quads
+  int H = 0, W = 0;   // logical size
+  int Hp = 0, Wp = 0; // allocated rows / row pitch in pixels (multiple of 128)
+  __host__ __device__ int64_t off4(int y, int cq, int x) const { return (((int64_t)y * Cq + cq) * Wp + x); }
+};
+
+// one filter tap of a (phase of a) convolution: input pixel = (sy*y + dy, sx*x + dx)
+struct ConvTap {
+  int dy, dx;
+  int ky, kx;  // index into the Torch weight tensor
+};
+
+}  // namespace fav

@@ -1,0 +1,183 @@
+// session.cu -- a-10: the frame loop with HOST buffers (fast_artistic_video_core.lua:189-229 +
+// fast_artistic_video.lua:93-170).  One session = one H x W stream on one GPU.
+//
+// The recurrent state last_frame_stylized stays on the device as unclamped fp32 (fast_artistic_video.lua:169).
+// Three streams: H2D (frame i+1 inputs), compute (frame i), D2H (frame i-1 result); inputs and outputs are
+// double buffered and ordered with events, so copies overlap compute whenever the caller's host buffers are
+// pinned.  Nothing in the loop synchronises the host except fav_session_sync().
+#include <memory>
+#include <vector>
+
+#include "fav_common.cuh"
+
+namespace fav {
+int launch_min_filter(const float *in, float *out, int n, int H, int W, int r, cudaStream_t st);
+int launch_consistency(const float *f1u, const float *f1v, const float *f2u, const float *f2v, const float *structure,
+                       const float *avg_dev, float avg_host, uint8_t *rel, float *cert, int W, int H, cudaStream_t st);
+}
+
+using namespace fav;
+
+struct fav_session {
+  fav_net_t *net = nullptr;
+  int H = 0, W = 0;
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  struct InSet {
+    float *content = nullptr, *flow = nullptr, *flow_fw = nullptr, *cert_raw = nullptr, *cert = nullptr;
+    cudaEvent_t uploaded = nullptr, consumed = nullptr;
+    bool used = false;
+  } in[2];
+  float *out[2] = {nullptr, nullptr};
+  cudaEvent_t computed[2] = {nullptr, nullptr}, downloaded[2] = {nullptr, nullptr};
+  bool out_used[2] = {false, false};
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  uint64_t frame = 0;
+  bool have_prev = false;
+  std::vector<void *> allocs;
+};
+
+static int s_alloc(fav_session *s, float **p, size_t n) {
+  void *d = nullptr;
+  FAV_TRY(check_cuda(cudaMalloc(&d, n * sizeof(float)), "cudaMalloc(session)"));
+  s->allocs.push_back(d);
+  *p = (float *)d;
+  return FAV_OK;
+}
+
+extern "C" {
+
+void fav_session_destroy(fav_session_t *s) {
+  if (!s) return;
+  cudaDeviceSynchronize();
+  for (void *p : s->allocs) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (s->in[i].uploaded) cudaEventDestroy(s->in[i].uploaded);
+    if (s->in[i].consumed) cudaEventDestroy(s->in[i].consumed);
+    if (s->computed[i]) cudaEventDestroy(s->computed[i]);
+    if (s->downloaded[i]) cudaEventDestroy(s->downloaded[i]);
+  }
+  if (s->t0) cudaEventDestroy(s->t0);
+  if (s->t1) cudaEventDestroy(s->t1);
+  if (s->s_h2d) cudaStreamDestroy(s->s_h2d);
+  if (s->s_comp) cudaStreamDestroy(s->s_comp);
+  if (s->s_d2h) cudaStreamDestroy(s->s_d2h);
+  delete s;
+}
+
+int fav_session_create(fav_net_t *net, int H, int W, fav_session_t **out) {
+  FAV_REQUIRE(net && out, "fav_session_create: null argument");
+  FAV_REQUIRE(H > 0 && W > 0, "fav_session_create: empty frame");
+  FAV_TRY(require_device());
+  std::unique_ptr<fav_session, void (*)(fav_session *)> s(new fav_session(), fav_session_destroy);
+  s->net = net; s->H = H; s->W = W;
+  FAV_TRY(check_cuda(cudaStreamCreateWithFlags(&s->s_h2d, cudaStreamNonBlocking), "cudaStreamCreate"));
+  FAV_TRY(check_cuda(cudaStreamCreateWithFlags(&s->s_comp, cudaStreamNonBlocking), "cudaStreamCreate"));
+  FAV_TRY(check_cuda(cudaStreamCreateWithFlags(&s->s_d2h, cudaStreamNonBlocking), "cudaStreamCreate"));
+  const size_t HW = (size_t)H * W;
+  for (int i = 0; i < 2; ++i) {
+    FAV_TRY(s_alloc(s.get(), &s->in[i].content, 3 * HW));
+    FAV_TRY(s_alloc(s.get(), &s->in[i].flow, 2 * HW));
+    FAV_TRY(s_alloc(s.get(), &s->in[i].flow_fw, 2 * HW));
+    FAV_TRY(s_alloc(s.get(), &s->in[i].cert_raw, HW));
+    FAV_TRY(s_alloc(s.get(), &s->in[i].cert, HW));
+    FAV_TRY(s_alloc(s.get(), &s->out[i], 3 * HW));
+    FAV_TRY(check_cuda(cudaEventCreateWithFlags(&s->in[i].uploaded, cudaEventDisableTiming), "cudaEventCreate"));
+    FAV_TRY(check_cuda(cudaEventCreateWithFlags(&s->in[i].consumed, cudaEventDisableTiming), "cudaEventCreate"));
+    FAV_TRY(check_cuda(cudaEventCreateWithFlags(&s->computed[i], cudaEventDisableTiming), "cudaEventCreate"));
+    FAV_TRY(check_cuda(cudaEventCreateWithFlags(&s->downloaded[i], cudaEventDisableTiming), "cudaEventCreate"));
+  }
+  FAV_TRY(check_cuda(cudaEventCreate(&s->t0), "cudaEventCreate"));
+  FAV_TRY(check_cuda(cudaEventCreate(&s->t1), "cudaEventCreate"));
+  *out = s.release();
+  return FAV_OK;
+}
+
+// mode 0: first frame; 1: cert given; 2: cert from the flow pair
+static int session_step(fav_session *s, int mode, const float *content_host, const float *flow_a, const float *flow_b,
+                        const float *cert_host, int min_filter_r, int border_mode, float *out_host) {
+  FAV_REQUIRE(s && content_host && out_host, "fav_session: null argument");
+  FAV_REQUIRE(mode == 0 || s->have_prev, "fav_session_run_next_image: no previous frame (call run_image first)");
+  FAV_REQUIRE(min_filter_r == 0 || ((min_filter_r & 1) && min_filter_r <= 15), "occlusions_min_filter must be odd <= 15");
+  const int H = s->H, W = s->W;
+  const size_t HW = (size_t)H * W;
+  const int si = (int)(s->frame & 1), so = (int)(s->frame & 1);
+  fav_session::InSet &in = s->in[si];
+  // ---- H2D (waits until the frame that last used this input set has consumed it)
+  if (in.used) FAV_TRY(check_cuda(cudaStreamWaitEvent(s->s_h2d, in.consumed, 0), "cudaStreamWaitEvent"));
+  FAV_TRY(check_cuda(cudaMemcpyAsync(in.content, content_host, 3 * HW * 4, cudaMemcpyHostToDevice, s->s_h2d), "H2D content"));
+  if (mode == 1) {
+    FAV_TRY(check_cuda(cudaMemcpyAsync(in.flow, flow_a, 2 * HW * 4, cudaMemcpyHostToDevice, s->s_h2d), "H2D flow"));
+    FAV_TRY(check_cuda(cudaMemcpyAsync(in.cert_raw, cert_host, HW * 4, cudaMemcpyHostToDevice, s->s_h2d), "H2D cert"));
+  } else if (mode == 2) {
+    // backward flow arrives in .flo order (u,v); the warp wants (dy,dx) = (v,u): swap planes while uploading
+    FAV_TRY(check_cuda(cudaMemcpyAsync(in.flow + HW, flow_a, HW * 4, cudaMemcpyHostToDevice, s->s_h2d), "H2D flow u"));
+    FAV_TRY(check_cuda(cudaMemcpyAsync(in.flow, flow_a + HW, HW * 4, cudaMemcpyHostToDevice, s->s_h2d), "H2D flow v"));
+    FAV_TRY(check_cuda(cudaMemcpyAsync(in.flow_fw, flow_b, 2 * HW * 4, cudaMemcpyHostToDevice, s->s_h2d), "H2D flow fw"));
+  }
+  FAV_TRY(check_cuda(cudaEventRecord(in.uploaded, s->s_h2d), "cudaEventRecord"));
+  // ---- compute
+  FAV_TRY(check_cuda(cudaStreamWaitEvent(s->s_comp, in.uploaded, 0), "cudaStreamWaitEvent"));
+  if (s->out_used[so])  // the D2H of the frame that last wrote out[so] must be finished
+    FAV_TRY(check_cuda(cudaStreamWaitEvent(s->s_comp, s->downloaded[so], 0), "cudaStreamWaitEvent"));
+  FAV_TRY(check_cuda(cudaEventRecord(s->t0, s->s_comp), "cudaEventRecord"));
+  if (mode == 0) {
+    FAV_TRY(fav_run_image(s->net, in.content, nullptr, H, W, s->out[so], s->s_comp));
+  } else {
+    const float *cert = in.cert_raw;
+    if (mode == 2) {
+      // flow1 = backward flow (u at flow+HW, v at flow), flow2 = forward flow; 3-argument mode
+      FAV_TRY(launch_consistency(in.flow + HW, in.flow, in.flow_fw, in.flow_fw + HW, nullptr, nullptr, 0.f, nullptr,
+                                 in.cert_raw, W, H, s->s_comp));
+    }
+    if (min_filter_r > 1) {  // utils.min_filter(cert, opt.occlusions_min_filter)  core.lua:207
+      FAV_TRY(launch_min_filter(in.cert_raw, in.cert, 1, H, W, min_filter_r, s->s_comp));
+      cert = in.cert;
+    }
+    FAV_TRY(fav_run_next_image(s->net, in.content, s->out[so ^ 1], in.flow, cert, nullptr, nullptr, H, W, border_mode,
+                               s->out[so], s->s_comp));
+  }
+  FAV_TRY(check_cuda(cudaEventRecord(s->t1, s->s_comp), "cudaEventRecord"));
+  FAV_TRY(check_cuda(cudaEventRecord(in.consumed, s->s_comp), "cudaEventRecord"));
+  FAV_TRY(check_cuda(cudaEventRecord(s->computed[so], s->s_comp), "cudaEventRecord"));
+  in.used = true;
+  // ---- D2H
+  FAV_TRY(check_cuda(cudaStreamWaitEvent(s->s_d2h, s->computed[so], 0), "cudaStreamWaitEvent"));
+  FAV_TRY(check_cuda(cudaMemcpyAsync(out_host, s->out[so], 3 * HW * 4, cudaMemcpyDeviceToHost, s->s_d2h), "D2H out"));
+  FAV_TRY(check_cuda(cudaEventRecord(s->downloaded[so], s->s_d2h), "cudaEventRecord"));
+  s->out_used[so] = true;
+  s->have_prev = true;
+  s->frame++;
+  return FAV_OK;
+}
+
+int fav_session_run_image(fav_session_t *s, const float *content_host, float *out_host) {
+  return session_step(s, 0, content_host, nullptr, nullptr, nullptr, 0, 0, out_host);
+}
+
+int fav_session_run_next_image(fav_session_t *s, const float *content_host, const float *flow_host,
+                               const float *cert_host, int min_filter_r, int border_mode, float *out_host) {
+  FAV_REQUIRE(flow_host && cert_host, "fav_session_run_next_image: null flow / cert");
+  return session_step(s, 1, content_host, flow_host, nullptr, cert_host, min_filter_r, border_mode, out_host);
+}
+
+int fav_session_run_next_image_flows(fav_session_t *s, const float *content_host, const float *flow_bw_uv_host,
+                                     const float *flow_fw_uv_host, int min_filter_r, int border_mode, float *out_host) {
+  FAV_REQUIRE(flow_bw_uv_host && flow_fw_uv_host, "fav_session_run_next_image_flows: null flow");
+  return session_step(s, 2, content_host, flow_bw_uv_host, flow_fw_uv_host, nullptr, min_filter_r, border_mode, out_host);
+}
+
+int fav_session_sync(fav_session_t *s) {
+  FAV_REQUIRE(s, "fav_session_sync: null session");
+  FAV_TRY(check_cuda(cudaStreamSynchronize(s->s_h2d), "sync h2d"));
+  FAV_TRY(check_cuda(cudaStreamSynchronize(s->s_comp), "sync compute"));
+  return check_cuda(cudaStreamSynchronize(s->s_d2h), "sync d2h");
+}
+
+float fav_session_last_gpu_ms(fav_session_t *s) {
+  if (!s || !s->t0 || !s->t1) return -1.f;
+  if (cudaEventSynchronize(s->t1) != cudaSuccess) return -1.f;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, s->t0, s->t1) != cudaSuccess) return -1.f;
+  return ms;
+}
+}

@@ -1,0 +1,51 @@
+"""Host-buffer frame loop (fav_session_*, include/fav.h): the reference-facing call whose e2e time bench.py reports."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .models_video import StyleNet
+
+
+def _hp(a):
+    if isinstance(a, torch.Tensor):
+        assert not a.is_cuda and a.is_contiguous() and a.dtype == torch.float32
+        return C.c_void_p(a.data_ptr())
+    assert isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Session:
+    def __init__(self, net: StyleNet, H: int, W: int):
+        h = C.c_void_p()
+        _lib.check(_lib.lib.fav_session_create(net._h, H, W, C.byref(h)))
+        self._h, self.net, self.H, self.W = h, net, H, W
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _lib is not None and getattr(_lib, "lib", None) is not None:
+            _lib.lib.fav_session_destroy(h)
+            self._h = None
+
+    def run_image(self, content_host, out_host):
+        _lib.check(_lib.lib.fav_session_run_image(self._h, _hp(content_host), _hp(out_host)))
+
+    def run_next_image(self, content_host, flow_host, cert_host, out_host, min_filter_r=7,
+                       border_mode=_lib.BORDER_PER_TAP):
+        _lib.check(_lib.lib.fav_session_run_next_image(self._h, _hp(content_host), _hp(flow_host), _hp(cert_host),
+                                                       int(min_filter_r), border_mode, _hp(out_host)))
+
+    def run_next_image_flows(self, content_host, flow_bw_uv_host, flow_fw_uv_host, out_host, min_filter_r=7,
+                             border_mode=_lib.BORDER_PER_TAP):
+        _lib.check(_lib.lib.fav_session_run_next_image_flows(self._h, _hp(content_host), _hp(flow_bw_uv_host),
+                                                             _hp(flow_fw_uv_host), int(min_filter_r), border_mode,
+                                                             _hp(out_host)))
+
+    def sync(self):
+        _lib.check(_lib.lib.fav_session_sync(self._h))
+
+    def last_gpu_ms(self) -> float:
+        return float(_lib.lib.fav_session_last_gpu_ms(self._h))

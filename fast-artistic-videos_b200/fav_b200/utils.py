@@ -1,0 +1,45 @@
+"""fast_artistic_video/utils.lua: warp_image (:141-149), min_filter (:161-169), wait_for_file (:74-80)."""
+from __future__ import annotations
+
+import os
+import time
+
+import torch
+
+from . import _lib
+from .stn import BilinearSamplerBDHW
+
+
+def warp_image(img: torch.Tensor, map: torch.Tensor, dtype: str = "torch.CudaTensor") -> torch.Tensor:
+    """utils.warp_image(img, map, dtype) (utils.lua:141-149).
+
+    dtype 'torch.CudaTensor' -> the reference's CUDA semantics (per-corner zero fill, BilinearSamplerBDHW.cu);
+    dtype 'torch.FloatTensor' -> the reference's CPU semantics (image.warp(...,'bilinear',true,'pad',0)).
+    Both run on the GPU here; only the border rule differs.
+    """
+    mode = _lib.BORDER_PER_TAP if dtype == "torch.CudaTensor" else _lib.BORDER_PAD_PIXEL
+    return BilinearSamplerBDHW(mode).forward((img.contiguous(), map.contiguous()))
+
+
+def min_filter(batch: torch.Tensor, r: int, dtype=None) -> torch.Tensor:
+    """utils.min_filter(batch, r, dtype) (utils.lua:161-169): 1 - maxpool_{r x r, s1, pad r//2}(1 - x)."""
+    x = batch.contiguous()
+    assert x.dtype == torch.float32 and x.dim() >= 2
+    H, W = x.shape[-2:]
+    n = x.numel() // (H * W)
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib.fav_min_filter(_lib.dptr(x), _lib.dptr(out), n, H, W, int(r), _lib.stream_ptr()))
+    return out
+
+
+def file_exists(name: str) -> bool:  # utils.lua:68-71
+    return os.path.isfile(name)
+
+
+def wait_for_file(path: str, poll_s: float = 1.0) -> None:
+    """utils.wait_for_file (utils.lua:74-80): block until the producer (flow / occlusion job) wrote the file."""
+    if not file_exists(path):
+        print(f'Waiting for file "{path}"')
+        while not file_exists(path):
+            time.sleep(poll_s)
+        time.sleep(poll_s)

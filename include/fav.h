@@ -1,0 +1,199 @@
+/*
+ * fav.h -- C ABI of libfav_b200.so: the B200-native (sm_100a) replacement for the per-frame
+ * video-style-transfer hot path of manuelruder/fast-artistic-videos (reference @ bf1d072).
+ *
+ * Plain C: raw DEVICE pointers (unless a parameter says "host"), sizes, element strides and a
+ * cudaStream_t passed as void*.  No torch / THC / Lua types.  Every entry point returns an int
+ * status (FAV_OK == 0); fav_last_error() returns a thread-local message for the last failure.
+ * Nothing here allocates or frees caller tensors; kernels are enqueued on the given stream and
+ * NOT synchronised (same contract as the reference: BilinearSamplerBDHW.cu:123,146-150).
+ *
+ * Each declaration cites the reference interface it replaces (path:line under the reference).
+ * The reference-side binding a maintainer would add is shown in INTEGRATION.md; the Lua shim
+ * source that registers these under the reference's names is fast-artistic-videos_b200/lua/.
+ *
+ * Tensor conventions (the reference's): fp32, "BDHW" = NCHW.  Optical flow in the Lua loader's
+ * layout: channel 0 = dy (v), channel 1 = dx (u), pixel offsets (flowFileLoader.lua:31-32,
+ * BilinearSamplerBDHW.cu:72-73).  The occlusion checker takes the .flo-native layout
+ * (plane 0 = u, plane 1 = v; consistencyChecker.cpp:29-33).
+ */
+#ifndef FAV_H_
+#define FAV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FAV_API __attribute__((visibility("default")))
+
+/* status codes */
+enum {
+  FAV_OK = 0,
+  FAV_ERR_INVALID = 1,         /* bad argument (the Lua asserts of BilinearSamplerBDHW.lua:26-42) */
+  FAV_ERR_CUDA = 2,            /* cudaGetLastError() != success (BilinearSamplerBDHW.cu:146-150)   */
+  FAV_ERR_NOT_IMPLEMENTED = 3, /* gradient entry points (BilinearSamplerBDHW.cu:171-184)           */
+  FAV_ERR_IO = 4,
+  FAV_ERR_UNSUPPORTED = 5,     /* arch token / device the sm_100a path does not cover              */
+  FAV_ERR_NO_DEVICE = 6        /* no CUDA device: there is NO CPU fallback, calls fail loudly      */
+};
+
+/* warp border semantics */
+enum {
+  FAV_BORDER_PER_TAP = 0,  /* CUDA path: each out-of-range corner contributes 0
+                              (BilinearSamplerBDHW.cu:92-101)                                       */
+  FAV_BORDER_PAD_PIXEL = 1 /* CPU path of utils.warp_image: image.warp(...,'pad',0)
+                              (fast_artistic_video/utils.lua:145-147): whole pixel = pad value when
+                              the source coordinate is off-image, else clamped neighbours            */
+};
+
+FAV_API const char *fav_last_error(void);
+FAV_API int fav_version(void);
+/* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
+FAV_API uint64_t fav_launch_count(void);
+FAV_API int fav_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a-1  nn.BilinearSamplerBDHW
+ * replaces cunn_BilinearSamplerBDHW_updateOutput        stnbdhw/BilinearSamplerBDHW.cu:111-152
+ *      (kernel BilinearSamplerBDHW_bilinearSamplingFromGrid                         :48-109)
+ * img  [B,C,Hin,Win], grid [B,2,Hout,Wout] (ch0 = dy, ch1 = dx), out [B,C,Hout,Wout];
+ * *_stride are ELEMENT strides (arbitrary strides honoured, as the reference kernel does :123-142).
+ * ------------------------------------------------------------------------------------------- */
+FAV_API int fav_bilinear_sampler_bdhw_update_output(const float *img, const int64_t img_size[4],
+                                                    const int64_t img_stride[4], const float *grid,
+                                                    const int64_t grid_size[4],
+                                                    const int64_t grid_stride[4], float *out,
+                                                    const int64_t out_stride[4], int border_mode,
+                                                    void *stream);
+/* replaces cunn_BilinearSamplerBDHW_updateGradInput / _updateGradInputOnlyGrid (:171-184):
+ * always FAV_ERR_NOT_IMPLEMENTED with the reference's message. */
+FAV_API int fav_bilinear_sampler_bdhw_update_grad_input(void);
+FAV_API int fav_bilinear_sampler_bdhw_update_grad_input_only_grid(void);
+
+/* a-2  utils.warp_image(img, map, dtype)           fast_artistic_video/utils.lua:141-149
+ * img [C,Hin,Win] contiguous, flow [2,Hout,Wout] contiguous, out [C,Hout,Wout]. */
+FAV_API int fav_warp_image(const float *img, int C, int Hin, int Win, const float *flow, int Hout,
+                           int Wout, float *out, int border_mode, void *stream);
+
+/* a-5  utils.min_filter(batch, r)                  fast_artistic_video/utils.lua:161-169
+ * in/out [n,H,W] contiguous: 1 - maxpool_{r x r, stride 1, pad floor(r/2)}(1 - x). r odd, <= 15. */
+FAV_API int fav_min_filter(const float *in, float *out, int n, int H, int W, int r, void *stream);
+
+/* a-6  preprocess.vgg.preprocess / deprocess       fast_artistic_video/preprocess.lua:57-62, :66-71
+ * in/out [N,3,H,W] contiguous. */
+FAV_API int fav_vgg_preprocess(const float *in, float *out, int N, int H, int W, void *stream);
+FAV_API int fav_vgg_deprocess(const float *in, float *out, int N, int H, int W, void *stream);
+
+/* a-8 (front half)  the 7-channel net input of run_next_image
+ *                                               fast_artistic_video_core.lua:161-171
+ * ONE fused kernel: warp(prev, flow) -> preprocess -> * cert -> + fill, preprocess(content), concat.
+ * content, prev [3,H,W] RGB; flow [2,H,W] (dy,dx); cert [H,W]; fill [3,H,W] or NULL ('vgg-mean',
+ * generate_fill :108-117); flow_mask [H,W] or NULL (:169); out7 [7,H,W]. */
+FAV_API int fav_temporal_input(const float *content, const float *prev, const float *flow,
+                               const float *cert, const float *fill, const float *flow_mask,
+                               float *out7, int H, int W, int border_mode, void *stream);
+/* a-9 (front half)  run_image with model_img == nil: cat(pre(img), fill(cert=0), zeros)  :133-137 */
+FAV_API int fav_first_frame_input(const float *content, const float *fill, float *out7, int H, int W,
+                                  void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a-11  checkConsistency                       consistencyChecker/consistencyChecker.cpp:80-134
+ * flow1, flow2: [2,H,W] planar, plane 0 = u, plane 1 = v (readMiddlebury :16-36).
+ * structure: [H,W] normalised corner measure or NULL (3-argument mode, :161-163);
+ * structure_avg: CMatrix::avg of it (CMatrix.h:1245-1251), ignored when structure == NULL.
+ * reliable_u8 [H,W]: the PGM payload in {0,255} (clip + (char) cast, :169-171, CMatrix.h:1068), may be NULL.
+ * cert_f32   [H,W]: reliable/255 as image.load(pgm,1) yields it (fast_artistic_video.lua:103), may be NULL.
+ * Evaluated with the reference's mixed float/double arithmetic: results are bit-identical.
+ * ------------------------------------------------------------------------------------------- */
+FAV_API int fav_consistency_check(const float *flow1, const float *flow2, const float *structure,
+                                  float structure_avg, uint8_t *reliable_u8, float *cert_f32, int W,
+                                  int H, void *stream);
+/* a-12  computeCorners + normalize(0,1) + avg   consistencyChecker.cpp:39-78,158-159; CMatrix.h:721-736
+ * image [Z,H,W] planes with values 0..255 (CTensor::readFromPPM, CTensor.h:888-936); corners [H,W];
+ * workspace: device scratch of fav_compute_corners_workspace(Z,W,H) bytes; avg_out: DEVICE float. */
+FAV_API size_t fav_compute_corners_workspace(int Z, int W, int H);
+FAV_API int fav_compute_corners(const float *image, int Z, int W, int H, float rho, float *corners,
+                                float *avg_out, void *workspace, void *stream);
+
+/* a-3 / a-13  Middlebury .flo (HOST side)          flowFileLoader.lua:17-37, consistencyChecker.cpp:16-36
+ * layout 0: [dy,dx] (Lua loader order); layout 1: [u,v] (checker order). out: host [2,H,W]. */
+FAV_API int fav_flo_read_header(const char *path, int *W, int *H);
+FAV_API int fav_flo_read(const char *path, float *out_host, int layout);
+
+/* ---------------------------------------------------------------------------------------------
+ * a-N*  the stylization network                fast_artistic_video/models_video.lua:55-140
+ * fav_net_create parses the reference's arch string (tokens cXsY-Z, dX, uX, UX, RX) with
+ * padding_type 'reflect-start' (train_video.lua:25; the lazily inserted SpatialReflectionPadding
+ * :319-324 is part of the net), InstanceNormalization (InstanceNormalization.lua:33-53), Tanh,
+ * MulConstant(tanh_constant), TotalVariation (identity fwd).  Parameters are addressed by name:
+ *   "l<i>.weight|bias" conv (Torch layout: conv [Cout,Cin,k,k]; full conv [Cin,Cout,k,k]),
+ *   "l<i>.n.weight|bias" IN after layer i, "l<i>.c1|c2.*", "l<i>.n1|n2.*" inside residual block i.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fav_net fav_net_t;
+
+FAV_API int fav_net_create(const char *arch, const char *padding_type, float tanh_constant, int in_dim,
+                           fav_net_t **out);
+FAV_API void fav_net_destroy(fav_net_t *net);
+FAV_API int fav_net_num_params(const fav_net_t *net);
+/* name_out: >= 64 bytes; shape_out[4] (unused dims = 1); returns element count via *numel */
+FAV_API int fav_net_param_info(const fav_net_t *net, int index, char *name_out, int64_t shape_out[4],
+                               int64_t *numel);
+FAV_API int fav_net_set_param(fav_net_t *net, const char *name, const float *host_data, int64_t numel);
+/* upload + repack weights for the tcgen05 path; must be called once after all set_param calls */
+FAV_API int fav_net_finalize(fav_net_t *net);
+/* conv implementation: 0 = tcgen05 implicit GEMM (default), 1 = CUDA-core debug comparator */
+FAV_API int fav_net_set_conv_impl(fav_net_t *net, int impl);
+/* model:forward(input)                          fast_artistic_video_core.lua:138,172
+ * in7 [in_dim,H,W] device fp32 -> out3 [3,H,W] device fp32 in net space (before deprocess). */
+FAV_API int fav_net_forward(fav_net_t *net, const float *in7, int H, int W, float *out3, void *stream);
+/* debugging / per-layer parity: copy activation after layer `index` (post IN/ReLU) to NCHW fp32.
+ * Valid after a forward at the same H,W.  out [C,Hl,Wl]; sizes returned through C/Hl/Wl. */
+FAV_API int fav_net_layer_output(fav_net_t *net, int index, float *out, int *C, int *Hl, int *Wl,
+                                 void *stream);
+
+/* a-9  run_image (frame 1, model_img == nil)    fast_artistic_video_core.lua:121-158
+ * content [3,H,W] RGB [0,1] -> out_rgb [3,H,W] = deprocess(model_vid(...))[1]. */
+FAV_API int fav_run_image(fav_net_t *net, const float *content, const float *fill, int H, int W,
+                          float *out_rgb, void *stream);
+/* a-8  run_next_image                           fast_artistic_video_core.lua:161-180
+ * (+ func_make_last_frame_warped, fast_artistic_video.lua:153-158: the warp of prev_rgb by flow) */
+FAV_API int fav_run_next_image(fav_net_t *net, const float *content, const float *prev_rgb,
+                               const float *flow, const float *cert, const float *fill,
+                               const float *flow_mask, int H, int W, int border_mode, float *out_rgb,
+                               void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a-10  frame loop with HOST buffers (the reference-facing call bench.py's e2e times)
+ *                                               fast_artistic_video_core.lua:189-229
+ * A session owns device + pinned staging buffers for one H x W stream on one GPU, keeps the
+ * recurrent state last_frame_stylized on the device as unclamped fp32 (fast_artistic_video.lua:169)
+ * and overlaps H2D / compute / D2H on three streams.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fav_session fav_session_t;
+FAV_API int fav_session_create(fav_net_t *net, int H, int W, fav_session_t **out);
+FAV_API void fav_session_destroy(fav_session_t *s);
+/* frame 1 (func_is_single_image): host content [3,H,W] fp32 -> host out [3,H,W] fp32 */
+FAV_API int fav_session_run_image(fav_session_t *s, const float *content_host, float *out_host);
+/* frames >= 2: host content, host flow [2,H,W] (dy,dx), host cert [H,W] fp32 in [0,1] BEFORE the
+ * min filter (func_load_cert output); min_filter_r = opt.occlusions_min_filter (0 = skip). */
+FAV_API int fav_session_run_next_image(fav_session_t *s, const float *content_host,
+                                       const float *flow_host, const float *cert_host,
+                                       int min_filter_r, int border_mode, float *out_host);
+/* same, but the certainty is computed on the GPU from the forward/backward flow pair
+ * (fused consistency check, 3-argument mode): flow_bw/flow_fw host [2,H,W] in .flo (u,v) order. */
+FAV_API int fav_session_run_next_image_flows(fav_session_t *s, const float *content_host,
+                                             const float *flow_bw_uv_host,
+                                             const float *flow_fw_uv_host, int min_filter_r,
+                                             int border_mode, float *out_host);
+/* block until every queued frame has landed in its out_host buffer */
+FAV_API int fav_session_sync(fav_session_t *s);
+/* device time (ms, CUDA events on the compute stream) of the last frame's GPU work */
+FAV_API float fav_session_last_gpu_ms(fav_session_t *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAV_H_ */

@@ -1,0 +1,174 @@
+// conv_emu.cu -- TEST INFRASTRUCTURE: a CPU emulation of conv_tc_kernel's ADDRESSING (bulk-copy segments, patch
+// stages, K-step tables, canonical no-swizzle K-major UMMA operand layout, packed weight chunks, output
+// placement) driven by the very same host planning code the product uses (csrc/conv_plan.hpp).  It checks the
+// tables against a direct convolution, so that table / packing bugs are caught here on the CPU and GPU time is
+// spent on hardware semantics only.  Not part of libfav_b200.so.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <random>
+#include <vector>
+
+#include "../../fast-artistic-videos_b200/csrc/conv_plan.hpp"
+
+namespace fav {
+static char g_err[512];
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+std::atomic<uint64_t> g_launches{0};
+size_t conv_tc_smem_bytes(const ConvJob &job) {  // mirror of conv_tc.cu (kNA=2, kNB=4)
+  return (size_t)2 * 2 * job.stage16 * 16 + (size_t)4 * job.chunk16 * 16 + 256;
+}
+}  // namespace fav
+
+using namespace fav;
+
+extern "C" const char *emu_last_error() { return fav::g_err; }
+
+// returns 0 on success; max_err = max |emulated - direct|, max_ref = max |direct|
+extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int transposed, int adj, int H, int W,
+                              unsigned seed, double *max_err, double *max_ref, int *smem_bytes, int *n_mma) {
+  ConvDef c;
+  init_conv_def(c, "emu", cin, cout, k, stride, pad, transposed != 0, adj);
+  build_phases(c);
+  std::mt19937 rng(seed);
+  std::uniform_real_distribution<float> U(-1.f, 1.f);
+  std::vector<float> w((size_t)cin * cout * k * k), x((size_t)cin * H * W);
+  for (auto &v : w) v = U(rng) * 0.1f;
+  for (auto &v : x) v = U(rng) * 3.f;
+  // operand (host mirror)
+  Operand op = operand_geometry(cin, H, W, &c);
+  std::vector<uint16_t> hi(op.elems16 * 8, 0), lo(op.elems16 * 8, 0);
+  std::vector<float> xq((size_t)cin * H * W);
+  for (int ci = 0; ci < cin; ++ci)
+    for (int y = 0; y < H; ++y)
+      for (int xx = 0; xx < W; ++xx) {
+        float v = x[((size_t)ci * H + y) * W + xx];
+        uint16_t hb = f2h_bits(v), lb = f2h_bits(v - h2f_bits(hb));
+        int64_t o = op.off16(op.padT + y, ci / 8, op.padL + xx) * 8 + ci % 8;
+        hi[o] = hb; lo[o] = lb;
+        xq[((size_t)ci * H + y) * W + xx] = h2f_bits(hb) + h2f_bits(lb);
+      }
+  int Ho, Wo;
+  conv_out_size(c, H, W, &Ho, &Wo);
+  std::vector<double> out((size_t)cout * Ho * Wo, 0.0), ref((size_t)cout * Ho * Wo, 0.0);
+  std::vector<char> written((size_t)Ho * Wo, 0);
+  int mma_count = 0;
+  size_t smem_max = 0;
+  for (ConvPhase &ph : c.phases) {
+    if (build_phase_tables(c, ph) != FAV_OK) return 1;
+    std::vector<uint16_t> pk = pack_phase_weights(c, ph, w);
+    ConvJob j;
+    if (fill_conv_job(c, ph, op, j) != FAV_OK) return 2;
+    smem_max = std::max(smem_max, conv_tc_smem_bytes(j));
+    if (conv_tc_smem_bytes(j) > 227 * 1024) { set_error("smem budget"); return 3; }
+    const int Npad = j.Npad;
+    std::vector<uint16_t> st_hi((size_t)j.stage16 * 8), st_lo((size_t)j.stage16 * 8);
+    std::vector<double> acc((size_t)kTileM * Npad);
+    for (int tile = 0; tile < j.ntiles; ++tile) {
+      const int y = tile / j.tiles_x, x0 = (tile % j.tiles_x) * kTileM;
+      std::fill(acc.begin(), acc.end(), 0.0);
+      for (int g = 0; g < j.ngroups; ++g) {
+        // A producer
+        std::fill(st_hi.begin(), st_hi.end(), (uint16_t)0x7e00);  // NaN poison: reading an unloaded byte is a bug
+        std::fill(st_lo.begin(), st_lo.end(), (uint16_t)0x7e00);
+        for (int ri = 0; ri < j.nrows; ++ri)
+          for (int cbi = 0; cbi < j.CbG; ++cbi)
+            for (int seg = 0; seg < j.nseg; ++seg) {
+              int64_t src16 = ((int64_t)(j.row_mul * y + j.grp_row[g][ri]) * j.a_Cb + j.grp_cb0[g] + cbi) * j.a_slab16 +
+                              j.seg_src16[seg] + x0;
+              int64_t dst16 = (int64_t)(ri * j.CbG + cbi) * j.pslab16 + j.seg_dst16[seg];
+              if (src16 < 0 || src16 + j.seg_len16[seg] > (int64_t)op.elems16) { set_error("src OOB"); return 4; }
+              if (dst16 + j.seg_len16[seg] > j.stage16) { set_error("dst OOB"); return 5; }
+              for (int64_t e = 0; e < (int64_t)j.seg_len16[seg] * 8; ++e) {
+                st_hi[dst16 * 8 + e] = hi[src16 * 8 + e];
+                st_lo[dst16 * 8 + e] = lo[src16 * 8 + e];
+              }
+            }
+        for (int ch = 0; ch < j.nchunks; ++ch) {
+          const uint16_t *chunk = pk.data() + (size_t)(g * j.nchunks + ch) * j.chunk16 * 8;
+          const uint16_t *b_hi = chunk, *b_lo = chunk + (size_t)j.spc * 2 * Npad * 8;
+          for (int st = 0; st < j.spc; ++st) {
+            const KStep ks = j.steps[ch * j.spc + st];
+            mma_count += 3;
+            for (int m = 0; m < kTileM; ++m)
+              for (int u = 0; u < 2; ++u) {
+                int64_t a16 = (int64_t)ks.a_off16 + (int64_t)u * ks.lbo16 + m;  // row m: +16 B (SBO = 8 rows * 16 B)
+                if (a16 >= j.stage16) { set_error("A desc OOB"); return 6; }
+                for (int i = 0; i < 8; ++i) {
+                  double ah = h2f_bits(st_hi[a16 * 8 + i]), al = h2f_bits(st_lo[a16 * 8 + i]);
+                  for (int n = 0; n < Npad; ++n) {
+                    int64_t b16 = (int64_t)st * 2 * Npad + (int64_t)u * Npad + n;
+                    double bh = h2f_bits(b_hi[b16 * 8 + i]), bl = h2f_bits(b_lo[b16 * 8 + i]);
+                    acc[(size_t)m * Npad + n] += ah * bh + al * bh + ah * bl;
+                  }
+                }
+              }
+          }
+        }
+      }
+      // epilogue placement
+      for (int m = 0; m < kTileM; ++m) {
+        int xx = x0 + m;
+        if (xx >= j.Wo) continue;
+        int yo = y * j.oy_mul + j.oy_off, xo = xx * j.ox_mul + j.ox_off;
+        if (yo >= Ho || xo >= Wo) { set_error("output OOB"); return 7; }
+        written[(size_t)yo * Wo + xo]++;
+        for (int n = 0; n < cout; ++n) out[((size_t)n * Ho + yo) * Wo + xo] = acc[(size_t)m * Npad + n];
+      }
+    }
+  }
+  for (char wv : written)
+    if (wv != 1) { set_error("output pixel written %d times", (int)wv); return 8; }
+  // direct reference
+  if (!transposed) {
+    for (int co = 0; co < cout; ++co)
+      for (int oy = 0; oy < Ho; ++oy)
+        for (int ox = 0; ox < Wo; ++ox) {
+          double s = 0;
+          for (int ci = 0; ci < cin; ++ci)
+            for (int ky = 0; ky < k; ++ky) {
+              int iy = oy * stride + ky - pad;
+              if (iy < 0 || iy >= H) continue;
+              for (int kx = 0; kx < k; ++kx) {
+                int ix = ox * stride + kx - pad;
+                if (ix < 0 || ix >= W) continue;
+                s += (double)w[(((size_t)co * cin + ci) * k + ky) * k + kx] * xq[((size_t)ci * H + iy) * W + ix];
+              }
+            }
+          ref[((size_t)co * Ho + oy) * Wo + ox] = s;
+        }
+  } else {
+    for (int ci = 0; ci < cin; ++ci)
+      for (int iy = 0; iy < H; ++iy)
+        for (int ix = 0; ix < W; ++ix) {
+          double xv = xq[((size_t)ci * H + iy) * W + ix];
+          for (int ky = 0; ky < k; ++ky) {
+            int oy = iy * stride - pad + ky;
+            if (oy < 0 || oy >= Ho) continue;
+            for (int kx = 0; kx < k; ++kx) {
+              int ox = ix * stride - pad + kx;
+              if (ox < 0 || ox >= Wo) continue;
+              for (int co = 0; co < cout; ++co)
+                ref[((size_t)co * Ho + oy) * Wo + ox] += xv * w[(((size_t)ci * cout + co) * k + ky) * k + kx];
+            }
+          }
+        }
+  }
+  double me = 0, mr = 0;
+  for (size_t i = 0; i < ref.size(); ++i) {
+    double d = std::fabs(out[i] - ref[i]);
+    if (!(d <= 1e300)) d = 1e300;  // NaN -> huge
+    me = std::max(me, d);
+    mr = std::max(mr, std::fabs(ref[i]));
+  }
+  *max_err = me; *max_ref = mr;
+  if (smem_bytes) *smem_bytes = (int)smem_max;
+  if (n_mma) *n_mma = mma_count;
+  return 0;
+}
