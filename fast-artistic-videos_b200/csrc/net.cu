@@ -296,11 +296,43 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
   return FAV_OK;
 }
 
-static int run_plan(fav_net *net, Plan &pl, const float *in7, float *out3, int final_mode, cudaStream_t st) {
+struct ProfRec {
+  int kind;  // 0 pack, 1 conv, 2 in_stats(+finalize), 3 in_apply
+  float ms;
+  double work;  // conv: algorithmic FLOPs (logical channels); others: algorithmic bytes
+  char name[24];
+  cudaEvent_t e0, e1;
+};
+
+static int run_plan(fav_net *net, Plan &pl, const float *in7, float *out3, int final_mode, cudaStream_t st,
+                    std::vector<ProfRec> *prof = nullptr) {
+  auto begin = [&](int kind, double work, const std::string &name) -> int {
+    if (!prof) return FAV_OK;
+    ProfRec r;
+    r.kind = kind; r.ms = 0; r.work = work;
+    snprintf(r.name, sizeof(r.name), "%s", name.c_str());
+    FAV_TRY(check_cuda(cudaEventCreate(&r.e0), "cudaEventCreate"));
+    FAV_TRY(check_cuda(cudaEventCreate(&r.e1), "cudaEventCreate"));
+    FAV_TRY(check_cuda(cudaEventRecord(r.e0, st), "cudaEventRecord"));
+    prof->push_back(r);
+    return FAV_OK;
+  };
+  auto end = [&]() -> int {
+    if (!prof) return FAV_OK;
+    return check_cuda(cudaEventRecord(prof->back().e1, st), "cudaEventRecord");
+  };
   FAV_TRY(check_cuda(cudaMemsetAsync(pl.stats, 0, pl.stats_bytes, st), "cudaMemsetAsync(stats)"));
+  FAV_TRY(begin(0, (double)pl.ops[0].H * pl.ops[0].W * (4.0 * net->in_dim + 32.0), "pack_input"));
   FAV_TRY(launch_pack_input(in7, net->in_dim, pl.H, pl.W, net->reflect_pad, pl.ops[0], st));
+  FAV_TRY(end());
   for (PlanStep &s : pl.steps) {
     if (s.kind == 0) {
+      {
+        const ConvDef &c = net->convs[s.conv];
+        const Operand &in = pl.ops[s.src];
+        double px = c.transposed ? (double)in.H * in.W : (double)s.raw.H * s.raw.W;
+        FAV_TRY(begin(1, 2.0 * c.cin * c.cout * c.k * c.k * px, c.name));
+      }
       if (net->conv_impl == 0) {
         for (ConvJob &j : s.tc) {
           if (j.final_mode) { j.final_mode = final_mode; j.out3 = out3; }
@@ -312,14 +344,20 @@ static int run_plan(fav_net *net, Plan &pl, const float *in7, float *out3, int f
           FAV_TRY(launch_conv_simt(j, st));
         }
       }
+      FAV_TRY(end());
     } else {
       const InDef &n = net->inorms[s.inorm];
       double *sums = pl.stats + s.stats_off;
       float *msb = pl.msb + (size_t)s.stats_off * 2;
+      const double elems = (double)n.C * s.raw.H * s.raw.W;
+      FAV_TRY(begin(2, 4.0 * elems, n.name + ".stats"));
       FAV_TRY(launch_in_stats(s.raw, sums, st));
       // InstanceNormalization.lua:21,39: eps = 1e-5, statistics over H*W of each (n, c)
       FAV_TRY(launch_in_finalize(sums, n.d_gamma, n.d_beta, n.C, (int64_t)s.raw.H * s.raw.W, 1e-5f, msb, st));
+      FAV_TRY(end());
+      FAV_TRY(begin(3, (s.skip >= 0 ? 12.0 : 8.0) * elems, n.name + ".apply"));
       FAV_TRY(launch_in_apply(s.raw, msb, s.relu, s.skip >= 0 ? &pl.ops[s.skip] : nullptr, 2, pl.ops[s.dst], st));
+      FAV_TRY(end());
     }
   }
   return FAV_OK;
@@ -466,6 +504,31 @@ int fav_net_forward(fav_net_t *net, const float *in7, int H, int W, float *out3,
   Plan *pl;
   FAV_TRY(build_plan(net, H, W, &pl));
   return run_plan(net, *pl, in7, out3, 1, (cudaStream_t)stream);
+}
+
+int fav_net_profile(fav_net_t *net, const float *in7, int H, int W, float *out3, int max_steps, int *kinds, float *ms,
+                    double *work, char *names24, int *n_out, void *stream) {
+  FAV_REQUIRE(net && in7 && out3 && kinds && ms && work && n_out, "fav_net_profile: null argument");
+  FAV_REQUIRE(net->finalized, "fav_net_profile: call fav_net_finalize first");
+  Plan *pl;
+  FAV_TRY(build_plan(net, H, W, &pl));
+  std::vector<ProfRec> prof;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = run_plan(net, *pl, in7, out3, 1, st, &prof);
+  if (rc == FAV_OK) rc = check_cuda(cudaStreamSynchronize(st), "fav_net_profile sync");
+  int n = 0;
+  for (ProfRec &r : prof) {
+    if (rc == FAV_OK && n < max_steps) {
+      cudaEventElapsedTime(&r.ms, r.e0, r.e1);
+      kinds[n] = r.kind; ms[n] = r.ms; work[n] = r.work;
+      if (names24) memcpy(names24 + 24 * n, r.name, 24);
+      ++n;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  *n_out = n;
+  return rc;
 }
 
 int fav_net_layer_output(fav_net_t *net, int index, float *out, int *C, int *Hl, int *Wl, void *stream) {

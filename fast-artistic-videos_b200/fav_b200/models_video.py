@@ -71,6 +71,21 @@ class StyleNet:
         _lib.check(_lib.lib.fav_net_forward(self._h, _lib.dptr(x), H, W, _lib.dptr(out), _lib.stream_ptr()))
         return out
 
+    def profile(self, input: torch.Tensor):
+        """One forward with per-step CUDA-event timing -> list of dict(kind, name, ms, work)."""
+        x = input.contiguous()
+        H, W = x.shape[-2:]
+        out = torch.empty((1, 3, H, W), dtype=torch.float32, device=x.device)
+        n_max = 256
+        kinds, ms, work = (C.c_int * n_max)(), (C.c_float * n_max)(), (C.c_double * n_max)()
+        names = C.create_string_buffer(24 * n_max)
+        n = C.c_int()
+        _lib.check(_lib.lib.fav_net_profile(self._h, _lib.dptr(x), H, W, _lib.dptr(out), n_max, kinds, ms, work, names,
+                                            C.byref(n), _lib.stream_ptr()))
+        kn = {0: "pack", 1: "conv", 2: "in_stats", 3: "in_apply"}
+        return [dict(kind=kn[kinds[i]], name=names.raw[24 * i:24 * i + 24].split(b"\0")[0].decode(), ms=float(ms[i]),
+                     work=float(work[i])) for i in range(n.value)]
+
     def layer_output(self, index: int) -> torch.Tensor:
         c, h, w = C.c_int(), C.c_int(), C.c_int()
         _lib.check(_lib.lib.fav_net_layer_output(self._h, index, None, C.byref(c), C.byref(h), C.byref(w), None))

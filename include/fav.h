@@ -149,6 +149,12 @@ FAV_API int fav_net_set_conv_impl(fav_net_t *net, int impl);
 /* model:forward(input)                          fast_artistic_video_core.lua:138,172
  * in7 [in_dim,H,W] device fp32 -> out3 [3,H,W] device fp32 in net space (before deprocess). */
 FAV_API int fav_net_forward(fav_net_t *net, const float *in7, int H, int W, float *out3, void *stream);
+/* measurement: one forward with CUDA events around every plan step (on `stream`, synchronised on return).
+ * kinds: 0 pack_input, 1 convolution (all phases), 2 IN statistics, 3 IN apply; ms: device time;
+ * work: algorithmic FLOPs (kind 1, logical channel counts) or algorithmic bytes (others);
+ * names24: max_steps x 24 chars (may be NULL). */
+FAV_API int fav_net_profile(fav_net_t *net, const float *in7, int H, int W, float *out3, int max_steps, int *kinds,
+                            float *ms, double *work, char *names24, int *n_out, void *stream);
 /* debugging / per-layer parity: copy activation after layer `index` (post IN/ReLU) to NCHW fp32.
  * Valid after a forward at the same H,W.  out [C,Hl,Wl]; sizes returned through C/Hl/Wl. */
 FAV_API int fav_net_layer_output(fav_net_t *net, int index, float *out, int *C, int *Hl, int *Wl,

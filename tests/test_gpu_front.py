@@ -1,0 +1,194 @@
+"""GPU parity tests of the temporal-consistency front end, through the C ABI (libfav_b200.so) vs the oracle.
+Bar: BIT-EXACT (the kernels evaluate in the reference's order with round-to-nearest intrinsics, no FMA contraction);
+the occlusion mask is additionally compared with the golden PGMs written by the reference's own binary."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from fav_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_golden  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def fav():
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    import fav_b200
+    from fav_b200 import _lib, consistencyChecker, preprocess, stn, utils  # noqa: F401
+
+    return fav_b200
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+SHAPES = [(64, 96), (100, 76), (97, 75), (33, 129), (256, 256)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("mode", ["torch.CudaTensor", "torch.FloatTensor"])
+def test_warp_image_bit_exact(fav, shape, mode):
+    from oracle import pyoracle
+
+    H, W = shape
+    img = synth.make_frame(H, W, 1)
+    for flow in (synth.checker_to_lua(synth.make_backward_flow(H, W, 2)), synth.stress_flow(H, W)):
+        g = fav.utils.warp_image(T(img), T(flow), mode).cpu().numpy()
+        o = pyoracle.warp_bdhw(img, flow) if mode == "torch.CudaTensor" else pyoracle.image_warp_pad(img, flow)
+        assert np.array_equal(g, o)
+
+
+def test_bilinear_sampler_module_surface(fav):
+    from oracle import pyoracle
+
+    rng = np.random.default_rng(0)
+    img = rng.uniform(size=(2, 5, 20, 28)).astype(np.float32)
+    grid = rng.uniform(-6, 6, size=(2, 2, 13, 36)).astype(np.float32)  # output size = grid size != input size
+    m = fav.stn.BilinearSamplerBDHW()
+    out = m.forward((T(img), T(grid)))
+    assert tuple(out.shape) == (2, 5, 13, 36)
+    assert np.array_equal(out.cpu().numpy(), pyoracle.warp_bdhw(img, grid))
+    out3 = m.forward((T(img[0]), T(grid[0])))  # 3-D input: batch dim added and removed (.lua:59-65,77-79)
+    assert out3.dim() == 3 and np.array_equal(out3.cpu().numpy(), pyoracle.warp_bdhw(img[0], grid[0]))
+    # single-channel mask warp (fast_artistic_video_vr.lua:171-177) and sentinel flow 99999 -> 0 (vr_helper.lua:10)
+    ones = np.ones((1, 20, 28), np.float32)
+    g = np.full((2, 20, 28), 99999.0, np.float32)
+    assert float(m.forward((T(ones), T(g))).abs().max()) == 0.0
+    with pytest.raises(AssertionError):
+        m.forward((T(img), T(grid[:, :1])))  # grids:size(2)==2
+    with pytest.raises(Exception) as e:
+        m.updateGradInput(None, None)
+    assert "Not implemented" in str(e.value)
+
+
+def test_warp_honours_arbitrary_strides(fav):
+    from fav_b200 import _lib
+    from oracle import pyoracle
+
+    rng = np.random.default_rng(1)
+    big = T(rng.uniform(size=(1, 3, 24, 40)).astype(np.float32))
+    img = big[:, :, 2:20, 3:35]  # non-contiguous view
+    grid = T(rng.uniform(-4, 4, size=(1, 2, 18, 32)).astype(np.float32))
+    out = torch.empty((1, 3, 18, 32), device="cuda")
+    _lib.check(_lib.lib.fav_bilinear_sampler_bdhw_update_output(
+        _lib.dptr(img), _lib.i64x4(img.shape), _lib.i64x4(img.stride()), _lib.dptr(grid), _lib.i64x4(grid.shape),
+        _lib.i64x4(grid.stride()), _lib.dptr(out), _lib.i64x4(out.stride()), 0, _lib.stream_ptr()))
+    assert np.array_equal(out.cpu().numpy(), pyoracle.warp_bdhw(img.cpu().numpy(), grid.cpu().numpy()))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_min_filter_pre_deprocess_bit_exact(fav, shape):
+    from oracle import pyoracle
+
+    H, W = shape
+    rng = np.random.default_rng(5)
+    for cert in ((rng.uniform(size=(H, W)) > 0.2).astype(np.float32), rng.uniform(size=(H, W)).astype(np.float32)):
+        for r in (3, 7):
+            assert np.array_equal(fav.utils.min_filter(T(cert), r).cpu().numpy(), pyoracle.min_filter(cert, r))
+    img = synth.make_frame(H, W, 3)
+    pre = fav.preprocess.vgg.preprocess(T(img)[None])
+    assert np.array_equal(pre.cpu().numpy()[0], pyoracle.vgg_preprocess(img))
+    assert np.array_equal(fav.preprocess.vgg.deprocess(pre).cpu().numpy()[0],
+                          pyoracle.vgg_deprocess(pyoracle.vgg_preprocess(img)))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("border", [0, 1])
+def test_fused_temporal_input_bit_exact(fav, shape, border):
+    from fav_b200 import _lib
+    from oracle import net_oracle, pyoracle
+
+    H, W = shape
+    c, p = synth.make_frame(H, W, 2), synth.make_frame(H, W, 1) * 1.2 - 0.1  # unclamped prior, ~[-0.1, 1.1]
+    flow = synth.checker_to_lua(synth.make_backward_flow(H, W, 2))
+    cert = net_oracle.make_cert(H, W, 2)
+    rng = np.random.default_rng(7)
+    fill = rng.normal(0, 40, size=(3, H, W)).astype(np.float32)
+    fmask = rng.uniform(size=(H, W)).astype(np.float32)
+    for (f, m) in ((None, None), (fill, fmask)):
+        tc, tp, tf, tcert = T(c), T(p), T(flow), T(cert)
+        tfill, tm = (T(f) if f is not None else None), (T(m) if m is not None else None)
+        out = torch.empty((7, H, W), device="cuda")
+        _lib.check(_lib.lib.fav_temporal_input(_lib.dptr(tc), _lib.dptr(tp), _lib.dptr(tf), _lib.dptr(tcert),
+                                               _lib.dptr(tfill), _lib.dptr(tm), _lib.dptr(out), H, W, border,
+                                               _lib.stream_ptr()))
+        ref = pyoracle.temporal_input(c, p, flow, cert, f, m, warp_mode=border)
+        assert np.array_equal(out.cpu().numpy(), ref)
+    out = torch.empty((7, H, W), device="cuda")
+    tc = T(c)
+    _lib.check(_lib.lib.fav_first_frame_input(_lib.dptr(tc), None, _lib.dptr(out), H, W, _lib.stream_ptr()))
+    assert np.array_equal(out.cpu().numpy(), pyoracle.first_frame_input(c))
+
+
+@pytest.mark.parametrize("case", make_golden.CONSISTENCY_CASES)
+def test_consistency_check_equals_reference_binary(fav, case):
+    H, W, idx, sigma, seed = case
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"consistency_{H}x{W}.npz"))
+    ref3 = np.unpackbits(g["ref3"])[: H * W].reshape(H, W).astype(np.uint8) * 255
+    ref4 = np.unpackbits(g["ref4"])[: H * W].reshape(H, W).astype(np.uint8) * 255
+    bw, fw, _, img255 = make_golden.consistency_inputs(H, W, idx, sigma, seed)
+    rel, cert = fav.consistencyChecker.check(T(bw), T(fw), want_cert=True)
+    assert np.array_equal(rel.cpu().numpy(), ref3)  # 0 flipped pixels vs the reference's own PGM
+    assert np.array_equal(cert.cpu().numpy(), ref3.astype(np.float32) / 255)
+    assert np.array_equal(fav.consistencyChecker.check(T(bw), T(fw), T(img255)).cpu().numpy(), ref4)
+
+
+def test_compute_corners_bit_exact(fav):
+    from oracle import pyoracle
+
+    _, _, _, img255 = make_golden.consistency_inputs(100, 76, 3, 0.6, 2)
+    corners, avg = fav.consistencyChecker.compute_corners(T(img255))
+    o = pyoracle.compute_corners(img255)
+    assert np.array_equal(corners.cpu().numpy(), o)
+    ref_avg = float(pyoracle.lib().orc_avg(o.ctypes.data_as(C.POINTER(C.c_float)), C.c_int64(o.size)))
+    assert float(avg.item()) == ref_avg
+
+
+def test_consistency_cli_contract(fav, tmp_path):
+    """argv contract of consistencyChecker.cpp:136-172 (used by makeOptFlow_*.sh:59-60)."""
+    from oracle import pyoracle
+
+    H, W = 64, 96
+    bw, fw, fr, _ = make_golden.consistency_inputs(H, W, 2, 0.4, 9)
+    d = str(tmp_path)
+    synth.write_flo(d + "/bw.flo", bw); synth.write_flo(d + "/fw.flo", fw); synth.write_ppm(d + "/f.ppm", fr)
+    assert fav.consistencyChecker.main(["consistencyChecker", d + "/bw.flo", d + "/fw.flo", d + "/r3.pgm"]) == 0
+    assert fav.consistencyChecker.main(["consistencyChecker", d + "/bw.flo", d + "/fw.flo", d + "/r4.pgm", d + "/f.ppm"]) == 0
+    img = fav.consistencyChecker.read_ppm_planes(d + "/f.ppm")
+    assert np.array_equal(synth.read_pgm(d + "/r3.pgm"), pyoracle.consistency(bw, fw))
+    assert np.array_equal(synth.read_pgm(d + "/r4.pgm"), pyoracle.consistency(bw, fw, img))
+
+
+def test_full_size_properties_720p(fav):
+    """At BASELINE.json's full size the oracle is too slow for the suite: size-independent properties instead."""
+    H, W = 720, 1280
+    img = T(synth.make_frame(H, W, 1))
+    zero = torch.zeros((2, H, W), device="cuda")
+    assert torch.equal(fav.utils.warp_image(img, zero), img)  # identity flow -> identity (weights exactly 1,0)
+    shift = zero.clone(); shift[1] += 3.0  # integer translation = exact pixel copy, zero fill at the border
+    w = fav.utils.warp_image(img, shift)
+    assert torch.equal(w[:, :, : W - 3], img[:, :, 3:]) and float(w[:, :, W - 3:].abs().max()) == 0.0
+    a, b = T(synth.make_frame(H, W, 2)), T(synth.make_frame(H, W, 3))
+    flow = T(synth.checker_to_lua(synth.make_backward_flow(H, W, 2)))
+    lin = fav.utils.warp_image(a + b, flow) - (fav.utils.warp_image(a, flow) + fav.utils.warp_image(b, flow))
+    assert float(lin.abs().max()) < 5e-6  # linearity in the image
+    cert = (torch.rand((H, W), device="cuda") > 0.1).float()
+    m = fav.utils.min_filter(cert, 7)
+    assert torch.equal(m, -torch.nn.functional.max_pool2d(-(cert[None, None]), 7, 1, 3)[0, 0])  # min filter of a {0,1} mask
+    assert bool((m <= cert).all())
+    bw, fw = T(synth.make_backward_flow(H, W, 2)), T(synth.make_forward_flow(H, W, 2))
+    rel = fav.consistencyChecker.check(bw, fw)
+    vals = torch.unique(rel).cpu().tolist()
+    assert set(vals) <= {0, 255} and 0 in vals and 255 in vals
+    zf = torch.zeros((2, H, W), device="cuda")
+    r0 = fav.consistencyChecker.check(zf, zf)  # zero flow is consistent except where x2/y2 leave the frame (:107)
+    assert bool((r0[: H - 1, : W - 1] == 255).all()) and bool((r0[H - 1] == 0).all()) and bool((r0[:, W - 1] == 0).all())

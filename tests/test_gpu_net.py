@@ -1,0 +1,181 @@
+"""GPU parity tests of the stylization net and the frame loop, through the C ABI, vs the fp64 PyTorch oracle and the
+committed golden clip.  Bar (BASELINE.json north_star): final deprocessed output within 1e-3 max-abs; the
+fp16-pair (hi/lo) tcgen05 path is expected near 1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from fav_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3  # north_star tolerance on the deprocessed [0,1] output
+
+
+@pytest.fixture(scope="module")
+def net():
+    assert torch.cuda.is_available()
+    from fav_b200 import models_video
+
+    return models_video.synthetic_model("candy")
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rand_input(H, W, seed=0):
+    from oracle import pyoracle
+
+    rng = np.random.default_rng(seed)
+    x7 = pyoracle.first_frame_input(synth.make_frame(H, W, 1))
+    x7[3:6] = rng.normal(0, 50, (3, H, W))
+    x7[6] = rng.uniform(0, 1, (H, W))
+    return x7.astype(np.float32)
+
+
+@pytest.mark.parametrize("shape", [(64, 96), (128, 200), (256, 256)])
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+def test_net_forward_and_every_layer_vs_fp64_oracle(net, shape, impl):
+    from oracle import net_oracle
+
+    H, W = shape
+    if impl == "simt" and H * W > 128 * 200:
+        pytest.skip("CUDA-core comparator only at small sizes")
+    net.set_conv_impl(impl)
+    try:
+        ora = net_oracle.NetOracle(style="candy", dtype=torch.float64)
+        x7 = rand_input(H, W)
+        taps = {}
+        ref = ora.forward(torch.from_numpy(x7)[None], taps)[0].numpy()
+        out = net.forward(T(x7)[None]).cpu().numpy()[0]
+        for i in range(len(ora.specs) - 1):  # every arch token's activation (post IN / ReLU / residual add)
+            r = taps[f"l{i}"][0].numpy()
+            g = net.layer_output(i).cpu().numpy()
+            assert g.shape == r.shape
+            assert np.abs(g - r).max() < 2e-4 * max(1.0, np.abs(r).max()), f"layer {i}"
+        assert np.abs(out - ref).max() / 255.0 < TOL / 10  # net space is 255x the [0,1] output
+    finally:
+        net.set_conv_impl("tcgen05")
+
+
+def test_tcgen05_agrees_with_cuda_core_comparator(net):
+    x = T(rand_input(96, 160, 3))[None]
+    a = net.forward(x)
+    net.set_conv_impl("simt")
+    try:
+        b = net.forward(x)
+    finally:
+        net.set_conv_impl("tcgen05")
+    assert float((a - b).abs().max()) / 255.0 < 5e-5
+
+
+def test_golden_clip_recurrence(net):
+    """3-frame clip through run_image / run_next_image with the occlusion mask computed on the GPU, vs the committed
+    fp64 oracle outputs (tests/golden/clip_64x96.npz); the recurrent state stays on the device."""
+    from fav_b200 import consistencyChecker, utils
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "clip_64x96.npz"))["outs"]
+    H, W = 64, 96
+    prev = None
+    for i in range(1, 4):
+        frame = T(synth.make_frame(H, W, i))
+        if i == 1:
+            out = net.run_image(frame)
+        else:
+            bw, fw = synth.make_backward_flow(H, W, i), synth.make_forward_flow(H, W, i)
+            _, cert = consistencyChecker.check(T(bw), T(fw), want_cert=True)
+            cert = utils.min_filter(cert, 7)
+            out = net.run_next_image(frame, prev, T(synth.checker_to_lua(bw)), cert)
+        err = float(np.abs(out.cpu().numpy() - g[i - 1]).max())
+        assert err < TOL, (i, err)
+        assert err < 1e-4, (i, err)  # what the hi/lo scheme actually delivers
+        prev = out
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (360, 640)])
+def test_run_next_image_teacher_forced(net, shape):
+    from oracle import net_oracle
+
+    H, W = shape
+    ora = net_oracle.NetOracle(style="candy", dtype=torch.float64)
+    f1, f2 = synth.make_frame(H, W, 1), synth.make_frame(H, W, 2)
+    ref1 = ora.run_image(f1)
+    out1 = net.run_image(T(f1)).cpu().numpy()
+    assert np.abs(out1 - ref1).max() < TOL / 10
+    cert = net_oracle.make_cert(H, W, 2)
+    flow = synth.checker_to_lua(synth.make_backward_flow(H, W, 2))
+    prev = ref1.astype(np.float32)
+    for border in (0, 1):  # CUDA and CPU warp semantics of utils.warp_image
+        ref2 = ora.run_next_image(f2, prev, flow, cert, warp_mode=border)
+        out2 = net.run_next_image(T(f2), T(prev), T(flow), T(cert), border_mode=border).cpu().numpy()
+        assert np.abs(out2 - ref2).max() < TOL / 10
+
+
+def test_session_host_buffer_loop_matches_device_api(net):
+    """fav_session_* (pinned host buffers, 3 streams) == the device-pointer API, and the fused-flow variant
+    (occlusion mask from the flow pair on the GPU) == explicit consistencyChecker + min_filter."""
+    from fav_b200 import consistencyChecker, session, utils
+
+    H, W = 96, 128
+    s = session.Session(net, H, W)
+    frames = [torch.from_numpy(synth.make_frame(H, W, i)).pin_memory() for i in range(1, 5)]
+    outs = [torch.empty((3, H, W)).pin_memory() for _ in range(4)]
+    s.run_image(frames[0], outs[0])
+    for i in range(2, 5):
+        bw = torch.from_numpy(synth.make_backward_flow(H, W, i)).pin_memory()
+        fw = torch.from_numpy(synth.make_forward_flow(H, W, i)).pin_memory()
+        s.run_next_image_flows(frames[i - 1], bw, fw, outs[i - 1], 7)
+    s.sync()
+    assert s.last_gpu_ms() > 0
+    prev = net.run_image(frames[0].cuda())
+    assert torch.equal(prev.cpu(), outs[0])
+    for i in range(2, 5):
+        bw, fw = synth.make_backward_flow(H, W, i), synth.make_forward_flow(H, W, i)
+        _, cert = consistencyChecker.check(T(bw), T(fw), want_cert=True)
+        prev = net.run_next_image(frames[i - 1].cuda(), prev, T(synth.checker_to_lua(bw)), utils.min_filter(cert, 7))
+        assert torch.equal(prev.cpu(), outs[i - 1]), i
+    # cert-given variant
+    s2 = session.Session(net, H, W)
+    o1, o2 = torch.empty((3, H, W)).pin_memory(), torch.empty((3, H, W)).pin_memory()
+    s2.run_image(frames[0], o1)
+    bw = synth.make_backward_flow(H, W, 2)
+    cert_raw = consistencyChecker.check(T(bw), T(synth.make_forward_flow(H, W, 2)), want_cert=True)[1].cpu().pin_memory()
+    s2.run_next_image(frames[1], torch.from_numpy(synth.checker_to_lua(bw)).pin_memory(), cert_raw, o2, 7)
+    s2.sync()
+    assert torch.equal(o2, outs[1])
+
+
+def test_full_size_720p_properties(net):
+    """BASELINE.json config 2 size.  The fp64 oracle needs ~10 s per 720p frame on a few cores, so one frame is checked
+    against it and the rest through properties: determinism, and invariance of frame 1 to the (masked) prior."""
+    from oracle import net_oracle
+
+    H, W = 720, 1280
+    f1 = synth.make_frame(H, W, 1)
+    a = net.run_image(T(f1))
+    b = net.run_image(T(f1))
+    assert torch.equal(a, b)  # deterministic (no atomics on the output path)
+    assert torch.isfinite(a).all()
+    ora = net_oracle.NetOracle(style="candy", dtype=torch.float32)
+    ref = ora.run_image(f1)
+    assert np.abs(a.cpu().numpy() - ref).max() < TOL / 10
+    # certainty 0 everywhere => the prior must not influence the output (core.lua:167: prior * cert)
+    flow = T(synth.checker_to_lua(synth.make_backward_flow(H, W, 2)))
+    zc = torch.zeros((H, W), device="cuda")
+    o1 = net.run_next_image(T(f1), a, flow, zc)
+    o2 = net.run_next_image(T(f1), torch.rand_like(a), flow, zc)
+    assert torch.equal(o1, o2) and torch.equal(o1, a)
+
+
+def test_error_behaviour(net):
+    from fav_b200 import _lib
+
+    with pytest.raises(_lib.FavError) as e:
+        net.forward(torch.zeros((1, 7, 50, 64), device="cuda"))  # H not a multiple of 4
+    assert e.value.status == _lib.FAV_ERR_INVALID
+    with pytest.raises(AssertionError):
+        net.forward(torch.zeros((1, 3, 64, 64), device="cuda"))
