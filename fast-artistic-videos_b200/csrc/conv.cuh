@@ -40,6 +40,10 @@ struct ConvJob {
   int chunk16;     // 2 * spc * 2 * Npad
   int Npad, Cout;
   const float *bias;
+  // x-fold (final 9x9, Cout <= 4): the filter COLUMNS are folded into N (n = kx*Cout + co), the patch has no
+  // horizontal halo, tiles advance by tile_dx = 128 - (KW-1) pixels and the epilogue adds the KW shifted partial
+  // sums through a shared-memory exchange buffer.  xfold_kw == 0: plain mode, tile_dx == 128.
+  int tile_dx, xfold_kw;
   // output placement: raw(y*oy_mul + oy_off, x*ox_mul + ox_off)
   float *raw;
   int raw_Cq, raw_Wp;

@@ -21,7 +21,9 @@ struct ConvPhase {
   std::vector<ConvTap> taps;
   int oy_off = 0, ox_off = 0;
   // tcgen05 tables (size independent)
-  int kind = 0;  // 0: stride-1 input, Cin_pad >= 16; 1: Cin_pad == 8 (tap pairing); 2: stride-2 parity-split input
+  int kind = 0;  // 0: stride-1 input, Cin_pad >= 16; 1: Cin_pad == 8 (tap pairing); 2: stride-2 parity-split input;
+                 // 3: x-fold (filter columns folded into N; final wide conv with Cout <= 4)
+  int Npad = 0;  // GEMM N of this phase
   int dxmin = 0, dxmax = 0;
   std::vector<int> rows;  // distinct dy, ascending
   int nrg = 1, nchg = 1, CbG = 1, rows_per_group = 1;
@@ -65,7 +67,20 @@ static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
     return -1;
   };
   const int nrows = (int)ph.rows.size();
-  if (c.in_stride == 2) {
+  ph.Npad = c.Npad;
+  const bool xfold = !c.transposed && c.in_stride == 1 && c.k >= 5 && c.cout <= 4 && c.Cb % 2 == 0 && c.pad == (c.k - 1) / 2;
+  if (xfold) {
+    ph.kind = 3; ph.Npad = round_up(c.k * c.cout, 16);
+    ph.CbG = (c.Cb % 4 == 0) ? 4 : 2; ph.nchg = c.Cb / ph.CbG;
+    ph.nseg = 1; ph.pslab16 = kTileM; ph.seg_len16[0] = kTileM; ph.seg_dst16[0] = 0;
+    ph.nrg = 0;
+    for (int rg = 1; rg <= nrows; ++rg) {
+      if (nrows % rg) continue;
+      if ((nrows / rg) * ph.CbG * ph.pslab16 * 32 <= kStageCapBytes) { ph.nrg = rg; break; }
+    }
+    if (!ph.nrg) { set_error("conv %s: patch stage too large", c.name.c_str()); return FAV_ERR_UNSUPPORTED; }
+    ph.rows_per_group = nrows / ph.nrg;
+  } else if (c.in_stride == 2) {
     if (!(c.k == 3 && c.pad == 1 && c.Cb >= 2 && c.Cb % 2 == 0)) {
       set_error("conv %s: stride-2 tcgen05 path needs k=3, pad=1, Cin%%16==0", c.name.c_str());
       return FAV_ERR_UNSUPPORTED;
@@ -112,6 +127,16 @@ static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
             ph.units[g].push_back(Unit{tap, 0});
           }
       }
+    } else if (ph.kind == 3) {
+      for (int j = 0; j < ph.CbG / 2; ++j) {
+        ph.steps.push_back(KStep{(uint16_t)((ri * ph.CbG + 2 * j) * ph.pslab16), (uint16_t)ph.pslab16});
+        for (int chg = 0; chg < ph.nchg; ++chg)
+          for (int rg = 0; rg < ph.nrg; ++rg) {
+            int g = chg * ph.nrg + rg;
+            int ky = ph.rows[rg * ph.rows_per_group + ri] + c.pad;  // unit.tap holds the filter ROW in x-fold mode
+            for (int u = 0; u < 2; ++u) ph.units[g].push_back(Unit{ky, chg * ph.CbG + 2 * j + u});
+          }
+      }
     } else {
       for (int dx : dxs) {
         int xoff = ph.kind == 2 ? (dx == -1 ? 0 : (dx == 0 ? kTileM + 1 : 1)) : dx - ph.dxmin;
@@ -129,7 +154,7 @@ static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
   }
   const int spg = (int)ph.steps.size();
   if (spg > kMaxSteps) { set_error("conv %s: too many K steps", c.name.c_str()); return FAV_ERR_UNSUPPORTED; }
-  const int step_bytes = 2 * 2 * c.Npad * 16;
+  const int step_bytes = 2 * 2 * ph.Npad * 16;
   ph.spc = 1;
   for (int d = 1; d <= spg; ++d)
     if (spg % d == 0 && d * step_bytes <= kChunkCapBytes) ph.spc = d;
@@ -198,18 +223,25 @@ static inline void init_conv_def(ConvDef &c, const std::string &name, int cin, i
 // packed tcgen05 weights of one phase: [group][chunk][hi|lo][step][k8 half][Npad][8] fp16 (as uint16 bit patterns)
 static inline std::vector<uint16_t> pack_phase_weights(const ConvDef &c, const ConvPhase &ph, const std::vector<float> &w) {
   const int ngroups = ph.nrg * ph.nchg, spg = (int)ph.steps.size();
-  std::vector<uint16_t> pk((size_t)ngroups * spg * 2 * 2 * c.Npad * 8, 0);
+  const int Npad = ph.Npad;
+  std::vector<uint16_t> pk((size_t)ngroups * spg * 2 * 2 * Npad * 8, 0);
   for (int g = 0; g < ngroups; ++g)
     for (int ch = 0; ch < ph.nchunks; ++ch)
       for (int part = 0; part < 2; ++part)
         for (int st = 0; st < ph.spc; ++st)
           for (int u = 0; u < 2; ++u) {
             const Unit un = ph.units[g][(ch * ph.spc + st) * 2 + u];
-            size_t base = (((((size_t)g * ph.nchunks + ch) * 2 + part) * ph.spc + st) * 2 + u) * c.Npad * 8;
+            size_t base = (((((size_t)g * ph.nchunks + ch) * 2 + part) * ph.spc + st) * 2 + u) * Npad * 8;
             if (un.tap < 0) continue;
-            for (int n = 0; n < c.Npad; ++n)
+            for (int n = 0; n < Npad; ++n)
               for (int i = 0; i < 8; ++i) {
-                float v = weight_at(c, w, n, un.cb * 8 + i, ph.taps[un.tap].ky, ph.taps[un.tap].kx);
+                float v;
+                if (ph.kind == 3) {  // n = kx * Cout + co, unit.tap = ky
+                  int kx = n / c.cout, co = n % c.cout;
+                  v = kx < c.k ? weight_at(c, w, co, un.cb * 8 + i, un.tap, kx) : 0.f;
+                } else {
+                  v = weight_at(c, w, n, un.cb * 8 + i, ph.taps[un.tap].ky, ph.taps[un.tap].kx);
+                }
                 uint16_t hb = f2h_bits(v);
                 pk[base + (size_t)n * 8 + i] = part == 0 ? hb : f2h_bits(v - h2f_bits(hb));
               }
@@ -250,7 +282,9 @@ static inline int fill_conv_job(const ConvDef &c, const ConvPhase &ph, const Ope
   memset(&j, 0, sizeof(j));
   j.a_hi = reinterpret_cast<const uint4 *>(in.hi); j.a_lo = reinterpret_cast<const uint4 *>(in.lo);
   j.a_Cb = in.Cb; j.a_slab16 = in.slab16();
-  j.Ho = pHo; j.Wo = pWo; j.tiles_x = ceil_div(pWo, kTileM); j.ntiles = j.tiles_x * pHo;
+  j.tile_dx = ph.kind == 3 ? kTileM - (c.k - 1) : kTileM;
+  j.xfold_kw = ph.kind == 3 ? c.k : 0;
+  j.Ho = pHo; j.Wo = pWo; j.tiles_x = ceil_div(pWo, j.tile_dx); j.ntiles = j.tiles_x * pHo;
   j.row_mul = c.in_stride;
   j.nseg = ph.nseg;
   for (int s = 0; s < ph.nseg; ++s) { j.seg_len16[s] = ph.seg_len16[s]; j.seg_dst16[s] = ph.seg_dst16[s]; }
@@ -266,12 +300,12 @@ static inline int fill_conv_job(const ConvDef &c, const ConvPhase &ph, const Ope
   j.pslab16 = ph.pslab16; j.stage16 = ph.rows_per_group * ph.CbG * ph.pslab16;
   j.nchunks = ph.nchunks; j.spc = ph.spc;
   for (size_t i = 0; i < ph.steps.size(); ++i) j.steps[i] = ph.steps[i];
-  j.chunk16 = 2 * ph.spc * 2 * c.Npad; j.Npad = c.Npad; j.Cout = c.cout;
+  j.chunk16 = 2 * ph.spc * 2 * ph.Npad; j.Npad = ph.Npad; j.Cout = c.cout;
   j.oy_mul = c.out_mul; j.ox_mul = c.out_mul; j.oy_off = ph.oy_off; j.ox_off = ph.ox_off;
   // every bulk copy must stay inside the operand allocation
   int64_t max_row = (int64_t)j.row_mul * (pHo - 1) + in.padT + ph.rows.back();
   int64_t last16 = ((max_row * in.Cb + in.Cb - 1) * (int64_t)in.slab16()) + j.seg_src16[ph.nseg - 1] +
-                   (int64_t)(j.tiles_x - 1) * kTileM + j.seg_len16[ph.nseg - 1];
+                   (int64_t)(j.tiles_x - 1) * j.tile_dx + j.seg_len16[ph.nseg - 1];
   if (max_row >= in.Hs || last16 > (int64_t)in.elems16) {
     set_error("conv %s: internal operand bounds error", c.name.c_str());
     return FAV_ERR_INVALID;

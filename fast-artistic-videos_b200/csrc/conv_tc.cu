@@ -31,6 +31,7 @@ constexpr int kNA = 2;
 constexpr int kNB = 4;
 constexpr int kTmemCols = 256;
 constexpr int kThreads = 224;
+constexpr int kExchPitch = 33;  // fp32 words per pixel in the x-fold exchange buffer (odd: conflict-free)
 
 struct __align__(16) TcShared {
   uint64_t a_full[kNA], a_empty[kNA], b_full[kNB], b_empty[kNB], t_full[2], t_empty[2];
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     stage_tx *= (uint32_t)(job.nrows * job.CbG * 2);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
-      const int y = tile / job.tiles_x, x0 = (tile - y * job.tiles_x) * kTileM;
+      const int y = tile / job.tiles_x, x0 = (tile - y * job.tiles_x) * job.tile_dx;
       for (int g = 0; g < ngroups; ++g, ++it) {
         const uint32_t s = it % kNA, ph = (it / kNA) & 1;
         mbar_wait(&sh->a_empty[s], ph ^ 1);
@@ -233,14 +234,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ===== epilogue warps 0..3: TMEM lane = pixel =====
     uint32_t tl = 0;
     const int px = warp * 32 + lane;
+    float *exch = reinterpret_cast<float *>(sh + 1);  // x-fold exchange buffer [128][kExchPitch]
     for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x, ++tl) {
-      const int y = tile / job.tiles_x, x = (tile - y * job.tiles_x) * kTileM + px;
+      const int y = tile / job.tiles_x, x = (tile - y * job.tiles_x) * job.tile_dx + px;
       const uint32_t as = tl & 1, tph = (tl >> 1) & 1;
       mbar_wait(&sh->t_full[as], tph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 128u;
       const int yo = y * job.oy_mul + job.oy_off, xo = x * job.ox_mul + job.ox_off;
       const bool valid = x < job.Wo;
+      if (job.xfold_kw) {
+        // partial sums Q[pixel][kx*Cout + co] -> shared memory, then out[x][co] = sum_kx Q[x + kx][kx*Cout + co]
+        for (int c0 = 0; c0 < Npad; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + (uint32_t)c0, r);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) exch[px * kExchPitch + c0 + i] = __uint_as_float(r[i]);
+        }
+        tc_fence_before();
+        mbar_arrive(&sh->t_empty[as]);  // TMEM stage drained: the next tile's MMAs may start
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (px < job.tile_dx && valid) {
+          for (int k = 0; k < job.Cout; ++k) {
+            float s = __ldg(job.bias + k);
+            for (int kx = 0; kx < job.xfold_kw; ++kx) s += exch[(px + kx) * kExchPitch + kx * job.Cout + k];
+            job.out3[((int64_t)(job.final_mode == 2 ? 2 - k : k) * job.Ho + yo) * job.Wo + xo] =
+                tc_final_value(s, k, job.final_mode, job.tanh_c);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // exch is rewritten by the next tile
+        continue;
+      }
       for (int c0 = 0; c0 < Npad; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + (uint32_t)c0, r);
@@ -261,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < 3; ++k)
             if (k < job.Cout)
-              job.out3[((int64_t)k * job.Ho + yo) * job.Wo + xo] =
+              job.out3[((int64_t)(job.final_mode == 2 ? 2 - k : k) * job.Ho + yo) * job.Wo + xo] =
                   tc_final_value(__uint_as_float(r[k]) + __ldg(job.bias + k), k, job.final_mode, job.tanh_c);
         }
       }
@@ -280,7 +304,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 }
 
 size_t conv_tc_smem_bytes(const ConvJob &job) {
-  return (size_t)kNA * 2 * job.stage16 * 16 + (size_t)kNB * job.chunk16 * 16 + sizeof(TcShared) + 128;
+  return (size_t)kNA * 2 * job.stage16 * 16 + (size_t)kNB * job.chunk16 * 16 + sizeof(TcShared) + 128 +
+         (job.xfold_kw ? (size_t)kTileM * kExchPitch * 4 : 0);
 }
 
 int launch_conv_tc(const ConvJob &job, int num_sms, cudaStream_t st) {

@@ -90,6 +90,7 @@ struct fav_net {
   int num_sms = 148;
   int device = 0;
   std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+  Plan *last_plan = nullptr;
   std::vector<void *> allocs;
   ~fav_net() {
     plans.clear();
@@ -211,7 +212,7 @@ static int build_conv_jobs(fav_net *net, Plan &pl, PlanStep &st, const ConvDef &
 static int build_plan(fav_net *net, int H, int W, Plan **out) {
   auto key = std::make_pair(H, W);
   auto it = net->plans.find(key);
-  if (it != net->plans.end()) { *out = it->second.get(); return FAV_OK; }
+  if (it != net->plans.end()) { *out = it->second.get(); net->last_plan = *out; return FAV_OK; }
   if (H % 4 || W % 4 || H < 16 || W < 16) {
     set_error("frame size %dx%d: H and W must be multiples of 4 (reflect-start nets restore the input size only "
               "then, SURVEY appendix B)", W, H);
@@ -292,6 +293,7 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
     }
   }
   *out = pl.get();
+  net->last_plan = pl.get();
   net->plans[key] = std::move(pl);
   return FAV_OK;
 }
@@ -532,8 +534,8 @@ int fav_net_profile(fav_net_t *net, const float *in7, int H, int W, float *out3,
 }
 
 int fav_net_layer_output(fav_net_t *net, int index, float *out, int *C, int *Hl, int *Wl, void *stream) {
-  FAV_REQUIRE(net && !net->plans.empty(), "fav_net_layer_output: run a forward first");
-  Plan *pl = net->plans.rbegin()->second.get();
+  FAV_REQUIRE(net && net->last_plan, "fav_net_layer_output: run a forward first");
+  Plan *pl = net->last_plan;
   auto it = pl->layer_operand.find(index);
   FAV_REQUIRE(it != pl->layer_operand.end(), "fav_net_layer_output: layer %d has no stored activation", index);
   const Operand &o = pl->ops[it->second];

@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ 
   } else {
     for (int k = 0; k < 8; ++k)
       if (co0 + k < j.Cout)
-        j.out3[((int64_t)(co0 + k) * j.Ho + yo) * j.Wo + xo] = final_value(acc[k], co0 + k, j.final_mode, j.tanh_c);
+        j.out3[((int64_t)(j.final_mode == 2 ? 2 - (co0 + k) : co0 + k) * j.Ho + yo) * j.Wo + xo] =
+            final_value(acc[k], co0 + k, j.final_mode, j.tanh_c);
   }
 }
 

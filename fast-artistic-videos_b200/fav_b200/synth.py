@@ -160,7 +160,7 @@ def make_forward_flow(H: int, W: int, idx: int) -> np.ndarray:
     sy = np.clip(np.rint(y - bw[1]), 0, H - 1).astype(np.int64)
     fw = -bw[:, sy, sx]
     fw += rng.normal(0.0, 0.05, size=fw.shape)
-    return fw.astype(np.float32)
+    return np.ascontiguousarray(fw, dtype=np.float32)
 
 
 def stress_flow(H: int, W: int, seed: int = 7, amp: float = 64.0) -> np.ndarray:

@@ -22,7 +22,7 @@ void set_error(const char *fmt, ...) {
 }
 std::atomic<uint64_t> g_launches{0};
 size_t conv_tc_smem_bytes(const ConvJob &job) {  // mirror of conv_tc.cu (kNA=2, kNB=4)
-  return (size_t)2 * 2 * job.stage16 * 16 + (size_t)4 * job.chunk16 * 16 + 256;
+  return (size_t)2 * 2 * job.stage16 * 16 + (size_t)4 * job.chunk16 * 16 + 256 + (job.xfold_kw ? 128 * 33 * 4 : 0);
 }
 }  // namespace fav
 
@@ -71,7 +71,7 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
     std::vector<uint16_t> st_hi((size_t)j.stage16 * 8), st_lo((size_t)j.stage16 * 8);
     std::vector<double> acc((size_t)kTileM * Npad);
     for (int tile = 0; tile < j.ntiles; ++tile) {
-      const int y = tile / j.tiles_x, x0 = (tile % j.tiles_x) * kTileM;
+      const int y = tile / j.tiles_x, x0 = (tile % j.tiles_x) * j.tile_dx;
       std::fill(acc.begin(), acc.end(), 0.0);
       for (int g = 0; g < j.ngroups; ++g) {
         // A producer
@@ -113,6 +113,19 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
         }
       }
       // epilogue placement
+      if (j.xfold_kw) {
+        for (int m = 0; m < j.tile_dx; ++m) {
+          int xx = x0 + m;
+          if (xx >= j.Wo) continue;
+          written[(size_t)y * Wo + xx]++;
+          for (int n = 0; n < cout; ++n) {
+            double sacc = 0;
+            for (int kx = 0; kx < j.xfold_kw; ++kx) sacc += acc[(size_t)(m + kx) * Npad + kx * cout + n];
+            out[((size_t)n * Ho + y) * Wo + xx] = sacc;
+          }
+        }
+        continue;
+      }
       for (int m = 0; m < kTileM; ++m) {
         int xx = x0 + m;
         if (xx >= j.Wo) continue;

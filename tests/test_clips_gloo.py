@@ -1,0 +1,83 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the clip sharding (assign / scatter / process / gather)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG, ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import sys
+
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from fav_b200 import clips
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 5
+        shapes = [(2 + c, 3, 8, 12) for c in range(n)]  # ragged clip lengths
+        data = [torch.arange(torch.Size(s).numel(), dtype=torch.float32).reshape(s) + 1000 * c
+                for c, s in enumerate(shapes)] if rank == 0 else None
+        mine = clips.scatter_clips(data, shapes)
+        assert sorted(mine) == clips.assign_clips(n, world)[rank]
+        # "stylize": a recurrent per-clip loop that depends only on the clip itself (stand-in for the GPU frame loop)
+        outs = {}
+        for c, t in mine.items():
+            prev = torch.zeros_like(t[0])
+            frames = []
+            for i in range(t.shape[0]):
+                prev = 0.5 * prev + t[i]
+                frames.append(prev)
+            outs[c] = torch.stack(frames)
+        res = clips.gather_clips(outs, shapes)
+        if rank == 0:
+            ok = True
+            for c, s in enumerate(shapes):
+                prev = torch.zeros(s[1:])
+                for i in range(s[0]):
+                    prev = 0.5 * prev + data[c][i]
+                    ok &= bool(torch.equal(res[c][i], prev))
+            q.put(ok)
+        else:
+            assert res is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_assign_clips_partitions():
+    from fav_b200 import clips
+
+    for n in (0, 1, 7, 8, 9):
+        for w in (1, 2, 8):
+            parts = clips.assign_clips(n, w)
+            assert sorted(c for p in parts for c in p) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_scatter_process_gather_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
