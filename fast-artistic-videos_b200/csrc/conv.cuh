@@ -44,6 +44,11 @@ struct ConvJob {
   // horizontal halo, tiles advance by tile_dx = 128 - (KW-1) pixels and the epilogue adds the KW shifted partial
   // sums through a shared-memory exchange buffer.  xfold_kw == 0: plain mode, tile_dx == 128.
   int tile_dx, xfold_kw;
+  // weight pipeline: b_slots ring slots of chunk16*16 bytes; b_resident: every chunk of the job has its own slot,
+  // is loaded once per CTA and never released (small layers: no per-tile weight traffic)
+  int b_slots, b_resident;
+  // fused InstanceNorm statistics: per-channel sum / sum of squares of the stored values (double, atomics), or null
+  double *stats;
   // output placement: raw(y*oy_mul + oy_off, x*ox_mul + ox_off)
   float *raw;
   int raw_Cq, raw_Wp;
@@ -75,14 +80,13 @@ struct SimtJob {
 int launch_conv_tc(const ConvJob &job, int num_sms, cudaStream_t st);
 int launch_conv_simt(const SimtJob &job, cudaStream_t st);
 size_t conv_tc_smem_bytes(const ConvJob &job);
+void conv_tc_choose_slots(ConvJob &job);  // fills b_slots / b_resident from the shared-memory budget
 
 // elementwise / reduction kernels of the net (net_kernels.cu)
 int launch_pack_input(const float *in, int Cin, int H, int W, int reflect, const Operand &dst, cudaStream_t st);
 int launch_in_stats(const RawTensor &raw, double *sums /*[2*C]*/, cudaStream_t st);
-int launch_in_finalize(const double *sums, const float *gamma, const float *beta, int C, int64_t count, float eps,
-                       float *mean_scale_beta /*[3*C]*/, cudaStream_t st);
-int launch_in_apply(const RawTensor &raw, const float *mean_scale_beta, int relu, const Operand *skip, int shave,
-                    const Operand &dst, cudaStream_t st);
+int launch_in_apply(const RawTensor &raw, const double *sums, const float *gamma, const float *beta, float eps, int relu,
+                    const Operand *skip, int shave, const Operand &dst, cudaStream_t st);
 int launch_unpack_operand(const Operand &src, float *out_nchw, cudaStream_t st);
 
 }  // namespace fav

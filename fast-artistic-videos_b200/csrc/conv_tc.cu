@@ -21,20 +21,20 @@
 //   warp  4    A producer (bulk copies of the patch, all lanes issue)
 //   warp  5    B producer (bulk copies of weight chunks)
 //   warp  6    TMEM allocator + single-thread MMA issuer
-// Pipelines: A stages (kNA) and B slots (kNB) with full/empty mbarriers; TMEM accumulator double-buffered so
+// Pipelines: A stages (kNA) and weight slots (ring, or resident for small layers) with full/empty mbarriers; TMEM accumulator double-buffered so
 // the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "conv.cuh"
 
 namespace fav {
 
 constexpr int kNA = 2;
-constexpr int kNB = 4;
+constexpr int kMaxB = 16;  // weight slots (ring or resident)
 constexpr int kTmemCols = 256;
 constexpr int kThreads = 224;
 constexpr int kExchPitch = 33;  // fp32 words per pixel in the x-fold exchange buffer (odd: conflict-free)
 
 struct __align__(16) TcShared {
-  uint64_t a_full[kNA], a_empty[kNA], b_full[kNB], b_empty[kNB], t_full[2], t_empty[2];
+  uint64_t a_full[kNA], a_empty[kNA], b_full[kMaxB], b_empty[kMaxB], t_full[2], t_empty[2];
   uint32_t tmem_base;
   uint32_t pad_;
 };
@@ -106,6 +106,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// sum over the 32 lanes of each of 16 per-lane values; lane L returns the total of value index (L >> 1)
+__device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float send = u16 ? v[i] : v[i + 8], keep = u16 ? v[i + 8] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float send = u8 ? a[i] : a[i + 4], keep = u8 ? a[i + 4] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float send = u4 ? b[i] : b[i + 2], keep = u4 ? b[i + 2] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  float send = u2 ? c[0] : c[1], keep = u2 ? c[1] : c[0];
+  float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  return d + __shfl_xor_sync(0xffffffffu, d, 1);
+}
+
 __device__ __forceinline__ float tc_final_value(float v, int k, int mode, float tanh_c) {
   float t = tanhf(v) * tanh_c;  // nn.Tanh -> nn.MulConstant(150) (models_video.lua:135-136)
   if (mode == 2) {              // fused vgg.deprocess (preprocess.lua:70)
@@ -121,13 +145,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t chunk_bytes = (uint32_t)job.chunk16 * 16u;
   uint8_t *a_base = smem;                                   // stage s: hi | lo
   uint8_t *b_base = a_base + kNA * 2 * a_stage_bytes;       // slot s: [hi steps][lo steps]
-  TcShared *sh = reinterpret_cast<TcShared *>(b_base + kNB * chunk_bytes);
+  const uint32_t nslots = (uint32_t)job.b_slots;
+  TcShared *sh = reinterpret_cast<TcShared *>(b_base + nslots * chunk_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNA; ++i) { mbar_init(&sh->a_full[i], 1); mbar_init(&sh->a_empty[i], 1); }
-    for (int i = 0; i < kNB; ++i) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], 1); }
+    for (int i = 0; i < kMaxB; ++i) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], 1); mbar_init(&sh->t_empty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -178,15 +203,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ===== B producer: weight chunks =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x)
+      for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
+        if (job.b_resident && tile != (int)blockIdx.x) break;  // resident weights: one pass fills every slot
         for (int g = 0; g < ngroups; ++g)
           for (int c = 0; c < nchunks; ++c, ++it) {
-            const uint32_t s = it % kNB, ph = (it / kNB) & 1;
+            const uint32_t s = it % nslots, ph = (it / nslots) & 1;
             mbar_wait(&sh->b_empty[s], ph ^ 1);
             mbar_arrive_expect_tx(&sh->b_full[s], chunk_bytes);
             bulk_g2s(b_base + s * chunk_bytes, job.b + (int64_t)(g * nchunks + c) * job.chunk16, chunk_bytes,
                      &sh->b_full[s]);
           }
+      }
     }
     __syncwarp();
   } else if (warp == 6) {
@@ -207,8 +234,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           tc_fence_after();
           const uint32_t a_hi = smem_u32(a_base + sa * 2 * a_stage_bytes), a_lo = a_hi + a_stage_bytes;
           for (int c = 0; c < nchunks; ++c, ++itb) {
-            const uint32_t sb = itb % kNB;
-            mbar_wait(&sh->b_full[sb], (itb / kNB) & 1);
+            // resident: slot = chunk index, filled once (waiting on parity 0 stays satisfied afterwards)
+            const uint32_t sb = job.b_resident ? (uint32_t)(g * nchunks + c) : itb % nslots;
+            mbar_wait(&sh->b_full[sb], job.b_resident ? 0u : (itb / nslots) & 1);
             tc_fence_after();
             const uint32_t b_hi = smem_u32(b_base + sb * chunk_bytes);
             const uint32_t b_lo = b_hi + (uint32_t)spc * 2u * (uint32_t)Npad * 16u;
@@ -222,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               tc_mma_f16(d_tmem, ad_lo, bd_hi, idesc, 1);
               tc_mma_f16(d_tmem, ad_hi, bd_lo, idesc, 1);
             }
-            tc_commit(&sh->b_empty[sb]);  // frees the weight slot when the MMAs above retire
+            if (!job.b_resident) tc_commit(&sh->b_empty[sb]);  // frees the weight slot when the MMAs above retire
           }
           tc_commit(&sh->a_empty[sa]);  // frees the patch stage
         }
@@ -234,7 +262,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ===== epilogue warps 0..3: TMEM lane = pixel =====
     uint32_t tl = 0;
     const int px = warp * 32 + lane;
-    float *exch = reinterpret_cast<float *>(sh + 1);  // x-fold exchange buffer [128][kExchPitch]
+    float *exch = reinterpret_cast<float *>(sh + 1);  // x-fold exchange buffer [128][kExchPitch] / stats [2][128]
+    float acc_s[8], acc_q[8];  // fused InstanceNorm statistics: this lane's channel (16*j + lane/2), all tiles
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc_s[j] = acc_q[j] = 0.f;
+    if (job.stats) {
+      exch[px] = 0.f;
+      exch[128 + px] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x, ++tl) {
       const int y = tile / job.tiles_x, x = (tile - y * job.tiles_x) * job.tile_dx + px;
       const uint32_t as = tl & 1, tph = (tl >> 1) & 1;
@@ -265,21 +301,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         asm volatile("bar.sync 1, 128;" ::: "memory");  // exch is rewritten by the next tile
         continue;
       }
-      for (int c0 = 0; c0 < Npad; c0 += 16) {
+#pragma unroll
+      for (int jc = 0; jc < 8; ++jc) {
+        const int c0 = jc * 16;
+        if (c0 >= Npad) break;
         uint32_t r[16];
         tmem_ld16(taddr + (uint32_t)c0, r);
         if (job.final_mode == 0) {
+          float v[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 bq = __ldg(reinterpret_cast<const float4 *>(job.bias + c0) + q);
+            v[4 * q] = __uint_as_float(r[4 * q]) + bq.x; v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bq.y;
+            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bq.z; v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bq.w;
+          }
           if (valid) {
             float4 *rp = reinterpret_cast<float4 *>(job.raw) + (((int64_t)yo * job.raw_Cq + (c0 >> 2)) * job.raw_Wp + xo);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (c0 + 4 * q < job.Cout) {
-                const float4 bq = __ldg(reinterpret_cast<const float4 *>(job.bias + c0) + q);
-                rp[(int64_t)q * job.raw_Wp] =
-                    make_float4(__uint_as_float(r[4 * q]) + bq.x, __uint_as_float(r[4 * q + 1]) + bq.y,
-                                __uint_as_float(r[4 * q + 2]) + bq.z, __uint_as_float(r[4 * q + 3]) + bq.w);
-              }
-            }
+            for (int q = 0; q < 4; ++q)
+              if (c0 + 4 * q < job.Cout) rp[(int64_t)q * job.raw_Wp] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+          if (job.stats) {
+            // per-channel sums over the warp's 32 pixels: butterfly transpose-reduce, 16 shuffles per quantity;
+            // afterwards lane L holds channel c0 + (L >> 1)
+            float sq[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
+            acc_s[jc] += warp_reduce16(v, lane);
+            acc_q[jc] += warp_reduce16(sq, lane);
           }
         } else if (c0 == 0 && valid) {
 #pragma unroll
@@ -292,6 +341,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tc_fence_before();
       mbar_arrive(&sh->t_empty[as]);
     }
+    if (job.stats) {
+      // 4 warps -> shared memory (float atomics), then one double atomic per channel and quantity per CTA
+      if ((lane & 1) == 0) {
+#pragma unroll
+        for (int jc = 0; jc < 8; ++jc)
+          if (jc * 16 < Npad) {
+            atomicAdd(&exch[jc * 16 + (lane >> 1)], acc_s[jc]);
+            atomicAdd(&exch[128 + jc * 16 + (lane >> 1)], acc_q[jc]);
+          }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (px < job.Cout) {
+        atomicAdd(job.stats + px, (double)exch[px]);
+        atomicAdd(job.stats + job.Cout + px, (double)exch[128 + px]);
+      }
+    }
   }
 
   tc_fence_before();
@@ -303,9 +368,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
 }
 
-size_t conv_tc_smem_bytes(const ConvJob &job) {
-  return (size_t)kNA * 2 * job.stage16 * 16 + (size_t)kNB * job.chunk16 * 16 + sizeof(TcShared) + 128 +
-         (job.xfold_kw ? (size_t)kTileM * kExchPitch * 4 : 0);
+static size_t tc_fixed_smem(const ConvJob &job) {
+  return (size_t)kNA * 2 * job.stage16 * 16 + sizeof(TcShared) + 128 +
+         (job.xfold_kw ? (size_t)kTileM * kExchPitch * 4 : (size_t)2 * 128 * 4);
+}
+size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
+
+void conv_tc_choose_slots(ConvJob &job) {
+  const size_t budget = 224 * 1024, chunk = (size_t)job.chunk16 * 16, fixed = tc_fixed_smem(job);
+  const int total = job.ngroups * job.nchunks;
+  if (total <= kMaxB && fixed + total * chunk <= budget) {
+    job.b_resident = 1;
+    job.b_slots = total;
+  } else {
+    job.b_resident = 0;
+    int n = (int)((budget - fixed) / chunk);
+    job.b_slots = n > kMaxB ? kMaxB : (n < 2 ? 2 : n);
+  }
 }
 
 int launch_conv_tc(const ConvJob &job, int num_sms, cudaStream_t st) {

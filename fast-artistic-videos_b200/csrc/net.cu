@@ -190,6 +190,7 @@ static int build_conv_jobs(fav_net *net, Plan &pl, PlanStep &st, const ConvDef &
     j.b = ph.d_b_tc; j.bias = c.d_bias;
     j.raw = st.raw.p; j.raw_Cq = st.raw.Cq; j.raw_Wp = st.raw.Wp;
     j.final_mode = last ? 1 : 0; j.out3 = out3; j.tanh_c = net->tanh_c;
+    conv_tc_choose_slots(j);
     if (conv_tc_smem_bytes(j) > 227 * 1024) {
       set_error("conv %s: shared memory budget exceeded", c.name.c_str());
       return FAV_ERR_UNSUPPORTED;
@@ -278,6 +279,7 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
       }
       PlanStep ns;
       ns.kind = 1; ns.inorm = op.inorm[i]; ns.raw = raw; ns.stats_off = stats_off;
+      for (ConvJob &j : pl->steps.back().tc) j.stats = pl->stats + stats_off;  // statistics fused into the epilogue
       stats_off += 2 * c.cout;
       const ConvDef *consumer = pos + 1 < order.size() ? &net->convs[order[pos + 1]] : nullptr;
       FAV_TRY(make_operand(*pl, c.cout, ho, wo, consumer, &ns.dst));
@@ -350,15 +352,16 @@ static int run_plan(fav_net *net, Plan &pl, const float *in7, float *out3, int f
     } else {
       const InDef &n = net->inorms[s.inorm];
       double *sums = pl.stats + s.stats_off;
-      float *msb = pl.msb + (size_t)s.stats_off * 2;
       const double elems = (double)n.C * s.raw.H * s.raw.W;
-      FAV_TRY(begin(2, 4.0 * elems, n.name + ".stats"));
-      FAV_TRY(launch_in_stats(s.raw, sums, st));
+      if (net->conv_impl != 0) {  // the tcgen05 epilogue already accumulated the statistics
+        FAV_TRY(begin(2, 4.0 * elems, n.name + ".stats"));
+        FAV_TRY(launch_in_stats(s.raw, sums, st));
+        FAV_TRY(end());
+      }
       // InstanceNormalization.lua:21,39: eps = 1e-5, statistics over H*W of each (n, c)
-      FAV_TRY(launch_in_finalize(sums, n.d_gamma, n.d_beta, n.C, (int64_t)s.raw.H * s.raw.W, 1e-5f, msb, st));
-      FAV_TRY(end());
       FAV_TRY(begin(3, (s.skip >= 0 ? 12.0 : 8.0) * elems, n.name + ".apply"));
-      FAV_TRY(launch_in_apply(s.raw, msb, s.relu, s.skip >= 0 ? &pl.ops[s.skip] : nullptr, 2, pl.ops[s.dst], st));
+      FAV_TRY(launch_in_apply(s.raw, sums, n.d_gamma, n.d_beta, 1e-5f, s.relu, s.skip >= 0 ? &pl.ops[s.skip] : nullptr, 2,
+                              pl.ops[s.dst], st));
       FAV_TRY(end());
     }
   }

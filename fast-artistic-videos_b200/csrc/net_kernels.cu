@@ -105,40 +105,33 @@ int launch_in_stats(const RawTensor &raw, double *sums, cudaStream_t st) {
   return post_launch("in_stats");
 }
 
-__global__ void in_finalize_kernel(const double *__restrict__ sums, const float *__restrict__ gamma,
-                                   const float *__restrict__ beta, int C, double inv_count, double eps,
-                                   float *__restrict__ msb) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double mean = sums[c] * inv_count;
-  double var = sums[C + c] * inv_count - mean * mean;  // biased variance (SpatialBatchNormalization, training mode)
-  if (var < 0) var = 0;
-  double rstd = 1.0 / sqrt(var + eps);
-  msb[c] = (float)mean;
-  msb[C + c] = (float)((double)gamma[c] * rstd);
-  msb[2 * C + c] = beta[c];
-}
-
-int launch_in_finalize(const double *sums, const float *gamma, const float *beta, int C, int64_t count, float eps,
-                       float *msb, cudaStream_t st) {
-  in_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, gamma, beta, C, 1.0 / (double)count, (double)eps, msb);
-  return post_launch("in_finalize");
-}
-
 // ---- in_apply ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const float *__restrict__ msb, int relu,
-                                                       Operand skip, int has_skip, int shave, Operand dst) {
+// mean / gamma*rstd / beta of the block's 8 channels are derived from the (double) sums by the first 8 threads:
+// biased variance, eps inside the sqrt (nn.SpatialBatchNormalization in training mode, InstanceNormalization.lua:39-50)
+__global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const double *__restrict__ sums,
+                                                       const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                       double inv_count, double eps, int relu, Operand skip, int has_skip,
+                                                       int shave, Operand dst) {
+  __shared__ float s_mean[8], s_scale[8], s_beta[8];
   int x = blockIdx.x * 128 + threadIdx.x;
   int y = blockIdx.y, cb = blockIdx.z;
+  if (threadIdx.x < 8) {
+    int c = cb * 8 + threadIdx.x;
+    double mean = sums[c] * inv_count;
+    double var = sums[raw.C + c] * inv_count - mean * mean;
+    if (var < 0) var = 0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_scale[threadIdx.x] = (float)((double)gamma[c] / sqrt(var + eps));
+    s_beta[threadIdx.x] = beta[c];
+  }
+  __syncthreads();
   if (x >= raw.W) return;
   const float4 *rp = reinterpret_cast<const float4 *>(raw.p);
   float4 a = __ldg(rp + raw.off4(y, 2 * cb, x)), b = __ldg(rp + raw.off4(y, 2 * cb + 1, x));
   float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  const int C = raw.C;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    int c = cb * 8 + i;
-    float t = (v[i] - __ldg(msb + c)) * __ldg(msb + C + c) + __ldg(msb + 2 * C + c);
+    float t = (v[i] - s_mean[i]) * s_scale[i] + s_beta[i];
     v[i] = relu ? fmaxf(t, 0.f) : t;
   }
   if (has_skip) {  // ConcatTable{conv_block, ShaveImage(2)} -> CAddTable (models_video.lua:41-53)
@@ -152,11 +145,12 @@ __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const floa
   split_store8(v, reinterpret_cast<uint4 *>(dst.hi) + o, reinterpret_cast<uint4 *>(dst.lo) + o);
 }
 
-int launch_in_apply(const RawTensor &raw, const float *msb, int relu, const Operand *skip, int shave,
-                    const Operand &dst, cudaStream_t st) {
+int launch_in_apply(const RawTensor &raw, const double *sums, const float *gamma, const float *beta, float eps, int relu,
+                    const Operand *skip, int shave, const Operand &dst, cudaStream_t st) {
   dim3 grid(ceil_div(raw.W, 128), raw.H, raw.C / 8);
   Operand sk = skip ? *skip : Operand();
-  in_apply_kernel<<<grid, 128, 0, st>>>(raw, msb, relu, sk, skip ? 1 : 0, shave, dst);
+  in_apply_kernel<<<grid, 128, 0, st>>>(raw, sums, gamma, beta, 1.0 / ((double)raw.H * raw.W), (double)eps, relu, sk,
+                                        skip ? 1 : 0, shave, dst);
   return post_launch("in_apply");
 }
 

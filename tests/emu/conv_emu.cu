@@ -21,8 +21,16 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 std::atomic<uint64_t> g_launches{0};
-size_t conv_tc_smem_bytes(const ConvJob &job) {  // mirror of conv_tc.cu (kNA=2, kNB=4)
-  return (size_t)2 * 2 * job.stage16 * 16 + (size_t)4 * job.chunk16 * 16 + 256 + (job.xfold_kw ? 128 * 33 * 4 : 0);
+// mirror of conv_tc.cu: kNA = 2 patch stages, up to 16 weight slots (resident when every chunk fits)
+static size_t tc_fixed_smem(const ConvJob &job) {
+  return (size_t)2 * 2 * job.stage16 * 16 + 512 + (job.xfold_kw ? (size_t)128 * 33 * 4 : (size_t)1024);
+}
+size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
+void conv_tc_choose_slots(ConvJob &job) {
+  const size_t budget = 224 * 1024, chunk = (size_t)job.chunk16 * 16, fixed = tc_fixed_smem(job);
+  const int total = job.ngroups * job.nchunks;
+  if (total <= 16 && fixed + total * chunk <= budget) { job.b_resident = 1; job.b_slots = total; }
+  else { job.b_resident = 0; int n = (int)((budget - fixed) / chunk); job.b_slots = n > 16 ? 16 : (n < 2 ? 2 : n); }
 }
 }  // namespace fav
 
@@ -65,6 +73,8 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
     std::vector<uint16_t> pk = pack_phase_weights(c, ph, w);
     ConvJob j;
     if (fill_conv_job(c, ph, op, j) != FAV_OK) return 2;
+    conv_tc_choose_slots(j);
+    if (j.b_slots < 2 && !j.b_resident) { set_error("weight ring too small"); return 9; }
     smem_max = std::max(smem_max, conv_tc_smem_bytes(j));
     if (conv_tc_smem_bytes(j) > 227 * 1024) { set_error("smem budget"); return 3; }
     const int Npad = j.Npad;
