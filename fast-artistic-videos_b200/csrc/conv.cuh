@@ -6,7 +6,7 @@ namespace fav {
 
 constexpr int kMaxTaps = 81;
 constexpr int kMaxSteps = 168;
-constexpr int kMaxRows = 9;
+constexpr int kMaxRows = 10;
 constexpr int kMaxGroups = 8;
 constexpr int kTileM = 128;  // output pixels per MMA tile = TMEM lanes
 
@@ -47,6 +47,9 @@ struct ConvJob {
   // weight pipeline: b_slots ring slots of chunk16*16 bytes; b_resident: every chunk of the job has its own slot,
   // is loaded once per CTA and never released (small layers: no per-tile weight traffic)
   int b_slots, b_resident;
+  // mt: output rows per work unit (1 or 2).  mt = 2 shares every weight chunk and the overlapping patch rows between
+  // two vertically adjacent 128-pixel tiles (M = 256, two TMEM accumulators): halves the weight traffic per pixel.
+  int mt;
   // fused InstanceNorm statistics: per-channel sum / sum of squares of the stored values (double, atomics), or null
   double *stats;
   // output placement: raw(y*oy_mul + oy_off, x*ox_mul + ox_off)

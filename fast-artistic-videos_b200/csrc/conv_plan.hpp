@@ -284,7 +284,14 @@ static inline int fill_conv_job(const ConvDef &c, const ConvPhase &ph, const Ope
   j.a_Cb = in.Cb; j.a_slab16 = in.slab16();
   j.tile_dx = ph.kind == 3 ? kTileM - (c.k - 1) : kTileM;
   j.xfold_kw = ph.kind == 3 ? c.k : 0;
-  j.Ho = pHo; j.Wo = pWo; j.tiles_x = ceil_div(pWo, j.tile_dx); j.ntiles = j.tiles_x * pHo;
+  // two rows per unit when the weights do not fit in shared memory (they would be re-streamed per tile) and the
+  // patch rows are consecutive input rows
+  const size_t total_b = (size_t)ph.nrg * ph.nchg * ph.steps.size() * 2 * 2 * ph.Npad * 16;
+  bool consecutive = ph.kind == 0 && c.in_stride == 1 && ph.nrg == 1;
+  for (size_t i = 1; i < ph.rows.size(); ++i) consecutive = consecutive && ph.rows[i] == ph.rows[i - 1] + 1;
+  j.mt = (consecutive && total_b > 160 * 1024 && ph.Npad * 2 * 2 <= 512 &&
+          (size_t)(ph.rows_per_group + 1) * ph.CbG * ph.pslab16 * 32 <= 72 * 1024 && pHo >= 2) ? 2 : 1;
+  j.Ho = pHo; j.Wo = pWo; j.tiles_x = ceil_div(pWo, j.tile_dx); j.ntiles = j.tiles_x * ceil_div(pHo, j.mt);
   j.row_mul = c.in_stride;
   j.nseg = ph.nseg;
   for (int s = 0; s < ph.nseg; ++s) { j.seg_len16[s] = ph.seg_len16[s]; j.seg_dst16[s] = ph.seg_dst16[s]; }
@@ -296,14 +303,16 @@ static inline int fill_conv_job(const ConvDef &c, const ConvPhase &ph, const Ope
       int g = chg * ph.nrg + rg;
       j.grp_cb0[g] = chg * ph.CbG;
       for (int ri = 0; ri < ph.rows_per_group; ++ri) j.grp_row[g][ri] = in.padT + ph.rows[rg * ph.rows_per_group + ri];
+      if (j.mt == 2) j.grp_row[g][ph.rows_per_group] = j.grp_row[g][ph.rows_per_group - 1] + 1;
     }
-  j.pslab16 = ph.pslab16; j.stage16 = ph.rows_per_group * ph.CbG * ph.pslab16;
+  j.nrows = ph.rows_per_group + (j.mt - 1);  // patch rows per stage
+  j.pslab16 = ph.pslab16; j.stage16 = j.nrows * ph.CbG * ph.pslab16;
   j.nchunks = ph.nchunks; j.spc = ph.spc;
   for (size_t i = 0; i < ph.steps.size(); ++i) j.steps[i] = ph.steps[i];
   j.chunk16 = 2 * ph.spc * 2 * ph.Npad; j.Npad = ph.Npad; j.Cout = c.cout;
   j.oy_mul = c.out_mul; j.ox_mul = c.out_mul; j.oy_off = ph.oy_off; j.ox_off = ph.ox_off;
   // every bulk copy must stay inside the operand allocation
-  int64_t max_row = (int64_t)j.row_mul * (pHo - 1) + in.padT + ph.rows.back();
+  int64_t max_row = (int64_t)j.row_mul * (ceil_div(pHo, j.mt) * j.mt - 1) + in.padT + ph.rows.back();
   int64_t last16 = ((max_row * in.Cb + in.Cb - 1) * (int64_t)in.slab16()) + j.seg_src16[ph.nseg - 1] +
                    (int64_t)(j.tiles_x - 1) * j.tile_dx + j.seg_len16[ph.nseg - 1];
   if (max_row >= in.Hs || last16 > (int64_t)in.elems16) {

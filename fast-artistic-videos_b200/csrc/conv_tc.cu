@@ -29,7 +29,7 @@ namespace fav {
 
 constexpr int kNA = 2;
 constexpr int kMaxB = 16;  // weight slots (ring or resident)
-constexpr int kTmemCols = 256;
+constexpr int kTmemCols = 512;  // 2 accumulator stages x mt (<= 2) tiles x Npad (<= 128) columns
 constexpr int kThreads = 224;
 constexpr int kExchPitch = 33;  // fp32 words per pixel in the x-fold exchange buffer (odd: conflict-free)
 
@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     stage_tx *= (uint32_t)(job.nrows * job.CbG * 2);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
-      const int y = tile / job.tiles_x, x0 = (tile - y * job.tiles_x) * job.tile_dx;
+      const int yu = tile / job.tiles_x, x0 = (tile - yu * job.tiles_x) * job.tile_dx;
+      const int y = yu * job.mt;
       for (int g = 0; g < ngroups; ++g, ++it) {
         const uint32_t s = it % kNA, ph = (it / kNA) & 1;
         mbar_wait(&sh->a_empty[s], ph ^ 1);
@@ -217,45 +218,59 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     __syncwarp();
   } else if (warp == 6) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      uint32_t ita = 0, itb = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x, ++tl) {
-        const uint32_t as = tl & 1, tph = (tl >> 1) & 1;
-        mbar_wait(&sh->t_empty[as], tph ^ 1);
+    // ===== MMA issuer: the whole warp runs the (warp-uniform) control flow so that descriptors live in uniform
+    // registers and the UTCHMMAs issue back to back; one elected lane executes the tcgen05 instructions =====
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    // descriptor high word: SBO = 8 (128 B between 8-row groups), version 1 (bit 46), no swizzle
+    const uint64_t desc_hi = ((uint64_t)8 << 32) | (1ull << 46);
+    const uint64_t b_desc_base = desc_hi | ((uint64_t)Npad << 16);  // LBO = Npad * 16 B between the two K halves
+    const uint32_t b_step16 = 2u * (uint32_t)Npad, b_lo16 = (uint32_t)spc * b_step16;
+    const uint32_t a_tile16 = (uint32_t)(job.CbG * job.pslab16);  // mt = 2: second output row = one patch row lower
+    const uint32_t a_stage16 = (uint32_t)job.stage16;
+    uint32_t ita = 0, itb = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x, ++tl) {
+      const uint32_t as = tl & 1, tph = (tl >> 1) & 1;
+      mbar_wait(&sh->t_empty[as], tph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * 256u;
+      uint32_t accumulate = 0;
+      for (int g = 0; g < ngroups; ++g, ++ita) {
+        const uint32_t sa = ita % kNA;
+        mbar_wait(&sh->a_full[sa], (ita / kNA) & 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * 128u;
-        uint32_t accumulate = 0;
-        for (int g = 0; g < ngroups; ++g, ++ita) {
-          const uint32_t sa = ita % kNA;
-          mbar_wait(&sh->a_full[sa], (ita / kNA) & 1);
+        const uint32_t a_hi16 = smem_u32(a_base + sa * 2 * a_stage_bytes) >> 4, a_lo16 = a_hi16 + a_stage16;
+        for (int c = 0; c < nchunks; ++c, ++itb) {
+          // resident: slot = chunk index, filled once (waiting on parity 0 stays satisfied afterwards)
+          const uint32_t sb = job.b_resident ? (uint32_t)(g * nchunks + c) : itb % nslots;
+          mbar_wait(&sh->b_full[sb], job.b_resident ? 0u : (itb / nslots) & 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(a_base + sa * 2 * a_stage_bytes), a_lo = a_hi + a_stage_bytes;
-          for (int c = 0; c < nchunks; ++c, ++itb) {
-            // resident: slot = chunk index, filled once (waiting on parity 0 stays satisfied afterwards)
-            const uint32_t sb = job.b_resident ? (uint32_t)(g * nchunks + c) : itb % nslots;
-            mbar_wait(&sh->b_full[sb], job.b_resident ? 0u : (itb / nslots) & 1);
-            tc_fence_after();
-            const uint32_t b_hi = smem_u32(b_base + sb * chunk_bytes);
-            const uint32_t b_lo = b_hi + (uint32_t)spc * 2u * (uint32_t)Npad * 16u;
-            for (int st = 0; st < spc; ++st) {
-              const KStep ks = job.steps[c * spc + st];
-              const uint32_t aoff = (uint32_t)ks.a_off16 * 16u, boff = (uint32_t)st * 2u * (uint32_t)Npad * 16u;
-              const uint64_t ad_hi = make_desc(a_hi + aoff, ks.lbo16, 8), ad_lo = make_desc(a_lo + aoff, ks.lbo16, 8);
-              const uint64_t bd_hi = make_desc(b_hi + boff, Npad, 8), bd_lo = make_desc(b_lo + boff, Npad, 8);
+          const uint32_t b_hi16 = smem_u32(b_base + sb * chunk_bytes) >> 4;
+          for (int st = 0; st < spc; ++st) {
+            const KStep ks = job.steps[c * spc + st];
+            const uint64_t a_desc_base = desc_hi | ((uint64_t)ks.lbo16 << 16);
+            const uint64_t ad_hi = a_desc_base | (uint64_t)(a_hi16 + ks.a_off16), ad_lo = a_desc_base | (uint64_t)(a_lo16 + ks.a_off16);
+            const uint64_t bd_hi = b_desc_base | (uint64_t)(b_hi16 + st * b_step16),
+                           bd_lo = b_desc_base | (uint64_t)(b_hi16 + b_lo16 + st * b_step16);
+            if (leader) {
               tc_mma_f16(d_tmem, ad_hi, bd_hi, idesc, accumulate);
-              accumulate = 1;
               tc_mma_f16(d_tmem, ad_lo, bd_hi, idesc, 1);
               tc_mma_f16(d_tmem, ad_hi, bd_lo, idesc, 1);
+              if (job.mt == 2) {  // second output row: same weights, patch shifted by one row
+                tc_mma_f16(d_tmem + 128u, ad_hi + a_tile16, bd_hi, idesc, accumulate);
+                tc_mma_f16(d_tmem + 128u, ad_lo + a_tile16, bd_hi, idesc, 1);
+                tc_mma_f16(d_tmem + 128u, ad_hi + a_tile16, bd_lo, idesc, 1);
+              }
             }
-            if (!job.b_resident) tc_commit(&sh->b_empty[sb]);  // frees the weight slot when the MMAs above retire
+            accumulate = 1;
           }
-          tc_commit(&sh->a_empty[sa]);  // frees the patch stage
+          if (!job.b_resident && leader) tc_commit(&sh->b_empty[sb]);  // frees the weight slot when the MMAs retire
         }
-        tc_commit(&sh->t_full[as]);  // accumulator complete -> epilogue
+        if (leader) tc_commit(&sh->a_empty[sa]);  // frees the patch stage
       }
+      if (leader) tc_commit(&sh->t_full[as]);  // accumulator complete -> epilogue
     }
     __syncwarp();
   } else {
@@ -266,19 +281,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     float acc_s[8], acc_q[8];  // fused InstanceNorm statistics: this lane's channel (16*j + lane/2), all tiles
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc_s[j] = acc_q[j] = 0.f;
-    if (job.stats) {
-      exch[px] = 0.f;
-      exch[128 + px] = 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
+
     for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x, ++tl) {
-      const int y = tile / job.tiles_x, x = (tile - y * job.tiles_x) * job.tile_dx + px;
+      const int yu = tile / job.tiles_x, x = (tile - yu * job.tiles_x) * job.tile_dx + px;
       const uint32_t as = tl & 1, tph = (tl >> 1) & 1;
       mbar_wait(&sh->t_full[as], tph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 128u;
+      for (int t = 0; t < job.mt; ++t) {
+      const int y = yu * job.mt + t;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 256u + (uint32_t)t * 128u;
       const int yo = y * job.oy_mul + job.oy_off, xo = x * job.ox_mul + job.ox_off;
-      const bool valid = x < job.Wo;
+      const bool valid = x < job.Wo && y < job.Ho;
       if (job.xfold_kw) {
         // partial sums Q[pixel][kx*Cout + co] -> shared memory, then out[x][co] = sum_kx Q[x + kx][kx*Cout + co]
         for (int c0 = 0; c0 < Npad; c0 += 16) {
@@ -299,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // exch is rewritten by the next tile
-        continue;
+        goto next_tile;  // (x-fold jobs always have mt == 1)
       }
 #pragma unroll
       for (int jc = 0; jc < 8; ++jc) {
@@ -338,23 +351,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                   tc_final_value(__uint_as_float(r[k]) + __ldg(job.bias + k), k, job.final_mode, job.tanh_c);
         }
       }
+      }  // t
       tc_fence_before();
       mbar_arrive(&sh->t_empty[as]);
+    next_tile:;
     }
     if (job.stats) {
-      // 4 warps -> shared memory (float atomics), then one double atomic per channel and quantity per CTA
+      // 4 warps -> shared memory in per-warp slots, summed in a FIXED order (deterministic per CTA: the tile ->
+      // CTA assignment is static), then one double atomic per channel and quantity per CTA
+      float *slot = exch + 256;  // [4 warps][2][128]
       if ((lane & 1) == 0) {
 #pragma unroll
         for (int jc = 0; jc < 8; ++jc)
           if (jc * 16 < Npad) {
-            atomicAdd(&exch[jc * 16 + (lane >> 1)], acc_s[jc]);
-            atomicAdd(&exch[128 + jc * 16 + (lane >> 1)], acc_q[jc]);
+            slot[(warp * 2 + 0) * 128 + jc * 16 + (lane >> 1)] = acc_s[jc];
+            slot[(warp * 2 + 1) * 128 + jc * 16 + (lane >> 1)] = acc_q[jc];
           }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (px < job.Cout) {
-        atomicAdd(job.stats + px, (double)exch[px]);
-        atomicAdd(job.stats + job.Cout + px, (double)exch[128 + px]);
+        float ssum = 0.f, qsum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { ssum += slot[(w * 2 + 0) * 128 + px]; qsum += slot[(w * 2 + 1) * 128 + px]; }
+        atomicAdd(job.stats + px, (double)ssum);
+        atomicAdd(job.stats + job.Cout + px, (double)qsum);
       }
     }
   }
@@ -370,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
 static size_t tc_fixed_smem(const ConvJob &job) {
   return (size_t)kNA * 2 * job.stage16 * 16 + sizeof(TcShared) + 128 +
-         (job.xfold_kw ? (size_t)kTileM * kExchPitch * 4 : (size_t)2 * 128 * 4);
+         (job.xfold_kw ? (size_t)kTileM * kExchPitch * 4 : (size_t)(256 + 4 * 2 * 128) * 4);
 }
 size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
 

@@ -106,6 +106,7 @@ int launch_in_stats(const RawTensor &raw, double *sums, cudaStream_t st) {
 }
 
 // ---- in_apply ----------------------------------------------------------------------------------------
+constexpr int kApplyIter = 4;  // pixels per thread: amortises the per-block finalisation
 // mean / gamma*rstd / beta of the block's 8 channels are derived from the (double) sums by the first 8 threads:
 // biased variance, eps inside the sqrt (nn.SpatialBatchNormalization in training mode, InstanceNormalization.lua:39-50)
 __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const double *__restrict__ sums,
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const doub
                                                        double inv_count, double eps, int relu, Operand skip, int has_skip,
                                                        int shave, Operand dst) {
   __shared__ float s_mean[8], s_scale[8], s_beta[8];
-  int x = blockIdx.x * 128 + threadIdx.x;
+  const int xbase = blockIdx.x * (128 * kApplyIter) + threadIdx.x;
   int y = blockIdx.y, cb = blockIdx.z;
   if (threadIdx.x < 8) {
     int c = cb * 8 + threadIdx.x;
@@ -125,8 +126,11 @@ __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const doub
     s_beta[threadIdx.x] = beta[c];
   }
   __syncthreads();
-  if (x >= raw.W) return;
   const float4 *rp = reinterpret_cast<const float4 *>(raw.p);
+#pragma unroll
+  for (int it = 0; it < kApplyIter; ++it) {
+  const int x = xbase + it * 128;
+  if (x >= raw.W) return;
   float4 a = __ldg(rp + raw.off4(y, 2 * cb, x)), b = __ldg(rp + raw.off4(y, 2 * cb + 1, x));
   float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -143,11 +147,12 @@ __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const doub
   }
   int64_t o = dst.off16(dst.padT + y, cb, dst.padL + x);
   split_store8(v, reinterpret_cast<uint4 *>(dst.hi) + o, reinterpret_cast<uint4 *>(dst.lo) + o);
+  }
 }
 
 int launch_in_apply(const RawTensor &raw, const double *sums, const float *gamma, const float *beta, float eps, int relu,
                     const Operand *skip, int shave, const Operand &dst, cudaStream_t st) {
-  dim3 grid(ceil_div(raw.W, 128), raw.H, raw.C / 8);
+  dim3 grid(ceil_div(raw.W, 128 * kApplyIter), raw.H, raw.C / 8);
   Operand sk = skip ? *skip : Operand();
   in_apply_kernel<<<grid, 128, 0, st>>>(raw, sums, gamma, beta, 1.0 / ((double)raw.H * raw.W), (double)eps, relu, sk,
                                         skip ? 1 : 0, shave, dst);

@@ -23,7 +23,7 @@ void set_error(const char *fmt, ...) {
 std::atomic<uint64_t> g_launches{0};
 // mirror of conv_tc.cu: kNA = 2 patch stages, up to 16 weight slots (resident when every chunk fits)
 static size_t tc_fixed_smem(const ConvJob &job) {
-  return (size_t)2 * 2 * job.stage16 * 16 + 512 + (job.xfold_kw ? (size_t)128 * 33 * 4 : (size_t)1024);
+  return (size_t)2 * 2 * job.stage16 * 16 + 512 + (job.xfold_kw ? (size_t)128 * 33 * 4 : (size_t)(256 + 1024) * 4);
 }
 size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
 void conv_tc_choose_slots(ConvJob &job) {
@@ -79,9 +79,9 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
     if (conv_tc_smem_bytes(j) > 227 * 1024) { set_error("smem budget"); return 3; }
     const int Npad = j.Npad;
     std::vector<uint16_t> st_hi((size_t)j.stage16 * 8), st_lo((size_t)j.stage16 * 8);
-    std::vector<double> acc((size_t)kTileM * Npad);
+    std::vector<double> acc((size_t)2 * kTileM * Npad);
     for (int tile = 0; tile < j.ntiles; ++tile) {
-      const int y = tile / j.tiles_x, x0 = (tile % j.tiles_x) * j.tile_dx;
+      const int y = (tile / j.tiles_x) * j.mt, x0 = (tile % j.tiles_x) * j.tile_dx;
       std::fill(acc.begin(), acc.end(), 0.0);
       for (int g = 0; g < j.ngroups; ++g) {
         // A producer
@@ -105,17 +105,19 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
           const uint16_t *b_hi = chunk, *b_lo = chunk + (size_t)j.spc * 2 * Npad * 8;
           for (int st = 0; st < j.spc; ++st) {
             const KStep ks = j.steps[ch * j.spc + st];
-            mma_count += 3;
+            mma_count += 3 * j.mt;
+            for (int t = 0; t < j.mt; ++t)
             for (int m = 0; m < kTileM; ++m)
               for (int u = 0; u < 2; ++u) {
-                int64_t a16 = (int64_t)ks.a_off16 + (int64_t)u * ks.lbo16 + m;  // row m: +16 B (SBO = 8 rows * 16 B)
+                // row m: +16 B (SBO = 8 rows * 16 B); second output row of an mt=2 unit: one patch row lower
+                int64_t a16 = (int64_t)ks.a_off16 + (int64_t)u * ks.lbo16 + m + (int64_t)t * j.CbG * j.pslab16;
                 if (a16 >= j.stage16) { set_error("A desc OOB"); return 6; }
                 for (int i = 0; i < 8; ++i) {
                   double ah = h2f_bits(st_hi[a16 * 8 + i]), al = h2f_bits(st_lo[a16 * 8 + i]);
                   for (int n = 0; n < Npad; ++n) {
                     int64_t b16 = (int64_t)st * 2 * Npad + (int64_t)u * Npad + n;
                     double bh = h2f_bits(b_hi[b16 * 8 + i]), bl = h2f_bits(b_lo[b16 * 8 + i]);
-                    acc[(size_t)m * Npad + n] += ah * bh + al * bh + ah * bl;
+                    acc[((size_t)t * kTileM + m) * Npad + n] += ah * bh + al * bh + ah * bl;
                   }
                 }
               }
@@ -136,13 +138,14 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
         }
         continue;
       }
+      for (int t = 0; t < j.mt; ++t)
       for (int m = 0; m < kTileM; ++m) {
         int xx = x0 + m;
-        if (xx >= j.Wo) continue;
-        int yo = y * j.oy_mul + j.oy_off, xo = xx * j.ox_mul + j.ox_off;
+        if (xx >= j.Wo || y + t >= j.Ho) continue;
+        int yo = (y + t) * j.oy_mul + j.oy_off, xo = xx * j.ox_mul + j.ox_off;
         if (yo >= Ho || xo >= Wo) { set_error("output OOB"); return 7; }
         written[(size_t)yo * Wo + xo]++;
-        for (int n = 0; n < cout; ++n) out[((size_t)n * Ho + yo) * Wo + xo] = acc[(size_t)m * Npad + n];
+        for (int n = 0; n < cout; ++n) out[((size_t)n * Ho + yo) * Wo + xo] = acc[((size_t)t * kTileM + m) * Npad + n];
       }
     }
   }
