@@ -35,7 +35,7 @@ struct ConvJob {
   int pslab16;   // patch slab pitch (16-byte units) per (row, cb)
   int stage16;   // one A stage (hi or lo) in 16-byte units
   int nchunks, spc;  // weight chunks per group, K16 steps per chunk
-  KStep steps[kMaxSteps];
+  KStep steps[kMaxSteps + 8];  // +spare: the issue loop reads kMaxSpc entries per chunk
   const uint4 *b;  // packed weights: [group][chunk][hi|lo][step][k8 half][Npad] x 16 B
   int chunk16;     // 2 * spc * 2 * Npad
   int Npad, Cout;
@@ -47,9 +47,13 @@ struct ConvJob {
   // weight pipeline: b_slots ring slots of chunk16*16 bytes; b_resident: every chunk of the job has its own slot,
   // is loaded once per CTA and never released (small layers: no per-tile weight traffic)
   int b_slots, b_resident;
+  int a_stages;  // patch pipeline depth (2..4), chosen from the shared-memory budget
   // mt: output rows per work unit (1 or 2).  mt = 2 shares every weight chunk and the overlapping patch rows between
   // two vertically adjacent 128-pixel tiles (M = 256, two TMEM accumulators): halves the weight traffic per pixel.
   int mt;
+  // timing ablations (env FAV_DBG, diagnostics only; results are wrong when non-zero): 1 = no epilogue stores/stats,
+  // 2 = 16-byte weight copies, 4 = 16-byte patch copies, 8 = epilogue skips the TMEM loads too
+  int dbg;
   // fused InstanceNorm statistics: per-channel sum / sum of squares of the stored values (double, atomics), or null
   double *stats;
   // output placement: raw(y*oy_mul + oy_off, x*ox_mul + ox_off)

@@ -157,7 +157,7 @@ static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
   const int step_bytes = 2 * 2 * ph.Npad * 16;
   ph.spc = 1;
   for (int d = 1; d <= spg; ++d)
-    if (spg % d == 0 && d * step_bytes <= kChunkCapBytes) ph.spc = d;
+    if (spg % d == 0 && d * step_bytes <= kChunkCapBytes && d <= 8) ph.spc = d;  // 8 = kMaxSpc of conv_tc.cu
   ph.nchunks = spg / ph.spc;
   return FAV_OK;
 }

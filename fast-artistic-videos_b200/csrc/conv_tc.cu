@@ -27,14 +27,15 @@
 
 namespace fav {
 
-constexpr int kNA = 2;
+constexpr int kMaxA = 4;  // patch stages
+constexpr int kMaxSpc = 8;  // K16 steps per weight chunk (conv_plan.hpp caps spc at this)
 constexpr int kMaxB = 16;  // weight slots (ring or resident)
 constexpr int kTmemCols = 512;  // 2 accumulator stages x mt (<= 2) tiles x Npad (<= 128) columns
 constexpr int kThreads = 224;
 constexpr int kExchPitch = 33;  // fp32 words per pixel in the x-fold exchange buffer (odd: conflict-free)
 
 struct __align__(16) TcShared {
-  uint64_t a_full[kNA], a_empty[kNA], b_full[kMaxB], b_empty[kMaxB], t_full[2], t_empty[2];
+  uint64_t a_full[kMaxA], a_empty[kMaxA], b_full[kMaxB], b_empty[kMaxB], t_full[2], t_empty[2];
   uint32_t tmem_base;
   uint32_t pad_;
 };
@@ -144,14 +145,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t a_stage_bytes = (uint32_t)job.stage16 * 16u;  // one of hi / lo
   const uint32_t chunk_bytes = (uint32_t)job.chunk16 * 16u;
   uint8_t *a_base = smem;                                   // stage s: hi | lo
-  uint8_t *b_base = a_base + kNA * 2 * a_stage_bytes;       // slot s: [hi steps][lo steps]
+  const uint32_t nstages = (uint32_t)job.a_stages;
+  uint8_t *b_base = a_base + nstages * 2 * a_stage_bytes;   // slot s: [hi steps][lo steps]
   const uint32_t nslots = (uint32_t)job.b_slots;
   TcShared *sh = reinterpret_cast<TcShared *>(b_base + nslots * chunk_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNA; ++i) { mbar_init(&sh->a_full[i], 1); mbar_init(&sh->a_empty[i], 1); }
+    for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], 1); mbar_init(&sh->a_empty[i], 1); }
     for (int i = 0; i < kMaxB; ++i) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], 1); mbar_init(&sh->t_empty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -174,14 +176,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int per_row = job.CbG * job.nseg * 2;  // copies per patch row (x2: hi, lo)
     const int ncopies = job.nrows * per_row;
     uint32_t stage_tx = 0;
-    for (int s = 0; s < job.nseg; ++s) stage_tx += (uint32_t)job.seg_len16[s] * 16u;
+    for (int s = 0; s < job.nseg; ++s) stage_tx += (job.dbg & 4) ? 16u : (uint32_t)job.seg_len16[s] * 16u;
     stage_tx *= (uint32_t)(job.nrows * job.CbG * 2);
-    uint32_t it = 0;
+    uint32_t s = 0, ph = 0;
     for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
       const int yu = tile / job.tiles_x, x0 = (tile - yu * job.tiles_x) * job.tile_dx;
       const int y = yu * job.mt;
-      for (int g = 0; g < ngroups; ++g, ++it) {
-        const uint32_t s = it % kNA, ph = (it / kNA) & 1;
+      for (int g = 0; g < ngroups; ++g) {
         mbar_wait(&sh->a_empty[s], ph ^ 1);
         if (lane == 0) mbar_arrive_expect_tx(&sh->a_full[s], stage_tx);
         __syncwarp();
@@ -196,23 +197,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint4 *src = (part ? job.a_lo : job.a_hi) + src16;
           uint8_t *dst = stage + part * a_stage_bytes +
                          (uint32_t)((ri * job.CbG + cbi) * job.pslab16 + job.seg_dst16[seg]) * 16u;
-          bulk_g2s(dst, src, (uint32_t)job.seg_len16[seg] * 16u, &sh->a_full[s]);
+          bulk_g2s(dst, src, (job.dbg & 4) ? 16u : (uint32_t)job.seg_len16[seg] * 16u, &sh->a_full[s]);
         }
+        if (++s == nstages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 5) {
     // ===== B producer: weight chunks =====
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
         if (job.b_resident && tile != (int)blockIdx.x) break;  // resident weights: one pass fills every slot
         for (int g = 0; g < ngroups; ++g)
-          for (int c = 0; c < nchunks; ++c, ++it) {
-            const uint32_t s = it % nslots, ph = (it / nslots) & 1;
+          for (int c = 0; c < nchunks; ++c) {
             mbar_wait(&sh->b_empty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&sh->b_full[s], chunk_bytes);
-            bulk_g2s(b_base + s * chunk_bytes, job.b + (int64_t)(g * nchunks + c) * job.chunk16, chunk_bytes,
-                     &sh->b_full[s]);
+            const uint32_t cb = (job.dbg & 2) ? 16u : chunk_bytes;
+            mbar_arrive_expect_tx(&sh->b_full[s], cb);
+            bulk_g2s(b_base + s * chunk_bytes, job.b + (int64_t)(g * nchunks + c) * job.chunk16, cb, &sh->b_full[s]);
+            if (++s == nslots) { s = 0; ph ^= 1; }
           }
       }
     }
@@ -224,51 +226,91 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
     // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | ((uint32_t)(Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-    // descriptor high word: SBO = 8 (128 B between 8-row groups), version 1 (bit 46), no swizzle
-    const uint64_t desc_hi = ((uint64_t)8 << 32) | (1ull << 46);
-    const uint64_t b_desc_base = desc_hi | ((uint64_t)Npad << 16);  // LBO = Npad * 16 B between the two K halves
+    // Matrix descriptors (K-major, no swizzle).  High word is constant: SBO = 8 (128 B between 8-row groups) and
+    // descriptor version 1 (bit 46).  Low word = start address>>4 | LBO<<16.  A KStep table entry is exactly the
+    // 32-bit word (a_off16 | lbo16 << 16), so the A descriptor of a step is one add on the uniform datapath; the
+    // dependent chain in front of each UTCHMMA is kept to that single add (the uniform pipe is slow on long chains:
+    // ~250 cycles/step when the descriptors were rebuilt per step, measured with FAV_DBG ablations).
+    const uint32_t desc_hi = 8u | (1u << 14);
     const uint32_t b_step16 = 2u * (uint32_t)Npad, b_lo16 = (uint32_t)spc * b_step16;
     const uint32_t a_tile16 = (uint32_t)(job.CbG * job.pslab16);  // mt = 2: second output row = one patch row lower
     const uint32_t a_stage16 = (uint32_t)job.stage16;
-    uint32_t ita = 0, itb = 0, tl = 0;
+    const uint32_t *steps32 = reinterpret_cast<const uint32_t *>(job.steps);
+    const bool two = job.mt == 2;
+    // NOTE: no runtime integer division / modulo on this warp: ~150 cycles each on the issue path (measured with
+    // tools/mma_bench.cu); ring positions are wrap counters.
+    uint32_t sa = 0, aph = 0, tl = 0, sb = 0, bph = 0;
     for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x, ++tl) {
       const uint32_t as = tl & 1, tph = (tl >> 1) & 1;
       mbar_wait(&sh->t_empty[as], tph ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * 256u;
+      const uint32_t d0 = tmem_base + as * 256u, d1 = d0 + 128u;
+      if (job.b_resident) sb = 0;
       uint32_t accumulate = 0;
-      for (int g = 0; g < ngroups; ++g, ++ita) {
-        const uint32_t sa = ita % kNA;
-        mbar_wait(&sh->a_full[sa], (ita / kNA) & 1);
+      for (int g = 0; g < ngroups; ++g) {
+        mbar_wait(&sh->a_full[sa], aph);
         tc_fence_after();
         const uint32_t a_hi16 = smem_u32(a_base + sa * 2 * a_stage_bytes) >> 4, a_lo16 = a_hi16 + a_stage16;
-        for (int c = 0; c < nchunks; ++c, ++itb) {
-          // resident: slot = chunk index, filled once (waiting on parity 0 stays satisfied afterwards)
-          const uint32_t sb = job.b_resident ? (uint32_t)(g * nchunks + c) : itb % nslots;
-          mbar_wait(&sh->b_full[sb], job.b_resident ? 0u : (itb / nslots) & 1);
+        int sidx = 0;
+        for (int c = 0; c < nchunks; ++c) {
+          // ring: slot sb, phase bph.  resident: slot = chunk index, filled once (parity 0 stays satisfied afterwards)
+          mbar_wait(&sh->b_full[sb], job.b_resident ? 0u : bph);
           tc_fence_after();
-          const uint32_t b_hi16 = smem_u32(b_base + sb * chunk_bytes) >> 4;
-          for (int st = 0; st < spc; ++st) {
-            const KStep ks = job.steps[c * spc + st];
-            const uint64_t a_desc_base = desc_hi | ((uint64_t)ks.lbo16 << 16);
-            const uint64_t ad_hi = a_desc_base | (uint64_t)(a_hi16 + ks.a_off16), ad_lo = a_desc_base | (uint64_t)(a_lo16 + ks.a_off16);
-            const uint64_t bd_hi = b_desc_base | (uint64_t)(b_hi16 + st * b_step16),
-                           bd_lo = b_desc_base | (uint64_t)(b_hi16 + b_lo16 + st * b_step16);
+          const uint32_t bh = (smem_u32(b_base + sb * chunk_bytes) >> 4) | ((uint32_t)Npad << 16);  // LBO = Npad * 16 B
+          if (Npad >= 128) {
+            // wide MMAs (>= 64 cycles each): one divergent region per K step is cheap enough and measured fastest
+            for (int st = 0; st < spc; ++st, ++sidx) {
+              const uint32_t dls = steps32[sidx];
+              const uint32_t bs = bh + (uint32_t)st * b_step16;
+              const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + dls), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + dls);
+              const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | bs, bd_lo = ((uint64_t)desc_hi << 32) | (bs + b_lo16);
+              if (leader) {
+                tc_mma_f16(d0, ad_hi, bd_hi, idesc, accumulate);
+                tc_mma_f16(d0, ad_lo, bd_hi, idesc, 1);
+                tc_mma_f16(d0, ad_hi, bd_lo, idesc, 1);
+                if (two) {  // second output row: same weights, patch shifted by one row
+                  tc_mma_f16(d1, ad_hi + a_tile16, bd_hi, idesc, accumulate);
+                  tc_mma_f16(d1, ad_lo + a_tile16, bd_hi, idesc, 1);
+                  tc_mma_f16(d1, ad_hi + a_tile16, bd_lo, idesc, 1);
+                }
+              }
+              accumulate = 1;
+            }
+          } else {
+          // All descriptors of the chunk are formed first (uniform datapath), then the elected lane issues every MMA of
+            // the chunk inside ONE divergent region: a reconvergence point (BSYNC) between MMA groups makes the warp
+            // wait for the previous UTCHMMAs to leave the scoreboard and serialises them (~2x slower at small N,
+            // measured with FAV_DBG=16).  spc <= kMaxSpc, guarded by warp-uniform predicates.
+            uint32_t dl[kMaxSpc];
+#pragma unroll
+            for (int st = 0; st < kMaxSpc; ++st) dl[st] = steps32[sidx + st];  // table is padded: reads stay in bounds
+            sidx += spc;
             if (leader) {
-              tc_mma_f16(d_tmem, ad_hi, bd_hi, idesc, accumulate);
-              tc_mma_f16(d_tmem, ad_lo, bd_hi, idesc, 1);
-              tc_mma_f16(d_tmem, ad_hi, bd_lo, idesc, 1);
-              if (job.mt == 2) {  // second output row: same weights, patch shifted by one row
-                tc_mma_f16(d_tmem + 128u, ad_hi + a_tile16, bd_hi, idesc, accumulate);
-                tc_mma_f16(d_tmem + 128u, ad_lo + a_tile16, bd_hi, idesc, 1);
-                tc_mma_f16(d_tmem + 128u, ad_hi + a_tile16, bd_lo, idesc, 1);
+#pragma unroll
+              for (int st = 0; st < kMaxSpc; ++st) {
+                if (st < spc) {
+                  const uint32_t bs = bh + (uint32_t)st * b_step16;
+                  const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + dl[st]), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + dl[st]);
+                  const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | bs, bd_lo = ((uint64_t)desc_hi << 32) | (bs + b_lo16);
+                  tc_mma_f16(d0, ad_hi, bd_hi, idesc, accumulate);
+                  tc_mma_f16(d0, ad_lo, bd_hi, idesc, 1);
+                  tc_mma_f16(d0, ad_hi, bd_lo, idesc, 1);
+                  if (two) {  // second output row: same weights, patch shifted by one row
+                    tc_mma_f16(d1, ad_hi + a_tile16, bd_hi, idesc, accumulate);
+                    tc_mma_f16(d1, ad_lo + a_tile16, bd_hi, idesc, 1);
+                    tc_mma_f16(d1, ad_hi + a_tile16, bd_lo, idesc, 1);
+                  }
+                  accumulate = 1;
+                }
               }
             }
-            accumulate = 1;
           }
+          accumulate = 1;
           if (!job.b_resident && leader) tc_commit(&sh->b_empty[sb]);  // frees the weight slot when the MMAs retire
+          if (++sb == nslots) { sb = 0; bph ^= 1; }
         }
         if (leader) tc_commit(&sh->a_empty[sa]);  // frees the patch stage
+        if (++sa == nstages) { sa = 0; aph ^= 1; }
       }
       if (leader) tc_commit(&sh->t_full[as]);  // accumulator complete -> epilogue
     }
@@ -287,11 +329,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t as = tl & 1, tph = (tl >> 1) & 1;
       mbar_wait(&sh->t_full[as], tph);
       tc_fence_after();
+      if (job.dbg & 8) { tc_fence_before(); mbar_arrive(&sh->t_empty[as]); continue; }
       for (int t = 0; t < job.mt; ++t) {
       const int y = yu * job.mt + t;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 256u + (uint32_t)t * 128u;
       const int yo = y * job.oy_mul + job.oy_off, xo = x * job.ox_mul + job.ox_off;
-      const bool valid = x < job.Wo && y < job.Ho;
+      const bool valid = x < job.Wo && y < job.Ho && !(job.dbg & 1);
       if (job.xfold_kw) {
         // partial sums Q[pixel][kx*Cout + co] -> shared memory, then out[x][co] = sum_kx Q[x + kx][kx*Cout + co]
         for (int c0 = 0; c0 < Npad; c0 += 16) {
@@ -389,14 +432,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 }
 
 static size_t tc_fixed_smem(const ConvJob &job) {
-  return (size_t)kNA * 2 * job.stage16 * 16 + sizeof(TcShared) + 128 +
+  return (size_t)job.a_stages * 2 * job.stage16 * 16 + sizeof(TcShared) + 128 +
          (job.xfold_kw ? (size_t)kTileM * kExchPitch * 4 : (size_t)(256 + 4 * 2 * 128) * 4);
 }
 size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
 
 void conv_tc_choose_slots(ConvJob &job) {
-  const size_t budget = 224 * 1024, chunk = (size_t)job.chunk16 * 16, fixed = tc_fixed_smem(job);
+  const size_t budget = 224 * 1024, chunk = (size_t)job.chunk16 * 16;
   const int total = job.ngroups * job.nchunks;
+  job.a_stages = 2;
+  // small-work groups (resident weights, several groups per tile) are latency bound on the patch pipeline:
+  // deepen it while everything still fits
+  {
+    ConvJob t = job;
+    for (int n = kMaxA; n > 2; --n) {
+      t.a_stages = n;
+      if (total <= kMaxB && tc_fixed_smem(t) + total * chunk <= budget) { job.a_stages = n; break; }
+    }
+  }
+  const size_t fixed = tc_fixed_smem(job);
   if (total <= kMaxB && fixed + total * chunk <= budget) {
     job.b_resident = 1;
     job.b_slots = total;

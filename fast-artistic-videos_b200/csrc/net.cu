@@ -191,6 +191,7 @@ static int build_conv_jobs(fav_net *net, Plan &pl, PlanStep &st, const ConvDef &
     j.raw = st.raw.p; j.raw_Cq = st.raw.Cq; j.raw_Wp = st.raw.Wp;
     j.final_mode = last ? 1 : 0; j.out3 = out3; j.tanh_c = net->tanh_c;
     conv_tc_choose_slots(j);
+    if (const char *e = getenv("FAV_DBG")) j.dbg = atoi(e);
     if (conv_tc_smem_bytes(j) > 227 * 1024) {
       set_error("conv %s: shared memory budget exceeded", c.name.c_str());
       return FAV_ERR_UNSUPPORTED;

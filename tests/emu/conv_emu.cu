@@ -23,12 +23,21 @@ void set_error(const char *fmt, ...) {
 std::atomic<uint64_t> g_launches{0};
 // mirror of conv_tc.cu: kNA = 2 patch stages, up to 16 weight slots (resident when every chunk fits)
 static size_t tc_fixed_smem(const ConvJob &job) {
-  return (size_t)2 * 2 * job.stage16 * 16 + 512 + (job.xfold_kw ? (size_t)128 * 33 * 4 : (size_t)(256 + 1024) * 4);
+  return (size_t)job.a_stages * 2 * job.stage16 * 16 + 640 + (job.xfold_kw ? (size_t)128 * 33 * 4 : (size_t)(256 + 1024) * 4);
 }
 size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
 void conv_tc_choose_slots(ConvJob &job) {
-  const size_t budget = 224 * 1024, chunk = (size_t)job.chunk16 * 16, fixed = tc_fixed_smem(job);
+  const size_t budget = 224 * 1024, chunk = (size_t)job.chunk16 * 16;
   const int total = job.ngroups * job.nchunks;
+  job.a_stages = 2;
+  {
+    ConvJob t = job;
+    for (int n = 4; n > 2; --n) {
+      t.a_stages = n;
+      if (total <= 16 && tc_fixed_smem(t) + total * chunk <= budget) { job.a_stages = n; break; }
+    }
+  }
+  const size_t fixed = tc_fixed_smem(job);
   if (total <= 16 && fixed + total * chunk <= budget) { job.b_resident = 1; job.b_slots = total; }
   else { job.b_resident = 0; int n = (int)((budget - fixed) / chunk); job.b_slots = n > 16 ? 16 : (n < 2 ? 2 : n); }
 }

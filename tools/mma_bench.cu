@@ -12,15 +12,17 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
                ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
-struct Cfg { int N; int layout; uint32_t a_lbo16, a_sbo16, b_lbo16, b_sbo16; int n_mma; int same_acc; int a_stride_bytes; };
+struct Cfg { int N; int layout; uint32_t a_lbo16, a_sbo16, b_lbo16, b_sbo16; int n_mma; int same_acc; int a_stride_bytes; int every; int what; int shift; int b_stride_bytes; };
 
-__global__ void __launch_bounds__(128, 1) bench(Cfg c, long long *out) {
+__global__ void __launch_bounds__(224, 1) bench(Cfg c, long long *out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t bars[8];
   __shared__ uint32_t tmem_base_s;
-  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = (c.what & 8) ? (0x3c003c00u ^ ((uint32_t)i * 2654435761u & 0x03ff03ffu)) : 0u;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[i])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 32) {
@@ -43,11 +45,24 @@ __global__ void __launch_bounds__(128, 1) bench(Cfg c, long long *out) {
     };
     long long t0 = clock64();
     const uint64_t ad0 = desc(a0, c.a_lbo16, c.a_sbo16), bd0 = desc(b0, c.b_lbo16, c.b_sbo16);
-    const uint32_t astep = (uint32_t)c.a_stride_bytes >> 4;
+    const uint32_t astep = (uint32_t)c.a_stride_bytes >> 4, bstep = (uint32_t)c.b_stride_bytes >> 4;
 #pragma unroll 8
     for (int i = 0; i < c.n_mma; ++i) {
-      uint64_t ad = ad0 + (uint64_t)((i & 7) * astep), bd = bd0 + (uint64_t)((i & 3) * 2);
+      uint64_t ad = ad0 + (uint64_t)((i & 15) * astep), bd = bd0 + (uint64_t)((i & 7) * bstep);
       if (leader) mma(tmem + (c.same_acc ? 0 : (i & 1) * 256), ad, bd, idesc, i > 0);
+      if (c.every && (i & (c.every - 1)) == c.every - 1) {
+        if ((c.what & 1) && leader)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[(i >> c.shift) & 7])) : "memory");
+        if (c.what & 2) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (c.what & 4) {  // wait for the commit issued 4 intervals ago (ring of 8 barriers, like a weight-slot ring)
+          int k = i >> c.shift;
+          if (k >= 4) {
+            uint32_t done = 0; uint32_t par = ((k - 4) >> 3) & 1;
+            while (!done)
+              asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bars[(k - 4) & 7])), "r"(par) : "memory");
+          }
+        }
+      }
     }
     if (leader) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     uint32_t done = 0;
@@ -55,6 +70,18 @@ __global__ void __launch_bounds__(128, 1) bench(Cfg c, long long *out) {
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
     long long t1 = clock64();
     if (leader) out[blockIdx.x] = t1 - t0;
+  }
+  else if (c.what & 16) {
+    // polling warps: wait for the final commit exactly like the conv kernel's epilogue / producer warps do
+    uint32_t done = 0;
+    const bool one_lane = (c.what & 32) != 0;
+    if (!one_lane || (threadIdx.x & 31) == 0) {
+      while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+        if ((c.what & 64) && !done) __nanosleep(200);
+      }
+    }
+    __syncwarp();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -65,24 +92,17 @@ int main() {
   long long *d; cudaMalloc(&d, 148 * 8);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   struct { const char *name; Cfg c; } cfgs[] = {
-      // name                       N  layout  a_lbo a_sbo b_lbo b_sbo  n   same stride
-      {"noswz N128 mine(lbo2080)", {128, 0, 130, 8, 128, 8, 2000, 1, 16}},
-      {"noswz N128 dense(lbo128)", {128, 0, 8, 16, 8, 16, 2000, 1, 16}},     // core matrices of a K pair adjacent
-      {"noswz N32  mine",          {32, 0, 130, 8, 32, 8, 2000, 1, 16}},
-      {"noswz N16  mine",          {16, 0, 130, 8, 16, 8, 2000, 1, 16}},
-      {"noswz N128 lbo=1(16B)",    {128, 0, 1, 8, 128, 8, 2000, 1, 16}},
-      {"sw128 N128",               {128, 2, 1, 64, 1, 64, 2000, 1, 32}},
-      {"sw128 N32",                {32, 2, 1, 64, 1, 64, 2000, 1, 32}},
-      {"sw128 N256",               {256, 2, 1, 64, 1, 64, 2000, 1, 32}},
-      {"sw64  N128",               {128, 4, 1, 32, 1, 32, 2000, 1, 32}},
-      {"sw32  N128",               {128, 6, 1, 16, 1, 16, 2000, 1, 32}},
-      {"noswz N128 mine alt-acc",  {128, 0, 130, 8, 128, 8, 2000, 0, 16}},
-      {"noswz N256 mine",          {256, 0, 130, 8, 256, 8, 2000, 1, 16}},
-      {"noswz N64 mine",           {64, 0, 130, 8, 64, 8, 2000, 1, 16}},
+      {"N32  no pollers",                      {32, 0, 130, 8, 32, 8, 4096, 1, 4096, 0, 8, 0, 1024}},
+      {"N32  6 warps polling (32 lanes)",      {32, 0, 130, 8, 32, 8, 4096, 1, 4096, 0, 8 | 16, 0, 1024}},
+      {"N32  6 warps polling (1 lane)",        {32, 0, 130, 8, 32, 8, 4096, 1, 4096, 0, 8 | 16 | 32, 0, 1024}},
+      {"N32  6 warps polling + nanosleep",     {32, 0, 130, 8, 32, 8, 4096, 1, 4096, 0, 8 | 16 | 64, 0, 1024}},
+      {"N128 no pollers",                      {128, 0, 130, 8, 128, 8, 4096, 1, 4096, 0, 8, 0, 4096}},
+      {"N128 6 warps polling (32 lanes)",      {128, 0, 130, 8, 128, 8, 4096, 1, 4096, 0, 8 | 16, 0, 4096}},
+      {"N128 6 warps polling + nanosleep",     {128, 0, 130, 8, 128, 8, 4096, 1, 4096, 0, 8 | 16 | 64, 0, 4096}},
   };
-  for (int g = 1; g <= 148; g += 147) {
+  for (int g = 148; g <= 148; g += 147) {
     for (auto &e : cfgs) {
-      bench<<<g, 128, 200 * 1024>>>(e.c, d);
+      bench<<<g, 224, 200 * 1024>>>(e.c, d);
       cudaError_t err = cudaDeviceSynchronize();
       long long h[148];
       cudaMemcpy(h, d, g * 8, cudaMemcpyDeviceToHost);
