@@ -94,6 +94,8 @@ int launch_pack_input(const float *in, int Cin, int H, int W, int reflect, const
 int launch_in_stats(const RawTensor &raw, double *sums /*[2*C]*/, cudaStream_t st);
 int launch_in_apply(const RawTensor &raw, const double *sums, const float *gamma, const float *beta, float eps, int relu,
                     const Operand *skip, int shave, const Operand &dst, cudaStream_t st);
+int launch_up_in(const Operand &src, double *sums, const float *gamma, const float *beta, float eps, int relu, int scale,
+                 const Operand &dst, cudaStream_t st);
 int launch_unpack_operand(const Operand &src, float *out_nchw, cudaStream_t st);
 
 }  // namespace fav

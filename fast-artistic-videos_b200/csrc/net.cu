@@ -38,14 +38,16 @@ struct InDef {
 
 // arch-level program
 struct SpecOp {
-  int kind;  // 0 conv(+in+relu), 1 res block
+  int kind;  // 0 conv(+in+relu), 1 res block, 2 nearest upsampling (+in+relu)
+  int scale = 1;
   int conv[2] = {-1, -1};
   int inorm[2] = {-1, -1};
   bool relu = false, last = false;
 };
 
 struct PlanStep {
-  int kind;  // 0 conv, 1 instance norm (+relu, +skip) -> operand
+  int kind;  // 0 conv, 1 instance norm (+relu, +skip) -> operand, 2 nearest upsampling + instance norm + relu
+  int scale = 1;
   int conv = -1, inorm = -1;
   int src = -1, dst = -1, skip = -1;
   int relu = 0;
@@ -230,6 +232,7 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
   {
     int h = H + 2 * R, w = W + 2 * R;
     for (auto &op : net->ops) {
+      if (op.kind == 2) { h *= op.scale; w *= op.scale; stats_slots += 2 * net->inorms[op.inorm[0]].C; continue; }
       int n = op.kind == 1 ? 2 : 1;
       for (int i = 0; i < n; ++i) {
         const ConvDef &c = net->convs[op.conv[i]];
@@ -250,13 +253,30 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
 
   // flat list of convs in execution order, to look up the consumer of each operand
   std::vector<int> order;
-  for (auto &op : net->ops) { order.push_back(op.conv[0]); if (op.kind == 1) order.push_back(op.conv[1]); }
+  for (auto &op : net->ops) {
+    if (op.kind == 2) continue;
+    order.push_back(op.conv[0]);
+    if (op.kind == 1) order.push_back(op.conv[1]);
+  }
   size_t pos = 0;
   int cur;
   FAV_TRY(make_operand(*pl, net->in_dim, H + 2 * R, W + 2 * R, &net->convs[order[0]], &cur));
   int stats_off = 0;
   for (size_t oi = 0; oi < net->ops.size(); ++oi) {
     const SpecOp &op = net->ops[oi];
+    if (op.kind == 2) {  // UX: operand -> upsampled, normalised operand for the next convolution
+      PlanStep us;
+      us.kind = 2; us.scale = op.scale; us.inorm = op.inorm[0]; us.src = cur; us.relu = 1; us.stats_off = stats_off;
+      const int C = net->inorms[op.inorm[0]].C;
+      stats_off += 2 * C;
+      const ConvDef *consumer = pos < order.size() ? &net->convs[order[pos]] : nullptr;
+      FAV_TRY(make_operand(*pl, C, pl->ops[cur].H * op.scale, pl->ops[cur].W * op.scale, consumer, &us.dst));
+      cur = us.dst;
+      us.layer_index = (int)oi;
+      pl->layer_operand[(int)oi] = cur;
+      pl->steps.push_back(std::move(us));
+      continue;
+    }
     const int n = op.kind == 1 ? 2 : 1;
     const int block_in = cur;
     for (int i = 0; i < n; ++i, ++pos) {
@@ -350,6 +370,12 @@ static int run_plan(fav_net *net, Plan &pl, const float *in7, float *out3, int f
         }
       }
       FAV_TRY(end());
+    } else if (s.kind == 2) {
+      const InDef &n = net->inorms[s.inorm];
+      const Operand &src = pl.ops[s.src];
+      FAV_TRY(begin(3, 12.0 * n.C * src.H * src.W * (1.0 + s.scale * s.scale) / 2.0, n.name + ".up"));
+      FAV_TRY(launch_up_in(src, pl.stats + s.stats_off, n.d_gamma, n.d_beta, 1e-5f, s.relu, s.scale, pl.ops[s.dst], st));
+      FAV_TRY(end());
     } else {
       const InDef &n = net->inorms[s.inorm];
       double *sums = pl.stats + s.stats_off;
@@ -421,6 +447,14 @@ int fav_net_create(const char *arch, const char *padding_type, float tanh_consta
       FAV_REQUIRE(next > 0, "bad arch token '%s'", v.c_str());
       op.conv[0] = add_conv(net.get(), name, prev, next, 3, 2, 1, true, 1);
       scale /= 2;
+    } else if (c0 == 'U') {  // UX  :94-98  SpatialUpSamplingNearest(X), followed by IN + ReLU (:121-130)
+      int sc = atoi(v.c_str() + 1);
+      FAV_REQUIRE(sc >= 1 && sc <= 4 && !op.last && prev % 8 == 0, "bad arch token '%s'", v.c_str());
+      next = prev;
+      op.kind = 2; op.scale = sc;
+      op.inorm[0] = add_in(net.get(), name + ".n", next);
+      needs_bn = false;
+      scale /= sc;
     } else if (c0 == 'R') {  // RX  :109-114
       next = atoi(v.c_str() + 1);
       FAV_REQUIRE(next == prev, "residual block R%d needs %d input channels (got %d)", next, next, prev);
@@ -432,7 +466,7 @@ int fav_net_create(const char *arch, const char *padding_type, float tanh_consta
       needs_bn = false; op.relu = false;
       shrink += 4 * scale;
     } else {
-      set_error("arch token '%s' is not supported by the sm_100a path (supported: cXsY-Z, dX, uX, RX)", v.c_str());
+      set_error("arch token '%s' is not supported by the sm_100a path (supported: cXsY-Z, dX, uX, UX, RX)", v.c_str());
       return FAV_ERR_UNSUPPORTED;
     }
     if (op.last) { needs_bn = false; op.relu = false; }  // :117-120

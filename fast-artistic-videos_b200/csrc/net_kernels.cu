@@ -9,6 +9,9 @@
 
 namespace fav {
 
+constexpr int kStatRows = 8;
+constexpr int kApplyIter = 4;  // pixels per thread in the apply kernels: amortises the per-block finalisation
+
 __device__ __forceinline__ void split_store8(const float v[8], uint4 *hi_dst, uint4 *lo_dst) {
   uint32_t h[4], l[4];
 #pragma unroll
@@ -64,7 +67,6 @@ int launch_pack_input(const float *in, int Cin, int H, int W, int reflect, const
 }
 
 // ---- in_stats ----------------------------------------------------------------------------------------
-constexpr int kStatRows = 8;
 __global__ void __launch_bounds__(256) in_stats_kernel(RawTensor raw, double *__restrict__ sums) {
   const int cq = blockIdx.x;
   const int y0 = blockIdx.y * kStatRows;
@@ -106,7 +108,6 @@ int launch_in_stats(const RawTensor &raw, double *sums, cudaStream_t st) {
 }
 
 // ---- in_apply ----------------------------------------------------------------------------------------
-constexpr int kApplyIter = 4;  // pixels per thread: amortises the per-block finalisation
 // mean / gamma*rstd / beta of the block's 8 channels are derived from the (double) sums by the first 8 threads:
 // biased variance, eps inside the sqrt (nn.SpatialBatchNormalization in training mode, InstanceNormalization.lua:39-50)
 __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const double *__restrict__ sums,
@@ -157,6 +158,86 @@ int launch_in_apply(const RawTensor &raw, const double *sums, const float *gamma
   in_apply_kernel<<<grid, 128, 0, st>>>(raw, sums, gamma, beta, 1.0 / ((double)raw.H * raw.W), (double)eps, relu, sk,
                                         skip ? 1 : 0, shave, dst);
   return post_launch("in_apply");
+}
+
+// ---- nn.SpatialUpSamplingNearest(s) -> InstanceNormalization -> ReLU on an OPERAND (arch token UX) ---------------
+// models_video.lua:94-98,121-130.  Statistics of a nearest-upsampled tensor equal those of its source, so the sums
+// are taken over the source operand and the upsampling happens while the normalised values are written.
+__global__ void __launch_bounds__(256) opnd_stats_kernel(Operand src, double *__restrict__ sums) {
+  const int cb = blockIdx.x;
+  const int y0 = blockIdx.y * kStatRows;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  for (int y = y0; y < min(y0 + kStatRows, src.H); ++y)
+    for (int x = threadIdx.x; x < src.W; x += 256) {
+      float v[8];
+      int64_t o = src.off16(src.padT + y, cb, src.padL + x);
+      load_join8(reinterpret_cast<const uint4 *>(src.hi) + o, reinterpret_cast<const uint4 *>(src.lo) + o, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
+    }
+  __shared__ double red[8][16];
+  double d[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { d[i] = s[i]; d[8 + i] = q[i]; }
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d[i] += __shfl_xor_sync(0xffffffffu, d[i], o);
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) red[warp][i] = d[i];
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    int c = cb * 8 + (threadIdx.x & 7);
+    if (c < src.C) atomicAdd(sums + (threadIdx.x < 8 ? c : src.C + c), t);
+  }
+}
+
+__global__ void __launch_bounds__(128) up_apply_kernel(Operand src, const double *__restrict__ sums,
+                                                       const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                       double inv_count, double eps, int relu, int scale, Operand dst) {
+  __shared__ float s_mean[8], s_scale[8], s_beta[8];
+  const int xbase = blockIdx.x * (128 * kApplyIter) + threadIdx.x;
+  const int y = blockIdx.y, cb = blockIdx.z;
+  if (threadIdx.x < 8) {
+    int c = cb * 8 + threadIdx.x;
+    double mean = sums[c] * inv_count;
+    double var = sums[src.C + c] * inv_count - mean * mean;
+    if (var < 0) var = 0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_scale[threadIdx.x] = (float)((double)gamma[c] / sqrt(var + eps));
+    s_beta[threadIdx.x] = beta[c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < kApplyIter; ++it) {
+    const int x = xbase + it * 128;
+    if (x >= dst.W) return;
+    float v[8];
+    int64_t so = src.off16(src.padT + y / scale, cb, src.padL + x / scale);
+    load_join8(reinterpret_cast<const uint4 *>(src.hi) + so, reinterpret_cast<const uint4 *>(src.lo) + so, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = (v[i] - s_mean[i]) * s_scale[i] + s_beta[i];
+      v[i] = relu ? fmaxf(t, 0.f) : t;
+    }
+    int64_t o = dst.off16(dst.padT + y, cb, dst.padL + x);
+    split_store8(v, reinterpret_cast<uint4 *>(dst.hi) + o, reinterpret_cast<uint4 *>(dst.lo) + o);
+  }
+}
+
+int launch_up_in(const Operand &src, double *sums, const float *gamma, const float *beta, float eps, int relu, int scale,
+                 const Operand &dst, cudaStream_t st) {
+  opnd_stats_kernel<<<dim3(src.Cb, ceil_div(src.H, kStatRows)), 256, 0, st>>>(src, sums);
+  FAV_TRY(post_launch("up_in.stats"));
+  dim3 grid(ceil_div(dst.W, 128 * kApplyIter), dst.H, dst.Cb);
+  up_apply_kernel<<<grid, 128, 0, st>>>(src, sums, gamma, beta, 1.0 / ((double)src.H * src.W), (double)eps, relu, scale, dst);
+  return post_launch("up_in.apply");
 }
 
 // ---- unpack_operand (debug) -----------------------------------------------------------------------------

@@ -62,6 +62,29 @@ def test_net_forward_and_every_layer_vs_fp64_oracle(net, shape, impl):
         net.set_conv_impl("tcgen05")
 
 
+@pytest.mark.parametrize("shape", [(64, 96), (200, 256)])
+def test_paper_arch_with_nearest_upsampling(shape):
+    """The arch of the paper's released models: ...,U2,c3s1-64,U2,c9s1-3 (README.md:256): UX = nearest upsampling followed
+    by InstanceNorm + ReLU (models_video.lua:94-98,121-130)."""
+    from fav_b200 import models_video
+    from oracle import net_oracle
+
+    H, W = shape
+    net_u = models_video.synthetic_model("mosaic", synth.PAPER_ARCH)
+    ora = net_oracle.NetOracle(arch=synth.PAPER_ARCH, style="mosaic", dtype=torch.float64)
+    x7 = rand_input(H, W, 5)
+    taps = {}
+    ref = ora.forward(torch.from_numpy(x7)[None], taps)[0].numpy()
+    out = net_u.forward(T(x7)[None]).cpu().numpy()[0]
+    for i in range(len(ora.specs) - 1):
+        r = taps[f"l{i}"][0].numpy()
+        g = net_u.layer_output(i).cpu().numpy()
+        assert g.shape == r.shape and np.abs(g - r).max() < 2e-4 * max(1.0, np.abs(r).max()), f"layer {i}"
+    assert np.abs(out - ref).max() / 255.0 < TOL / 10
+    f1 = synth.make_frame(H, W, 1)
+    assert np.abs(net_u.run_image(T(f1)).cpu().numpy() - ora.run_image(f1)).max() < TOL / 10
+
+
 def test_tcgen05_agrees_with_cuda_core_comparator(net):
     x = T(rand_input(96, 160, 3))[None]
     a = net.forward(x)
