@@ -188,6 +188,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on STDOUT at communicator creation; the contract is ONE JSON line on stdout,
+        # so fd 1 points at stderr until the final print.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     K, Wm = args.steps, args.warmup
     pk = peaks()
@@ -363,7 +368,12 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "checksum": checksum,
         }
+        if world > 1:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        if world > 1:
+            os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

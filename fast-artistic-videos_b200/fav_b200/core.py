@@ -35,16 +35,19 @@ def _opt(opt, k, d=None):
 
 
 def load_model(path_or_style: str, arch: str = synth.DEFAULT_ARCH) -> models_video.StyleNet:
-    """get_model (core.lua:38-57).  Torch7 .t7 checkpoints cannot be fetched or parsed here (no network; the .t7 reader is
-    SURVEY.md §8 f-1), so a `synthetic:<style>` spec (or a bare style name) builds seeded random-init weights and a
-    `.npz` path loads a name->array state dict."""
+    """get_model (core.lua:38-57): a Torch7 `.t7` checkpoint (fav_b200/t7.py; the arch is recovered from the module
+    tree), a `.npz` state dict, or `synthetic:<style>` = seeded random-init weights (no network here to fetch the
+    released checkpoints)."""
     if path_or_style.endswith(".npz"):
         import numpy as np
 
         w = dict(np.load(path_or_style))
         return models_video.StyleNet(arch).load_state(w)
-    if path_or_style.endswith(".t7"):
-        raise _lib.FavError(_lib.FAV_ERR_UNSUPPORTED, "Torch7 .t7 checkpoints: reader not built yet (SURVEY.md §8 f-1)")
+    if path_or_style.endswith(".t7"):  # torch.load(path).model (core.lua:39-47)
+        from . import t7
+
+        t7_arch, state, tanh_c, _pad = t7.load_checkpoint(path_or_style)
+        return models_video.StyleNet(t7_arch, tanh_constant=tanh_c).load_state(state)
     style = path_or_style.split(":", 1)[-1]
     return models_video.synthetic_model(style, arch)
 
