@@ -202,3 +202,43 @@ def test_error_behaviour(net):
     assert e.value.status == _lib.FAV_ERR_INVALID
     with pytest.raises(AssertionError):
         net.forward(torch.zeros((1, 3, 64, 64), device="cuda"))
+
+
+def test_video_driver_end_to_end_files(tmp_path):
+    """fast_artistic_video.lua equivalent on files: PPM frames + .flo + PGM certainty (written by the GPU
+    consistencyChecker CLI) -> PNGs; the recurrent state is the unclamped fp32 frame, not the PNG (fav.lua:169)."""
+    from PIL import Image
+
+    from fav_b200 import consistencyChecker, t7, video
+    from oracle import net_oracle, pyoracle
+
+    H, W, n = 64, 96, 3
+    d = str(tmp_path)
+    for i in range(1, n + 1):
+        synth.write_ppm(f"{d}/frame_{i:04d}.ppm", synth.make_frame(H, W, i))
+    for i in range(2, n + 1):
+        synth.write_flo(f"{d}/backward_{i}_{i - 1}.flo", synth.make_backward_flow(H, W, i))
+        synth.write_flo(f"{d}/forward_{i - 1}_{i}.flo", synth.make_forward_flow(H, W, i))
+        consistencyChecker.main(["consistencyChecker", f"{d}/backward_{i}_{i - 1}.flo", f"{d}/forward_{i - 1}_{i}.flo",
+                                 f"{d}/reliable_{i}_{i - 1}.pgm"])
+    # weights through a Torch7 .t7 checkpoint (f-1)
+    w = synth.make_weights(synth.DEFAULT_ARCH, "candy")
+    t7.write_checkpoint(f"{d}/checkpoint-candy-video.t7", synth.DEFAULT_ARCH, w)
+    video.main(["-input_pattern", f"{d}/frame_%04d.ppm", "-flow_pattern", f"{d}/backward_[%d]_{{%d}}.flo",
+                "-occlusions_pattern", f"{d}/reliable_[%d]_{{%d}}.pgm", "-model_vid", f"{d}/checkpoint-candy-video.t7",
+                "-output_prefix", f"{d}/out", "-num_frames", str(n)])
+    # oracle on the same files (frames are 8-bit PPMs here)
+    ora = net_oracle.NetOracle(style="candy", dtype=torch.float64)
+    prev = None
+    for i in range(1, n + 1):
+        frame = np.asarray(Image.open(f"{d}/frame_{i:04d}.ppm"), np.float32).transpose(2, 0, 1) / 255.0
+        if i == 1:
+            ref = ora.run_image(frame)
+        else:
+            bw = pyoracle.flo_read(f"{d}/backward_{i}_{i - 1}.flo", 1)
+            fw = pyoracle.flo_read(f"{d}/forward_{i - 1}_{i}.flo", 1)
+            cert = pyoracle.min_filter(pyoracle.consistency(bw, fw).astype(np.float32) / 255.0, 7)
+            ref = ora.run_next_image(frame, prev, synth.checker_to_lua(bw), cert)
+        prev = ref.astype(np.float32)
+        png = np.asarray(Image.open(f"{d}/out-{i:05d}.png"), np.float32).transpose(2, 0, 1) / 255.0
+        assert np.abs(png - np.clip(ref, 0, 1)).max() <= 0.5 / 255 + TOL, i
