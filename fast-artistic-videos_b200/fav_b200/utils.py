@@ -43,3 +43,14 @@ def wait_for_file(path: str, poll_s: float = 1.0) -> None:
         while not file_exists(path):
             time.sleep(poll_s)
         time.sleep(poll_s)
+
+
+def median_filter(img: torch.Tensor, r: int) -> torch.Tensor:
+    """utils.median_filter(img, r) (utils.lua:151-159): r x r windows (unfold), lower median, VALID region
+    (H-r+1) x (W-r+1) -- on the GPU (the reference casts to a CPU FloatTensor for it)."""
+    x = img.contiguous()
+    assert x.dim() == 3 and x.dtype == torch.float32
+    C, H, W = x.shape
+    out = torch.empty((C, H - r + 1, W - r + 1), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib.fav_median_filter(_lib.dptr(x), _lib.dptr(out), C, H, W, int(r), _lib.stream_ptr()))
+    return out
