@@ -51,6 +51,13 @@ struct ConvJob {
   // mt: output rows per work unit (1 or 2).  mt = 2 shares every weight chunk and the overlapping patch rows between
   // two vertically adjacent 128-pixel tiles (M = 256, two TMEM accumulators): halves the weight traffic per pixel.
   int mt;
+  // row-fold (tall filters with a narrow N block: conv1 9x9 7->32, x-folded final 9x9): a unit is rf_R output rows;
+  // the patch is walked row by row and the MMA of patch row iy accumulates into ALL output rows r with
+  // 0 <= iy - r < rf_kh at once: the resident weights are stored with the filter rows in DESCENDING ky order along N
+  // (n = (rf_kh-1-ky)*rf_nblk + c), so the valid output rows of a patch row are a contiguous N-slice of the weights
+  // and a contiguous column range of the accumulator.  3x fewer and fatter MMAs, patch re-read amplification
+  // (rf_R + rf_kh - 1) / rf_R instead of rf_kh.  rf_R == 0: off.
+  int rf_R, rf_kh, rf_nblk, rf_steps, rf_row16, rf_total_rows;
   // timing ablations (env FAV_DBG, diagnostics only; results are wrong when non-zero): 1 = no epilogue stores/stats,
   // 2 = 16-byte weight copies, 4 = 16-byte patch copies, 8 = epilogue skips the TMEM loads too
   int dbg;

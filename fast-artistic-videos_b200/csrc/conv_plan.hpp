@@ -29,6 +29,7 @@ struct ConvPhase {
   int nrg = 1, nchg = 1, CbG = 1, rows_per_group = 1;
   int pslab16 = 0, nseg = 1, seg_len16[2] = {0, 0}, seg_dst16[2] = {0, 0};
   int nchunks = 1, spc = 1;
+  int rf_R = 0, rf_rps = 0;                    // row-fold: output rows per unit, patch rows per stage (0 = off)
   std::vector<KStep> steps;                    // per group
   std::vector<std::vector<Unit>> units;        // [group][step*2 + u]
   float *d_w_simt = nullptr;
@@ -152,6 +153,38 @@ static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
       }
     }
   }
+  // ---- row-fold for tall filters with a narrow N block (see conv.cuh) -------------------------------------------
+  ph.rf_R = 0;
+  if ((ph.kind == 1 || ph.kind == 3) && !c.transposed && c.in_stride == 1 && nrows >= 5 && ph.Npad <= 32 &&
+      nrows * ph.Npad <= 512 && ph.nchg == 1) {
+    bool consecutive = true;
+    for (size_t i = 1; i < ph.rows.size(); ++i) consecutive = consecutive && ph.rows[i] == ph.rows[i - 1] + 1;
+    const int R = 4, total_rows = R + nrows - 1;
+    const int row_bytes = ph.CbG * ph.pslab16 * 32;  // hi + lo of one patch row
+    int rps = 0;
+    for (int d = total_rows; d >= 1; --d)
+      if (total_rows % d == 0 && total_rows / d <= kMaxGroups && d <= kMaxRows && d * row_bytes <= 36 * 1024) { rps = d; break; }
+    if (consecutive && rps > 0) {
+      ph.rf_R = R; ph.rf_rps = rps;
+      // K steps of ONE patch row; units hold (tap column or channel block) only -- the filter row comes from iy - r
+      ph.steps.clear();
+      ph.units.assign(1, {});
+      if (ph.kind == 1) {
+        for (int p = 0; p * 2 < (int)dxs.size(); ++p) {
+          ph.steps.push_back(KStep{(uint16_t)(2 * p), 1});
+          for (int u = 0; u < 2; ++u) ph.units[0].push_back(Unit{2 * p + u < (int)dxs.size() ? 2 * p + u : -1, 0});  // tap = kx
+        }
+      } else {
+        for (int j = 0; j < ph.CbG / 2; ++j) {
+          ph.steps.push_back(KStep{(uint16_t)(2 * j * ph.pslab16), (uint16_t)ph.pslab16});
+          for (int u = 0; u < 2; ++u) ph.units[0].push_back(Unit{0, 2 * j + u});
+        }
+      }
+      ph.nrg = 1; ph.rows_per_group = rps;
+      ph.spc = (int)ph.steps.size(); ph.nchunks = 1;  // weights: one resident image (see pack_phase_weights)
+      return FAV_OK;
+    }
+  }
   const int spg = (int)ph.steps.size();
   if (spg > kMaxSteps) { set_error("conv %s: too many K steps", c.name.c_str()); return FAV_ERR_UNSUPPORTED; }
   const int step_bytes = 2 * 2 * ph.Npad * 16;
@@ -222,6 +255,32 @@ static inline void init_conv_def(ConvDef &c, const std::string &name, int cin, i
 
 // packed tcgen05 weights of one phase: [group][chunk][hi|lo][step][k8 half][Npad][8] fp16 (as uint16 bit patterns)
 static inline std::vector<uint16_t> pack_phase_weights(const ConvDef &c, const ConvPhase &ph, const std::vector<float> &w) {
+  if (ph.rf_R) {
+    // row-fold image: [step][hi|lo][k-half][n = (KH-1-ky)*Nblk + cblk][8], loaded once per CTA (one chunk per step)
+    const int KH = (int)ph.rows.size(), Nblk = ph.Npad, NR = KH * Nblk, nst = (int)ph.steps.size();
+    std::vector<uint16_t> pk((size_t)nst * 2 * 2 * NR * 8, 0);
+    for (int st = 0; st < nst; ++st)
+      for (int part = 0; part < 2; ++part)
+        for (int u = 0; u < 2; ++u) {
+          const Unit un = ph.units[0][st * 2 + u];
+          if (un.tap < 0) continue;
+          for (int ky = 0; ky < KH; ++ky)
+            for (int cblk = 0; cblk < Nblk; ++cblk)
+              for (int i = 0; i < 8; ++i) {
+                float v;
+                if (ph.kind == 3) {  // x-fold: cblk = kx * Cout + co
+                  int kx = cblk / c.cout, co = cblk % c.cout;
+                  v = kx < c.k ? weight_at(c, w, co, un.cb * 8 + i, ky, kx) : 0.f;
+                } else {              // kind 1: unit.tap = kx, cblk = co
+                  v = weight_at(c, w, cblk, i, ky, un.tap);
+                }
+                uint16_t hb = f2h_bits(v);
+                size_t o = ((((size_t)st * 2 + part) * 2 + u) * NR + (size_t)(KH - 1 - ky) * Nblk + cblk) * 8 + i;
+                pk[o] = part == 0 ? hb : f2h_bits(v - h2f_bits(hb));
+              }
+        }
+    return pk;
+  }
   const int ngroups = ph.nrg * ph.nchg, spg = (int)ph.steps.size();
   const int Npad = ph.Npad;
   std::vector<uint16_t> pk((size_t)ngroups * spg * 2 * 2 * Npad * 8, 0);
@@ -256,7 +315,7 @@ static inline Operand operand_geometry(int C, int H, int W, const ConvDef *consu
   int pad = consumer ? consumer->pad : 0;
   if (consumer && consumer->transposed) pad = 0;
   o.padT = o.padL = pad;
-  o.Hs = H + 2 * pad + 2;
+  o.Hs = H + 2 * pad + 2 + 4;  // +2: transposed-conv / mt=2 overrun, +4: row-fold units of 4 output rows
   o.parity = (consumer && consumer->in_stride == 2) ? 1 : 0;
   o.Ws = pad + round_up(W, kTileM) + pad + 16;
   if (o.parity) o.Ws2 = round_up((W + 2 * pad + 1) / 2, kTileM) + 8;
@@ -291,6 +350,7 @@ static inline int fill_conv_job(const ConvDef &c, const ConvPhase &ph, const Ope
   for (size_t i = 1; i < ph.rows.size(); ++i) consecutive = consecutive && ph.rows[i] == ph.rows[i - 1] + 1;
   j.mt = (consecutive && total_b > 160 * 1024 && ph.Npad * 2 * 2 <= 512 &&
           (size_t)(ph.rows_per_group + 1) * ph.CbG * ph.pslab16 * 32 <= 72 * 1024 && pHo >= 2) ? 2 : 1;
+  if (ph.rf_R) j.mt = ph.rf_R;
   j.Ho = pHo; j.Wo = pWo; j.tiles_x = ceil_div(pWo, j.tile_dx); j.ntiles = j.tiles_x * ceil_div(pHo, j.mt);
   j.row_mul = c.in_stride;
   j.nseg = ph.nseg;
@@ -306,13 +366,25 @@ static inline int fill_conv_job(const ConvDef &c, const ConvPhase &ph, const Ope
       if (j.mt == 2) j.grp_row[g][ph.rows_per_group] = j.grp_row[g][ph.rows_per_group - 1] + 1;
     }
   j.nrows = ph.rows_per_group + (j.mt - 1);  // patch rows per stage
+  if (ph.rf_R) {  // stages = groups of rf_rps consecutive patch rows
+    const int KH = (int)ph.rows.size();
+    j.rf_R = ph.rf_R; j.rf_kh = KH; j.rf_nblk = ph.Npad; j.rf_steps = (int)ph.steps.size();
+    j.rf_row16 = ph.CbG * ph.pslab16; j.rf_total_rows = ph.rf_R + KH - 1;
+    j.nrows = ph.rf_rps; j.ngroups = j.rf_total_rows / ph.rf_rps;
+    for (int g = 0; g < j.ngroups; ++g) {
+      j.grp_cb0[g] = 0;
+      for (int ri = 0; ri < j.nrows; ++ri) j.grp_row[g][ri] = in.padT + ph.rows[0] + g * ph.rf_rps + ri;
+    }
+  }
   j.pslab16 = ph.pslab16; j.stage16 = j.nrows * ph.CbG * ph.pslab16;
   j.nchunks = ph.nchunks; j.spc = ph.spc;
   for (size_t i = 0; i < ph.steps.size(); ++i) j.steps[i] = ph.steps[i];
   j.chunk16 = 2 * ph.spc * 2 * ph.Npad; j.Npad = ph.Npad; j.Cout = c.cout;
+  if (ph.rf_R) { j.nchunks = j.rf_steps; j.spc = 1; j.chunk16 = 2 * 2 * j.rf_kh * ph.Npad; }  // one resident chunk per K step
   j.oy_mul = c.out_mul; j.ox_mul = c.out_mul; j.oy_off = ph.oy_off; j.ox_off = ph.ox_off;
   // every bulk copy must stay inside the operand allocation
   int64_t max_row = (int64_t)j.row_mul * (ceil_div(pHo, j.mt) * j.mt - 1) + in.padT + ph.rows.back();
+  if (ph.rf_R) max_row = (int64_t)(ceil_div(pHo, j.mt) - 1) * j.mt + in.padT + ph.rows[0] + j.rf_total_rows - 1;
   int64_t last16 = ((max_row * in.Cb + in.Cb - 1) * (int64_t)in.slab16()) + j.seg_src16[ph.nseg - 1] +
                    (int64_t)(j.tiles_x - 1) * j.tile_dx + j.seg_len16[ph.nseg - 1];
   if (max_row >= in.Hs || last16 > (int64_t)in.elems16) {

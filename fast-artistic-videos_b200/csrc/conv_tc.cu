@@ -206,6 +206,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ===== B producer: weight chunks =====
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
+      if (job.rf_R) {  // row-fold: one resident chunk per K step, shared by every patch row
+        for (int c = 0; c < job.rf_steps; ++c) {
+          mbar_arrive_expect_tx(&sh->b_full[c], chunk_bytes);
+          bulk_g2s(b_base + c * chunk_bytes, job.b + (int64_t)c * job.chunk16, chunk_bytes, &sh->b_full[c]);
+        }
+      } else
       for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
         if (job.b_resident && tile != (int)blockIdx.x) break;  // resident weights: one pass fills every slot
         for (int g = 0; g < ngroups; ++g)
@@ -245,6 +251,60 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_wait(&sh->t_empty[as], tph ^ 1);
       tc_fence_after();
       const uint32_t d0 = tmem_base + as * 256u, d1 = d0 + 128u;
+      if (job.rf_R) {
+        // ===== row-fold issue loop (conv.cuh): patch row iy feeds output rows r_min..r_max in ONE MMA per K step =====
+        const int KH = job.rf_kh, R = job.rf_R;
+        const uint32_t nblk = (uint32_t)job.rf_nblk, NR = (uint32_t)KH * nblk;  // weight rows per k-half
+        const uint32_t idesc_base = (1u << 4) | ((uint32_t)(kTileM >> 4) << 24);
+        if (tl == 0)
+          for (int c = 0; c < job.rf_steps; ++c) mbar_wait(&sh->b_full[c], 0);
+        tc_fence_after();
+        const uint32_t b16 = smem_u32(b_base) >> 4;
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(&sh->a_full[sa], aph);
+          tc_fence_after();
+          const uint32_t a_hi16 = smem_u32(a_base + sa * 2 * a_stage_bytes) >> 4, a_lo16 = a_hi16 + a_stage16;
+          if (leader) {
+            for (int ri = 0; ri < job.nrows; ++ri) {
+              const int iy = g * job.nrows + ri;
+              const int r_min = iy - (KH - 1) > 0 ? iy - (KH - 1) : 0, r_max = iy < R - 1 ? iy : R - 1;
+              const uint32_t nb = (uint32_t)(r_max - r_min + 1);
+              const uint32_t blk0 = (uint32_t)(KH - 1 - (iy - r_min));  // first weight block of the slice (ky = iy - r_min)
+              const bool fresh = iy < R;                               // output row r = iy receives its first product (ky = 0)
+              const uint32_t arow = (uint32_t)ri * (uint32_t)job.rf_row16;
+              for (int st = 0; st < job.rf_steps; ++st) {
+                const uint32_t dls = steps32[st];
+                const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + arow + dls), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + arow + dls);
+                // weight chunk st: [hi: 2 k-halves x NR rows][lo: ...]; LBO = NR rows
+                const uint32_t bq = (b16 + (uint32_t)st * (uint32_t)job.chunk16 + blk0 * nblk) | (NR << 16);
+                const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | bq, bd_lo = ((uint64_t)desc_hi << 32) | (bq + 2u * NR);
+                const uint32_t dcol = d0 + (uint32_t)r_min * nblk;
+                if (st == 0 && fresh) {
+                  if (nb > 1) {  // rows that already hold partial sums
+                    const uint32_t idn = idesc_base | ((((nb - 1) * nblk) >> 3) << 17);
+                    tc_mma_f16(dcol, ad_hi, bd_hi, idn, 1);
+                    tc_mma_f16(dcol, ad_lo, bd_hi, idn, 1);
+                    tc_mma_f16(dcol, ad_hi, bd_lo, idn, 1);
+                  }
+                  const uint32_t idn = idesc_base | ((nblk >> 3) << 17), off = (nb - 1) * nblk;  // the new row: overwrite
+                  tc_mma_f16(dcol + off, ad_hi, bd_hi + off, idn, 0);
+                  tc_mma_f16(dcol + off, ad_lo, bd_hi + off, idn, 1);
+                  tc_mma_f16(dcol + off, ad_hi, bd_lo + off, idn, 1);
+                } else {
+                  const uint32_t idn = idesc_base | (((nb * nblk) >> 3) << 17);
+                  tc_mma_f16(dcol, ad_hi, bd_hi, idn, 1);
+                  tc_mma_f16(dcol, ad_lo, bd_hi, idn, 1);
+                  tc_mma_f16(dcol, ad_hi, bd_lo, idn, 1);
+                }
+              }
+            }
+            tc_commit(&sh->a_empty[sa]);
+          }
+          if (++sa == nstages) { sa = 0; aph ^= 1; }
+        }
+        if (leader) tc_commit(&sh->t_full[as]);
+        continue;
+      }
       if (job.b_resident) sb = 0;
       uint32_t accumulate = 0;
       for (int g = 0; g < ngroups; ++g) {
@@ -254,8 +314,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         int sidx = 0;
         for (int c = 0; c < nchunks; ++c) {
           // ring: slot sb, phase bph.  resident: slot = chunk index, filled once (parity 0 stays satisfied afterwards)
-          mbar_wait(&sh->b_full[sb], job.b_resident ? 0u : bph);
-          tc_fence_after();
+          if (!job.b_resident || tl == 0) {  // resident weights are complete after the first tile
+            mbar_wait(&sh->b_full[sb], job.b_resident ? 0u : bph);
+            tc_fence_after();
+          }
           const uint32_t bh = (smem_u32(b_base + sb * chunk_bytes) >> 4) | ((uint32_t)Npad << 16);  // LBO = Npad * 16 B
           if (Npad >= 128) {
             // wide MMAs (>= 64 cycles each): one divergent region per K step is cheap enough and measured fastest
@@ -281,16 +343,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             // the chunk inside ONE divergent region: a reconvergence point (BSYNC) between MMA groups makes the warp
             // wait for the previous UTCHMMAs to leave the scoreboard and serialises them (~2x slower at small N,
             // measured with FAV_DBG=16).  spc <= kMaxSpc, guarded by warp-uniform predicates.
-            uint32_t dl[kMaxSpc];
-#pragma unroll
-            for (int st = 0; st < kMaxSpc; ++st) dl[st] = steps32[sidx + st];  // table is padded: reads stay in bounds
-            sidx += spc;
             if (leader) {
 #pragma unroll
               for (int st = 0; st < kMaxSpc; ++st) {
                 if (st < spc) {
                   const uint32_t bs = bh + (uint32_t)st * b_step16;
-                  const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + dl[st]), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + dl[st]);
+                  const uint32_t dls = steps32[sidx + st];
+                  const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + dls), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + dls);
                   const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | bs, bd_lo = ((uint64_t)desc_hi << 32) | (bs + b_lo16);
                   tc_mma_f16(d0, ad_hi, bd_hi, idesc, accumulate);
                   tc_mma_f16(d0, ad_lo, bd_hi, idesc, 1);
@@ -304,6 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 }
               }
             }
+            sidx += spc;
           }
           accumulate = 1;
           if (!job.b_resident && leader) tc_commit(&sh->b_empty[sb]);  // frees the weight slot when the MMAs retire
@@ -332,7 +392,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (job.dbg & 8) { tc_fence_before(); mbar_arrive(&sh->t_empty[as]); continue; }
       for (int t = 0; t < job.mt; ++t) {
       const int y = yu * job.mt + t;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 256u + (uint32_t)t * 128u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 256u +
+                             (uint32_t)t * (job.rf_R ? (uint32_t)job.rf_nblk : 128u);
       const int yo = y * job.oy_mul + job.oy_off, xo = x * job.ox_mul + job.ox_off;
       const bool valid = x < job.Wo && y < job.Ho && !(job.dbg & 1);
       if (job.xfold_kw) {
@@ -343,8 +404,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) exch[px * kExchPitch + c0 + i] = __uint_as_float(r[i]);
         }
-        tc_fence_before();
-        mbar_arrive(&sh->t_empty[as]);  // TMEM stage drained: the next tile's MMAs may start
+        if (t == job.mt - 1) {
+          tc_fence_before();
+          mbar_arrive(&sh->t_empty[as]);  // TMEM stage drained: the next tile's MMAs may start
+        }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (px < job.tile_dx && valid) {
           for (int k = 0; k < job.Cout; ++k) {
@@ -355,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // exch is rewritten by the next tile
-        goto next_tile;  // (x-fold jobs always have mt == 1)
+        continue;  // next output row of the unit
       }
 #pragma unroll
       for (int jc = 0; jc < 8; ++jc) {
@@ -395,9 +458,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
       }  // t
-      tc_fence_before();
-      mbar_arrive(&sh->t_empty[as]);
-    next_tile:;
+      if (!job.xfold_kw) {
+        tc_fence_before();
+        mbar_arrive(&sh->t_empty[as]);
+      }
     }
     if (job.stats) {
       // 4 warps -> shared memory in per-warp slots, summed in a FIXED order (deterministic per CTA: the tile ->
@@ -439,7 +503,7 @@ size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (siz
 
 void conv_tc_choose_slots(ConvJob &job) {
   const size_t budget = 224 * 1024, chunk = (size_t)job.chunk16 * 16;
-  const int total = job.ngroups * job.nchunks;
+  const int total = job.rf_R ? job.rf_steps : job.ngroups * job.nchunks;
   job.a_stages = 2;
   // small-work groups (resident weights, several groups per tile) are latency bound on the patch pipeline:
   // deepen it while everything still fits

@@ -28,7 +28,7 @@ static size_t tc_fixed_smem(const ConvJob &job) {
 size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
 void conv_tc_choose_slots(ConvJob &job) {
   const size_t budget = 224 * 1024, chunk = (size_t)job.chunk16 * 16;
-  const int total = job.ngroups * job.nchunks;
+  const int total = job.rf_R ? job.rf_steps : job.ngroups * job.nchunks;
   job.a_stages = 2;
   {
     ConvJob t = job;
@@ -88,10 +88,10 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
     if (conv_tc_smem_bytes(j) > 227 * 1024) { set_error("smem budget"); return 3; }
     const int Npad = j.Npad;
     std::vector<uint16_t> st_hi((size_t)j.stage16 * 8), st_lo((size_t)j.stage16 * 8);
-    std::vector<double> acc((size_t)2 * kTileM * Npad);
+    std::vector<double> acc(j.rf_R ? (size_t)kTileM * 512 : (size_t)2 * kTileM * Npad);
     for (int tile = 0; tile < j.ntiles; ++tile) {
       const int y = (tile / j.tiles_x) * j.mt, x0 = (tile % j.tiles_x) * j.tile_dx;
-      std::fill(acc.begin(), acc.end(), 0.0);
+      std::fill(acc.begin(), acc.end(), j.rf_R ? 1e30 : 0.0);  // row-fold: stale TMEM must be overwritten, not accumulated
       for (int g = 0; g < j.ngroups; ++g) {
         // A producer
         std::fill(st_hi.begin(), st_hi.end(), (uint16_t)0x7e00);  // NaN poison: reading an unloaded byte is a bug
@@ -109,6 +109,41 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
                 st_lo[dst16 * 8 + e] = lo[src16 * 8 + e];
               }
             }
+        if (j.rf_R) {
+          // row-fold: patch row iy -> output rows r_min..r_max, weights slice of the descending-ky image (conv.cuh)
+          const int KH = j.rf_kh, R = j.rf_R, nblk = j.rf_nblk, NR = KH * nblk;
+          for (int ri = 0; ri < j.nrows; ++ri) {
+            const int iy = g * j.nrows + ri;
+            const int r_min = std::max(0, iy - (KH - 1)), r_max = std::min(R - 1, iy);
+            const int nb = r_max - r_min + 1, blk0 = KH - 1 - (iy - r_min);
+            for (int st = 0; st < j.rf_steps; ++st) {
+              const KStep ks = j.steps[st];
+              const uint16_t *chunk = pk.data() + (size_t)st * j.chunk16 * 8;   // [hi: 2 x NR rows][lo: 2 x NR rows]
+              const bool fresh = (st == 0 && iy < R);
+              mma_count += 3 * (fresh && nb > 1 ? 2 : 1);
+              for (int m = 0; m < kTileM; ++m)
+                for (int u = 0; u < 2; ++u) {
+                  int64_t a16 = (int64_t)ri * j.rf_row16 + ks.a_off16 + (int64_t)u * ks.lbo16 + m;
+                  if (a16 >= j.stage16) { set_error("A desc OOB (rowfold)"); return 6; }
+                  for (int i = 0; i < 8; ++i) {
+                    double ah = h2f_bits(st_hi[a16 * 8 + i]), al = h2f_bits(st_lo[a16 * 8 + i]);
+                    for (int n = 0; n < nb * nblk; ++n) {
+                      int64_t brow = (int64_t)blk0 * nblk + n;              // row inside one k-half image
+                      if (brow >= NR) { set_error("B desc OOB (rowfold)"); return 6; }
+                      double bh = h2f_bits(chunk[((int64_t)u * NR + brow) * 8 + i]);
+                      double bl = h2f_bits(chunk[((int64_t)(2 + u) * NR + brow) * 8 + i]);
+                      size_t col = (size_t)r_min * nblk + n;               // accumulator column
+                      double &d = acc[(size_t)m * 512 + col];
+                      const bool overwrite = fresh && (n >= (nb - 1) * nblk) && u == 0 && i == 0;
+                      if (overwrite) d = 0;                                  // accumulate = 0 on the first MMA of the new row
+                      d += ah * bh + al * bh + ah * bl;
+                    }
+                  }
+                }
+            }
+          }
+          continue;
+        }
         for (int ch = 0; ch < j.nchunks; ++ch) {
           const uint16_t *chunk = pk.data() + (size_t)(g * j.nchunks + ch) * j.chunk16 * 8;
           const uint16_t *b_hi = chunk, *b_lo = chunk + (size_t)j.spc * 2 * Npad * 8;
@@ -134,6 +169,22 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
         }
       }
       // epilogue placement
+      if (j.rf_R) {
+        const int nblk = j.rf_nblk;
+        for (int t = 0; t < j.rf_R; ++t)
+          for (int m = 0; m < (j.xfold_kw ? j.tile_dx : kTileM); ++m) {
+            int xx = x0 + m;
+            if (xx >= j.Wo || y + t >= j.Ho) continue;
+            written[(size_t)(y + t) * Wo + xx]++;
+            for (int n = 0; n < cout; ++n) {
+              double v = 0;
+              if (j.xfold_kw) for (int kx = 0; kx < j.xfold_kw; ++kx) v += acc[(size_t)(m + kx) * 512 + (size_t)t * nblk + kx * cout + n];
+              else v = acc[(size_t)m * 512 + (size_t)t * nblk + n];
+              out[((size_t)n * Ho + y + t) * Wo + xx] = v;
+            }
+          }
+        continue;
+      }
       if (j.xfold_kw) {
         for (int m = 0; m < j.tile_dx; ++m) {
           int xx = x0 + m;
