@@ -7,7 +7,7 @@ namespace fav {
 constexpr int kMaxTaps = 81;
 constexpr int kMaxSteps = 168;
 constexpr int kMaxRows = 10;
-constexpr int kMaxGroups = 8;
+constexpr int kMaxGroups = 12;
 constexpr int kTileM = 128;  // output pixels per MMA tile = TMEM lanes
 
 // One K=16 step of the implicit GEMM: two K8 "units" (a unit = 8 input channels of one filter tap).

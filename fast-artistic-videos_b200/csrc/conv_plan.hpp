@@ -156,7 +156,9 @@ static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
   // ---- row-fold for tall filters with a narrow N block (see conv.cuh) -------------------------------------------
   ph.rf_R = 0;
   if ((ph.kind == 1 || ph.kind == 3) && !c.transposed && c.in_stride == 1 && nrows >= 5 && ph.Npad <= 32 &&
-      nrows * ph.Npad <= 512 && ph.nchg == 1) {
+      nrows * ph.Npad <= 512 && c.Cb <= 8) {
+    const int saveCbG = ph.CbG, saveNchg = ph.nchg;
+    ph.CbG = c.Cb; ph.nchg = 1;  // a row stage holds every channel block of the patch row
     bool consecutive = true;
     for (size_t i = 1; i < ph.rows.size(); ++i) consecutive = consecutive && ph.rows[i] == ph.rows[i - 1] + 1;
     const int R = 4, total_rows = R + nrows - 1;
@@ -184,6 +186,7 @@ static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
       ph.spc = (int)ph.steps.size(); ph.nchunks = 1;  // weights: one resident image (see pack_phase_weights)
       return FAV_OK;
     }
+    ph.CbG = saveCbG; ph.nchg = saveNchg;
   }
   const int spg = (int)ph.steps.size();
   if (spg > kMaxSteps) { set_error("conv %s: too many K steps", c.name.c_str()); return FAV_ERR_UNSUPPORTED; }
