@@ -5,8 +5,6 @@
 //   in_apply        : normalise (+ReLU) (+ShaveImage(2) skip add) -> next operand    models_video.lua:41-53,121-130
 //   unpack_operand  : operand -> fp32 NCHW (per-layer parity checks)
 //   conv_simt       : direct convolution on CUDA cores, same I/O as the tcgen05 kernel (bring-up comparator)
-#include <algorithm>
-
 #include "conv.cuh"
 
 namespace fav {
@@ -111,31 +109,14 @@ int launch_in_stats(const RawTensor &raw, double *sums, cudaStream_t st) {
 
 // ---- in_apply ----------------------------------------------------------------------------------------
 // mean / gamma*rstd / beta of the block's 8 channels are derived from the (double) sums by the first 8 threads:
-// biased variance, eps inside the sqrt (nn.SpatialBatchNormalization in training mode, InstanceNormalization.lua:39-50).
-// The raw loads are issued BEFORE that prologue so that its double-precision latency overlaps the memory latency.
+// biased variance, eps inside the sqrt (nn.SpatialBatchNormalization in training mode, InstanceNormalization.lua:39-50)
 __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const double *__restrict__ sums,
                                                        const float *__restrict__ gamma, const float *__restrict__ beta,
                                                        double inv_count, double eps, int relu, Operand skip, int has_skip,
-                                                       int shave, Operand dst, int nit) {
+                                                       int shave, Operand dst) {
   __shared__ float s_mean[8], s_scale[8], s_beta[8];
-  const int xbase = blockIdx.x * (128 * nit) + threadIdx.x;
-  const int y = blockIdx.y, cb = blockIdx.z;
-  const float4 *rp = reinterpret_cast<const float4 *>(raw.p);
-  float4 a[kApplyIter], b[kApplyIter];
-  uint4 sh_[kApplyIter], sl_[kApplyIter];
-#pragma unroll
-  for (int it = 0; it < kApplyIter; ++it) {
-    const int x = xbase + it * 128;
-    if (it < nit && x < raw.W) {
-      a[it] = __ldg(rp + raw.off4(y, 2 * cb, x));
-      b[it] = __ldg(rp + raw.off4(y, 2 * cb + 1, x));
-      if (has_skip) {  // ConcatTable{conv_block, ShaveImage(2)} -> CAddTable (models_video.lua:41-53)
-        int64_t so = skip.off16(skip.padT + y + shave, cb, skip.padL + x + shave);
-        sh_[it] = __ldg(reinterpret_cast<const uint4 *>(skip.hi) + so);
-        sl_[it] = __ldg(reinterpret_cast<const uint4 *>(skip.lo) + so);
-      }
-    }
-  }
+  const int xbase = blockIdx.x * (128 * kApplyIter) + threadIdx.x;
+  int y = blockIdx.y, cb = blockIdx.z;
   if (threadIdx.x < 8) {
     int c = cb * 8 + threadIdx.x;
     double mean = sums[c] * inv_count;
@@ -146,38 +127,36 @@ __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const doub
     s_beta[threadIdx.x] = beta[c];
   }
   __syncthreads();
+  const float4 *rp = reinterpret_cast<const float4 *>(raw.p);
 #pragma unroll
   for (int it = 0; it < kApplyIter; ++it) {
-    const int x = xbase + it * 128;
-    if (it >= nit || x >= raw.W) continue;
-    float v[8] = {a[it].x, a[it].y, a[it].z, a[it].w, b[it].x, b[it].y, b[it].z, b[it].w};
+  const int x = xbase + it * 128;
+  if (x >= raw.W) return;
+  float4 a = __ldg(rp + raw.off4(y, 2 * cb, x)), b = __ldg(rp + raw.off4(y, 2 * cb + 1, x));
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float t = (v[i] - s_mean[i]) * s_scale[i] + s_beta[i];
-      v[i] = relu ? fmaxf(t, 0.f) : t;
-    }
-    if (has_skip) {
-      const uint32_t hw[4] = {sh_[it].x, sh_[it].y, sh_[it].z, sh_[it].w}, lw[4] = {sl_[it].x, sl_[it].y, sl_[it].z, sl_[it].w};
+  for (int i = 0; i < 8; ++i) {
+    float t = (v[i] - s_mean[i]) * s_scale[i] + s_beta[i];
+    v[i] = relu ? fmaxf(t, 0.f) : t;
+  }
+  if (has_skip) {  // ConcatTable{conv_block, ShaveImage(2)} -> CAddTable (models_video.lua:41-53)
+    float sk[8];
+    int64_t so = skip.off16(skip.padT + y + shave, cb, skip.padL + x + shave);
+    load_join8(reinterpret_cast<const uint4 *>(skip.hi) + so, reinterpret_cast<const uint4 *>(skip.lo) + so, sk);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        v[2 * i] += __half2float(__ushort_as_half((unsigned short)(hw[i] & 0xffff))) +
-                    __half2float(__ushort_as_half((unsigned short)(lw[i] & 0xffff)));
-        v[2 * i + 1] += __half2float(__ushort_as_half((unsigned short)(hw[i] >> 16))) +
-                        __half2float(__ushort_as_half((unsigned short)(lw[i] >> 16)));
-      }
-    }
-    int64_t o = dst.off16(dst.padT + y, cb, dst.padL + x);
-    split_store8(v, reinterpret_cast<uint4 *>(dst.hi) + o, reinterpret_cast<uint4 *>(dst.lo) + o);
+    for (int i = 0; i < 8; ++i) v[i] += sk[i];
+  }
+  int64_t o = dst.off16(dst.padT + y, cb, dst.padL + x);
+  split_store8(v, reinterpret_cast<uint4 *>(dst.hi) + o, reinterpret_cast<uint4 *>(dst.lo) + o);
   }
 }
 
 int launch_in_apply(const RawTensor &raw, const double *sums, const float *gamma, const float *beta, float eps, int relu,
                     const Operand *skip, int shave, const Operand &dst, cudaStream_t st) {
-  const int nit = std::min(kApplyIter, ceil_div(raw.W, 128));  // pixels per thread, sized to the row
-  dim3 grid(ceil_div(raw.W, 128 * nit), raw.H, raw.C / 8);
+  dim3 grid(ceil_div(raw.W, 128 * kApplyIter), raw.H, raw.C / 8);
   Operand sk = skip ? *skip : Operand();
   in_apply_kernel<<<grid, 128, 0, st>>>(raw, sums, gamma, beta, 1.0 / ((double)raw.H * raw.W), (double)eps, relu, sk,
-                                        skip ? 1 : 0, shave, dst, nit);
+                                        skip ? 1 : 0, shave, dst);
   return post_launch("in_apply");
 }
 
