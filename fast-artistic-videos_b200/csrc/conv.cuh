@@ -58,6 +58,12 @@ struct ConvJob {
   // and a contiguous column range of the accumulator.  3x fewer and fatter MMAs, patch re-read amplification
   // (rf_R + rf_kh - 1) / rf_R instead of rf_kh.  rf_R == 0: off.
   int rf_R, rf_kh, rf_nblk, rf_steps, rf_row16, rf_total_rows;
+  // phase-fold (stride-2 transposed conv): the 4 sub-pixel phases are folded into N in the order
+  // (a,b) = (0,0),(0,1),(1,1),(1,0) so that the phases fed by tap (dy,dx) are a contiguous block range:
+  // tap(0,0) -> blocks 0..3, (0,1) -> 1..2, (1,0) -> 2..3, (1,1) -> 2.  One weight chunk per tap (pf_n = N of its MMAs,
+  // pf_col = first accumulator column); the patch is loaded once for all phases and each thread stores 2x2 pixels.
+  int pf;
+  int pf_n[4], pf_col[4], pf_len16[4], pf_src16[4], pf_grp16, pf_cout;
   // timing ablations (env FAV_DBG, diagnostics only; results are wrong when non-zero): 1 = no epilogue stores/stats,
   // 2 = 16-byte weight copies, 4 = 16-byte patch copies, 8 = epilogue skips the TMEM loads too
   int dbg;

@@ -3,6 +3,7 @@
 // code is exercised on the CPU by tests/emu (an emulation of the kernel's addressing) and on the GPU by net.cu.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -30,11 +31,15 @@ struct ConvPhase {
   int pslab16 = 0, nseg = 1, seg_len16[2] = {0, 0}, seg_dst16[2] = {0, 0};
   int nchunks = 1, spc = 1;
   int rf_R = 0, rf_rps = 0;                    // row-fold: output rows per unit, patch rows per stage (0 = off)
+  int pf = 0;                                  // phase-fold (transposed conv): see conv.cuh
   std::vector<KStep> steps;                    // per group
   std::vector<std::vector<Unit>> units;        // [group][step*2 + u]
   float *d_w_simt = nullptr;
   uint4 *d_b_tc = nullptr;
 };
+
+struct ConvDef;
+static inline int build_phase_fold(const ConvDef &c, struct ConvPhase &ph);
 
 struct ConvDef {
   std::string name;
@@ -44,6 +49,8 @@ struct ConvDef {
   int in_stride = 1;  // stride of the input sampling grid (2 for 'd' layers)
   int out_mul = 1;    // 2 for transposed stride-2 (sub-pixel phases)
   std::vector<ConvPhase> phases;
+  ConvPhase fold;    // transposed conv: all 4 phases in one tcgen05 job (phase-fold); phases[] stay for the comparator
+  bool has_fold = false;
   float *d_bias = nullptr;
   int pw = -1, pb = -1;  // param indices
 };
@@ -98,7 +105,9 @@ static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
       set_error("conv %s: Cin must be 8 or a multiple of 16 for the tcgen05 path", c.name.c_str());
       return FAV_ERR_UNSUPPORTED;
     }
-    ph.kind = 0; ph.CbG = (c.Cb % 4 == 0) ? 4 : 2; ph.nchg = c.Cb / ph.CbG;
+    ph.kind = 0; ph.CbG = (c.Cb % 4 == 0) ? 4 : 2;
+    if (const char *e = getenv("FAV_CBG")) { int v = atoi(e); if (v == 2 || v == 4) ph.CbG = v; }  // tuning knob
+    ph.nchg = c.Cb / ph.CbG;
     ph.nseg = 1; ph.pslab16 = kTileM + (ph.dxmax - ph.dxmin); ph.seg_len16[0] = ph.pslab16; ph.seg_dst16[0] = 0;
     ph.nrg = 0;
     for (int rg = 1; rg <= nrows; ++rg) {
@@ -217,6 +226,61 @@ static inline float weight_at(const ConvDef &c, const std::vector<float> &w, int
 }
 
 
+// ---- phase-fold ---------------------------------------------------------------------------------------------------
+static const int kPfA[4] = {0, 0, 1, 1}, kPfB[4] = {0, 1, 1, 0};               // block -> phase (a,b)
+static const int kPfTapDy[4] = {0, 0, 1, 1}, kPfTapDx[4] = {0, 1, 0, 1};       // chunk -> tap (dy,dx)
+static const int kPfBlk0[4] = {0, 1, 2, 2}, kPfNblk[4] = {4, 2, 2, 1};         // chunk -> first block, #blocks
+
+static inline int build_phase_fold(const ConvDef &c, ConvPhase &ph) {
+  if (!(c.transposed && c.k == 3 && c.stride == 2 && c.pad == 1 && c.adj == 1 && c.Cb % 2 == 0 && c.cout % 16 == 0 &&
+        4 * c.cout <= 256))
+    return FAV_ERR_UNSUPPORTED;
+  ph.pf = 1; ph.kind = 0; ph.Npad = 4 * c.cout;
+  ph.taps.clear();
+  for (int t = 0; t < 4; ++t) ph.taps.push_back(ConvTap{kPfTapDy[t], kPfTapDx[t], 0, 0});
+  ph.rows = {0, 1}; ph.dxmin = 0; ph.dxmax = 1;
+  ph.CbG = (c.Cb % 4 == 0) ? 4 : 2; ph.nchg = c.Cb / ph.CbG; ph.nrg = 1; ph.rows_per_group = 2;
+  ph.nseg = 1; ph.pslab16 = kTileM + 1; ph.seg_len16[0] = ph.pslab16; ph.seg_dst16[0] = 0;
+  ph.steps.clear();
+  for (int t = 0; t < 4; ++t)
+    for (int j = 0; j < ph.CbG / 2; ++j)
+      ph.steps.push_back(KStep{(uint16_t)((kPfTapDy[t] * ph.CbG + 2 * j) * ph.pslab16 + kPfTapDx[t]), (uint16_t)ph.pslab16});
+  ph.spc = ph.CbG / 2; ph.nchunks = 4;
+  return FAV_OK;
+}
+
+// weights of the folded job: [group][tap chunk][hi|lo][pair][k-half][n = blk*Cout + co][8]
+static inline std::vector<uint16_t> pack_phase_fold(const ConvDef &c, const ConvPhase &ph, const std::vector<float> &w) {
+  const int spc = ph.CbG / 2;
+  size_t grp = 0;
+  for (int t = 0; t < 4; ++t) grp += (size_t)2 * spc * 2 * kPfNblk[t] * c.cout * 8;
+  std::vector<uint16_t> pk((size_t)ph.nchg * grp, 0);
+  for (int g = 0; g < ph.nchg; ++g) {
+    size_t base = (size_t)g * grp;
+    for (int t = 0; t < 4; ++t) {
+      const int n = kPfNblk[t] * c.cout;
+      for (int part = 0; part < 2; ++part)
+        for (int j = 0; j < spc; ++j)
+          for (int u = 0; u < 2; ++u) {
+            const int cb = g * ph.CbG + 2 * j + u;
+            for (int bi = 0; bi < kPfNblk[t]; ++bi) {
+              const int blk = kPfBlk0[t] + bi, a = kPfA[blk], b = kPfB[blk];
+              const int ky = a + c.pad - 2 * kPfTapDy[t], kx = b + c.pad - 2 * kPfTapDx[t];  // oy = 2*iy - pad + ky
+              for (int co = 0; co < c.cout; ++co)
+                for (int i = 0; i < 8; ++i) {
+                  float v = (ky >= 0 && ky < c.k && kx >= 0 && kx < c.k) ? weight_at(c, w, co, cb * 8 + i, ky, kx) : 0.f;
+                  uint16_t hb = f2h_bits(v);
+                  size_t o = base + ((((size_t)part * spc + j) * 2 + u) * n + (size_t)bi * c.cout + co) * 8 + i;
+                  pk[o] = part == 0 ? hb : f2h_bits(v - h2f_bits(hb));
+                }
+            }
+          }
+      base += (size_t)2 * spc * 2 * n * 8;
+    }
+  }
+  return pk;
+}
+
 // taps of a plain convolution / the 4 sub-pixel phases of a stride-2 transposed convolution
 static inline void build_phases(ConvDef &c) {
   c.phases.clear();
@@ -242,6 +306,7 @@ static inline void build_phases(ConvDef &c) {
         }
         c.phases.push_back(std::move(ph));
       }
+    c.has_fold = build_phase_fold(c, c.fold) == FAV_OK;
   }
 }
 
@@ -354,6 +419,7 @@ static inline int fill_conv_job(const ConvDef &c, const ConvPhase &ph, const Ope
   j.mt = (consecutive && total_b > 160 * 1024 && ph.Npad * 2 * 2 <= 512 &&
           (size_t)(ph.rows_per_group + 1) * ph.CbG * ph.pslab16 * 32 <= 72 * 1024 && pHo >= 2) ? 2 : 1;
   if (ph.rf_R) j.mt = ph.rf_R;
+  if (ph.pf) j.mt = 1;
   j.Ho = pHo; j.Wo = pWo; j.tiles_x = ceil_div(pWo, j.tile_dx); j.ntiles = j.tiles_x * ceil_div(pHo, j.mt);
   j.row_mul = c.in_stride;
   j.nseg = ph.nseg;
@@ -384,6 +450,18 @@ static inline int fill_conv_job(const ConvDef &c, const ConvPhase &ph, const Ope
   for (size_t i = 0; i < ph.steps.size(); ++i) j.steps[i] = ph.steps[i];
   j.chunk16 = 2 * ph.spc * 2 * ph.Npad; j.Npad = ph.Npad; j.Cout = c.cout;
   if (ph.rf_R) { j.nchunks = j.rf_steps; j.spc = 1; j.chunk16 = 2 * 2 * j.rf_kh * ph.Npad; }  // one resident chunk per K step
+  if (ph.pf) {
+    j.pf = 1; j.pf_cout = c.cout; j.mt = 1;
+    int src = 0;
+    for (int t = 0; t < 4; ++t) {
+      j.pf_n[t] = kPfNblk[t] * c.cout; j.pf_col[t] = kPfBlk0[t] * c.cout;
+      j.pf_len16[t] = 2 * ph.spc * 2 * j.pf_n[t]; j.pf_src16[t] = src;
+      src += j.pf_len16[t];
+    }
+    j.pf_grp16 = src;
+    j.chunk16 = j.pf_len16[0];  // slot size = largest chunk (tap (0,0): all four phases)
+    j.oy_mul = j.ox_mul = 2; j.oy_off = j.ox_off = 0;
+  }
   j.oy_mul = c.out_mul; j.ox_mul = c.out_mul; j.oy_off = ph.oy_off; j.ox_off = ph.ox_off;
   // every bulk copy must stay inside the operand allocation
   int64_t max_row = (int64_t)j.row_mul * (ceil_div(pHo, j.mt) * j.mt - 1) + in.padT + ph.rows.back();

@@ -211,6 +211,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           mbar_arrive_expect_tx(&sh->b_full[c], chunk_bytes);
           bulk_g2s(b_base + c * chunk_bytes, job.b + (int64_t)c * job.chunk16, chunk_bytes, &sh->b_full[c]);
         }
+      } else if (job.pf) {  // phase-fold: one chunk per (channel group, tap), sizes differ per tap
+        for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
+          if (job.b_resident && tile != (int)blockIdx.x) break;
+          for (int g = 0; g < ngroups; ++g)
+            for (int c = 0; c < 4; ++c) {
+              mbar_wait(&sh->b_empty[s], ph ^ 1);
+              const uint32_t cb = (uint32_t)job.pf_len16[c] * 16u;
+              mbar_arrive_expect_tx(&sh->b_full[s], cb);
+              bulk_g2s(b_base + s * chunk_bytes, job.b + (int64_t)g * job.pf_grp16 + job.pf_src16[c], cb, &sh->b_full[s]);
+              if (++s == nslots) { s = 0; ph ^= 1; }
+            }
+        }
       } else
       for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
         if (job.b_resident && tile != (int)blockIdx.x) break;  // resident weights: one pass fills every slot
@@ -306,6 +318,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         continue;
       }
       if (job.b_resident) sb = 0;
+      if (job.pf) {
+        // ===== phase-fold issue loop: chunk c = tap c; its MMAs write pf_n[c] columns starting at pf_col[c] =====
+        const uint32_t idesc_base = (1u << 4) | ((uint32_t)(kTileM >> 4) << 24);
+        uint32_t acc = 0;
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(&sh->a_full[sa], aph);
+          tc_fence_after();
+          const uint32_t a_hi16 = smem_u32(a_base + sa * 2 * a_stage_bytes) >> 4, a_lo16 = a_hi16 + a_stage16;
+          for (int c = 0; c < 4; ++c) {
+            if (!job.b_resident || tl == 0) {
+              mbar_wait(&sh->b_full[sb], job.b_resident ? 0u : bph);
+              tc_fence_after();
+            }
+            const uint32_t n = (uint32_t)job.pf_n[c], dcol = d0 + (uint32_t)job.pf_col[c];
+            const uint32_t idn = idesc_base | ((n >> 3) << 17);
+            const uint32_t bq = (smem_u32(b_base + sb * chunk_bytes) >> 4) | (n << 16);   // LBO = n rows
+            const uint32_t blo = (uint32_t)spc * 2u * n;                                     // lo image follows the hi image
+            if (leader) {
+              for (int j = 0; j < spc; ++j) {
+                const uint32_t dls = steps32[c * spc + j];
+                const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + dls), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + dls);
+                const uint32_t bs = bq + (uint32_t)j * 2u * n;
+                const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | bs, bd_lo = ((uint64_t)desc_hi << 32) | (bs + blo);
+                tc_mma_f16(dcol, ad_hi, bd_hi, idn, acc);  // acc == 0 only for the very first step: tap (0,0) covers all columns
+                tc_mma_f16(dcol, ad_lo, bd_hi, idn, 1);
+                tc_mma_f16(dcol, ad_hi, bd_lo, idn, 1);
+                acc = 1;
+              }
+              if (!job.b_resident) tc_commit(&sh->b_empty[sb]);
+            }
+            acc = 1;
+            if (++sb == nslots) { sb = 0; bph ^= 1; }
+          }
+          if (leader) tc_commit(&sh->a_empty[sa]);
+          if (++sa == nstages) { sa = 0; aph ^= 1; }
+        }
+        if (leader) tc_commit(&sh->t_full[as]);
+        continue;
+      }
       uint32_t accumulate = 0;
       for (int g = 0; g < ngroups; ++g) {
         mbar_wait(&sh->a_full[sa], aph);
@@ -390,6 +441,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_wait(&sh->t_full[as], tph);
       tc_fence_after();
       if (job.dbg & 8) { tc_fence_before(); mbar_arrive(&sh->t_empty[as]); continue; }
+      if (job.pf) {
+        // 4 phase blocks of pf_cout columns: block k -> output pixel (2y + a, 2x + b), (a,b) = (0,0),(0,1),(1,1),(1,0)
+        const int yi = yu;  // mt == 1
+        const bool valid = x < job.Wo && yi < job.Ho && !(job.dbg & 1);
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 256u;
+        const int C = job.pf_cout;
+        for (int blk = 0; blk < 4; ++blk) {
+          const int a = blk >> 1, b = (blk == 1 || blk == 2) ? 1 : 0;
+          const int yo = 2 * yi + a, xo = 2 * x + b;
+#pragma unroll
+          for (int jc = 0; jc < 4; ++jc) {
+            const int c0 = jc * 16;
+            if (c0 >= C) break;
+            uint32_t r[16];
+            tmem_ld16(taddr0 + (uint32_t)(blk * C + c0), r);
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 bq4 = __ldg(reinterpret_cast<const float4 *>(job.bias + c0) + q);
+              v[4 * q] = __uint_as_float(r[4 * q]) + bq4.x; v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bq4.y;
+              v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bq4.z; v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bq4.w;
+            }
+            if (valid) {
+              float4 *rp = reinterpret_cast<float4 *>(job.raw) + (((int64_t)yo * job.raw_Cq + (c0 >> 2)) * job.raw_Wp + xo);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) rp[(int64_t)q * job.raw_Wp] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            if (job.stats) {
+              float sq[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
+              acc_s[jc] += warp_reduce16(v, lane);
+              acc_q[jc] += warp_reduce16(sq, lane);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&sh->t_empty[as]);
+        continue;
+      }
       for (int t = 0; t < job.mt; ++t) {
       const int y = yu * job.mt + t;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 256u +
@@ -470,7 +561,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if ((lane & 1) == 0) {
 #pragma unroll
         for (int jc = 0; jc < 8; ++jc)
-          if (jc * 16 < Npad) {
+          if (jc * 16 < (job.pf ? job.pf_cout : Npad)) {
             slot[(warp * 2 + 0) * 128 + jc * 16 + (lane >> 1)] = acc_s[jc];
             slot[(warp * 2 + 1) * 128 + jc * 16 + (lane >> 1)] = acc_q[jc];
           }
@@ -503,7 +594,7 @@ size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (siz
 
 void conv_tc_choose_slots(ConvJob &job) {
   const size_t budget = 224 * 1024, chunk = (size_t)job.chunk16 * 16;
-  const int total = job.rf_R ? job.rf_steps : job.ngroups * job.nchunks;
+  const int total = job.rf_R ? job.rf_steps : (job.pf ? job.ngroups * 4 : job.ngroups * job.nchunks);
   job.a_stages = 2;
   // small-work groups (resident weights, several groups per tile) are latency bound on the patch pipeline:
   // deepen it while everything still fits

@@ -164,6 +164,12 @@ static int pack_conv_weights(fav_net *net, ConvDef &c) {
     FAV_TRY(dev_upload(net, pk, &d));
     ph.d_b_tc = reinterpret_cast<uint4 *>(d);
   }
+  if (c.has_fold) {  // transposed conv: one tcgen05 job for all four sub-pixel phases
+    std::vector<uint16_t> pk = pack_phase_fold(c, c.fold, w);
+    uint16_t *d = nullptr;
+    FAV_TRY(dev_upload(net, pk, &d));
+    c.fold.d_b_tc = reinterpret_cast<uint4 *>(d);
+  }
   return FAV_OK;
 }
 
@@ -186,8 +192,24 @@ static int make_operand(Plan &pl, int C, int H, int W, const ConvDef *consumer, 
 
 static int build_conv_jobs(fav_net *net, Plan &pl, PlanStep &st, const ConvDef &c, bool last, float *out3) {
   const Operand &in = pl.ops[st.src];
-  for (const ConvPhase &ph : c.phases) {
+  bool fold_done = false;
+  for (const ConvPhase &ph0 : c.phases) {
+    const bool use_fold = c.has_fold && !getenv("FAV_NO_FOLD");
+    const ConvPhase &ph = ph0;
     ConvJob j;
+    if (use_fold) {
+      if (!fold_done) {
+        FAV_TRY(fill_conv_job(c, c.fold, in, j));
+        j.b = c.fold.d_b_tc; j.bias = c.d_bias;
+        j.raw = st.raw.p; j.raw_Cq = st.raw.Cq; j.raw_Wp = st.raw.Wp;
+        j.final_mode = 0; j.out3 = out3; j.tanh_c = net->tanh_c;
+        conv_tc_choose_slots(j);
+        if (const char *e = getenv("FAV_DBG")) j.dbg = atoi(e);
+        if (conv_tc_smem_bytes(j) > 227 * 1024) { set_error("conv %s: shared memory budget exceeded (fold)", c.name.c_str()); return FAV_ERR_UNSUPPORTED; }
+        st.tc.push_back(j);
+        fold_done = true;
+      }
+    } else {
     FAV_TRY(fill_conv_job(c, ph, in, j));
     j.b = ph.d_b_tc; j.bias = c.d_bias;
     j.raw = st.raw.p; j.raw_Cq = st.raw.Cq; j.raw_Wp = st.raw.Wp;
@@ -199,13 +221,14 @@ static int build_conv_jobs(fav_net *net, Plan &pl, PlanStep &st, const ConvDef &
       return FAV_ERR_UNSUPPORTED;
     }
     st.tc.push_back(j);
+    }
 
     SimtJob s;
     memset(&s, 0, sizeof(s));
     s.in = in; s.sy = s.sx = c.in_stride; s.ntaps = (int)ph.taps.size();
     for (int t = 0; t < s.ntaps; ++t) { s.tdy[t] = (int8_t)ph.taps[t].dy; s.tdx[t] = (int8_t)ph.taps[t].dx; }
     s.w = ph.d_w_simt; s.Cin_pad = c.cin_pad; s.Cout = c.cout; s.Cout_pad8 = c.cout_pad8; s.bias = c.d_bias;
-    s.Ho = j.Ho; s.Wo = j.Wo; s.raw = st.raw.p; s.raw_Cq = st.raw.Cq; s.raw_Wp = st.raw.Wp;
+    s.Ho = c.transposed ? in.H : st.raw.H; s.Wo = c.transposed ? in.W : st.raw.W; s.raw = st.raw.p; s.raw_Cq = st.raw.Cq; s.raw_Wp = st.raw.Wp;
     s.oy_mul = s.ox_mul = c.out_mul; s.oy_off = ph.oy_off; s.ox_off = ph.ox_off;
     s.final_mode = last ? 1 : 0; s.out3 = out3; s.tanh_c = net->tanh_c;
     st.simt.push_back(s);

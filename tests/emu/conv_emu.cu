@@ -28,7 +28,7 @@ static size_t tc_fixed_smem(const ConvJob &job) {
 size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
 void conv_tc_choose_slots(ConvJob &job) {
   const size_t budget = 224 * 1024, chunk = (size_t)job.chunk16 * 16;
-  const int total = job.rf_R ? job.rf_steps : job.ngroups * job.nchunks;
+  const int total = job.rf_R ? job.rf_steps : (job.pf ? job.ngroups * 4 : job.ngroups * job.nchunks);
   job.a_stages = 2;
   {
     ConvJob t = job;
@@ -77,9 +77,13 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
   std::vector<char> written((size_t)Ho * Wo, 0);
   int mma_count = 0;
   size_t smem_max = 0;
-  for (ConvPhase &ph : c.phases) {
-    if (build_phase_tables(c, ph) != FAV_OK) return 1;
-    std::vector<uint16_t> pk = pack_phase_weights(c, ph, w);
+  std::vector<ConvPhase *> todo;
+  if (c.has_fold) todo.push_back(&c.fold);
+  else for (ConvPhase &p : c.phases) todo.push_back(&p);
+  for (ConvPhase *php : todo) {
+    ConvPhase &ph = *php;
+    if (!ph.pf && build_phase_tables(c, ph) != FAV_OK) return 1;
+    std::vector<uint16_t> pk = ph.pf ? pack_phase_fold(c, ph, w) : pack_phase_weights(c, ph, w);
     ConvJob j;
     if (fill_conv_job(c, ph, op, j) != FAV_OK) return 2;
     conv_tc_choose_slots(j);
@@ -144,6 +148,34 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
           }
           continue;
         }
+        if (j.pf) {
+          // phase-fold: chunk = tap; N = pf_n[ch] columns starting at pf_col[ch]
+          for (int ch = 0; ch < 4; ++ch) {
+            const int n_ = j.pf_n[ch];
+            if (j.pf_len16[ch] > j.chunk16) { set_error("pf chunk larger than slot"); return 6; }
+            const uint16_t *chunk = pk.data() + ((size_t)g * j.pf_grp16 + j.pf_src16[ch]) * 8;
+            const uint16_t *b_hi = chunk, *b_lo = chunk + (size_t)j.spc * 2 * n_ * 8;
+            for (int st = 0; st < j.spc; ++st) {
+              const KStep ks = j.steps[ch * j.spc + st];
+              mma_count += 3;
+              for (int m = 0; m < kTileM; ++m)
+                for (int u = 0; u < 2; ++u) {
+                  int64_t a16 = (int64_t)ks.a_off16 + (int64_t)u * ks.lbo16 + m;
+                  if (a16 >= j.stage16) { set_error("A desc OOB (pf)"); return 6; }
+                  for (int i = 0; i < 8; ++i) {
+                    double ah = h2f_bits(st_hi[a16 * 8 + i]), al = h2f_bits(st_lo[a16 * 8 + i]);
+                    for (int n = 0; n < n_; ++n) {
+                      int64_t b16 = (int64_t)st * 2 * n_ + (int64_t)u * n_ + n;
+                      if ((b16 + 1) > j.pf_len16[ch] / 2) { set_error("B desc OOB (pf)"); return 6; }
+                      double bh = h2f_bits(b_hi[b16 * 8 + i]), bl = h2f_bits(b_lo[b16 * 8 + i]);
+                      acc[(size_t)m * Npad + j.pf_col[ch] + n] += ah * bh + al * bh + ah * bl;
+                    }
+                  }
+                }
+            }
+          }
+          continue;
+        }
         for (int ch = 0; ch < j.nchunks; ++ch) {
           const uint16_t *chunk = pk.data() + (size_t)(g * j.nchunks + ch) * j.chunk16 * 8;
           const uint16_t *b_hi = chunk, *b_lo = chunk + (size_t)j.spc * 2 * Npad * 8;
@@ -183,6 +215,20 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
               out[((size_t)n * Ho + y + t) * Wo + xx] = v;
             }
           }
+        continue;
+      }
+      if (j.pf) {
+        for (int m = 0; m < kTileM; ++m) {
+          int xx = x0 + m;
+          if (xx >= j.Wo || y >= j.Ho) continue;
+          for (int blk = 0; blk < 4; ++blk) {
+            const int a = blk >> 1, b = (blk == 1 || blk == 2) ? 1 : 0;
+            int yo = 2 * y + a, xo = 2 * xx + b;
+            if (yo >= Ho || xo >= Wo) { set_error("output OOB (pf)"); return 7; }
+            written[(size_t)yo * Wo + xo]++;
+            for (int n = 0; n < cout; ++n) out[((size_t)n * Ho + yo) * Wo + xo] = acc[(size_t)m * Npad + blk * j.pf_cout + n];
+          }
+        }
         continue;
       }
       if (j.xfold_kw) {

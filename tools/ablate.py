@@ -10,7 +10,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     for _ in range(3): prof = net.profile(x)
     torch.cuda.synchronize(); print(json.dumps({p["name"]: round(p["ms"] * 1e3, 1) for p in prof if p["kind"] == "conv"}))
 else:
-    for dbg in (0,):
+    for dbg, nofold in ((0, ""), (0, "1")):
         env = dict(os.environ, FAV_DBG=str(dbg))
+        cbg = nofold
+        if nofold: env["FAV_NO_FOLD"] = "1"
         out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-        print("FAV_DBG=%2d" % dbg, "\n".join(out.stdout.strip().splitlines()[-24:]) if out.stdout.strip() else out.stderr[-300:], flush=True)
+        print("FAV_DBG=%2d NO_FOLD=%s" % (dbg, cbg), "\n".join(out.stdout.strip().splitlines()[-24:]) if out.stdout.strip() else out.stderr[-300:], flush=True)
