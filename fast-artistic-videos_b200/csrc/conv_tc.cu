@@ -31,7 +31,7 @@ constexpr int kMaxA = 4;  // patch stages
 constexpr int kMaxSpc = 8;  // K16 steps per weight chunk (conv_plan.hpp caps spc at this)
 constexpr int kMaxB = 16;  // weight slots (ring or resident)
 constexpr int kTmemCols = 512;  // 2 accumulator stages x mt (<= 2) tiles x Npad (<= 128) columns
-constexpr int kThreads = 224;
+constexpr int kThreads = 384;  // warps 0-3 + 8-11 epilogue (TMEM lane quarter = warp % 4), 4 A producer, 5 B producer, 6 MMA issuer, 7 idle
 constexpr int kExchPitch = 33;  // fp32 words per pixel in the x-fold exchange buffer (odd: conflict-free)
 
 struct __align__(16) TcShared {
@@ -107,6 +107,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {  // completed by the next tmem_ld16
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
 // sum over the 32 lanes of each of 16 per-lane values; lane L returns the total of value index (L >> 1)
 __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
   float a[8], b[4], c[2];
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], 1); mbar_init(&sh->a_empty[i], 1); }
     for (int i = 0; i < kMaxB; ++i) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], 1); mbar_init(&sh->t_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], 1); mbar_init(&sh->t_empty[i], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 6) {
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int g = 0; g < ngroups; ++g)
             for (int c = 0; c < 4; ++c) {
               mbar_wait(&sh->b_empty[s], ph ^ 1);
-              const uint32_t cb = (uint32_t)job.pf_len16[c] * 16u;
+              const uint32_t cb = (job.dbg & 2) ? 16u : (uint32_t)job.pf_len16[c] * 16u;
               mbar_arrive_expect_tx(&sh->b_full[s], cb);
               bulk_g2s(b_base + s * chunk_bytes, job.b + (int64_t)g * job.pf_grp16 + job.pf_src16[c], cb, &sh->b_full[s]);
               if (++s == nslots) { s = 0; ph ^= 1; }
@@ -358,14 +366,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         continue;
       }
       uint32_t accumulate = 0;
+      const bool dbg_nowait = job.dbg & 16, dbg_one = job.dbg & 32;
       for (int g = 0; g < ngroups; ++g) {
-        mbar_wait(&sh->a_full[sa], aph);
+        if (!dbg_nowait) mbar_wait(&sh->a_full[sa], aph);
         tc_fence_after();
         const uint32_t a_hi16 = smem_u32(a_base + sa * 2 * a_stage_bytes) >> 4, a_lo16 = a_hi16 + a_stage16;
         int sidx = 0;
         for (int c = 0; c < nchunks; ++c) {
           // ring: slot sb, phase bph.  resident: slot = chunk index, filled once (parity 0 stays satisfied afterwards)
-          if (!job.b_resident || tl == 0) {  // resident weights are complete after the first tile
+          if ((!job.b_resident || tl == 0) && !dbg_nowait) {  // resident weights are complete after the first tile
             mbar_wait(&sh->b_full[sb], job.b_resident ? 0u : bph);
             tc_fence_after();
           }
@@ -379,12 +388,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | bs, bd_lo = ((uint64_t)desc_hi << 32) | (bs + b_lo16);
               if (leader) {
                 tc_mma_f16(d0, ad_hi, bd_hi, idesc, accumulate);
+                if (!dbg_one) {
                 tc_mma_f16(d0, ad_lo, bd_hi, idesc, 1);
                 tc_mma_f16(d0, ad_hi, bd_lo, idesc, 1);
+                }
                 if (two) {  // second output row: same weights, patch shifted by one row
                   tc_mma_f16(d1, ad_hi + a_tile16, bd_hi, idesc, accumulate);
+                  if (!dbg_one) {
                   tc_mma_f16(d1, ad_lo + a_tile16, bd_hi, idesc, 1);
                   tc_mma_f16(d1, ad_hi + a_tile16, bd_lo, idesc, 1);
+                  }
                 }
               }
               accumulate = 1;
@@ -426,10 +439,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (leader) tc_commit(&sh->t_full[as]);  // accumulator complete -> epilogue
     }
     __syncwarp();
-  } else {
-    // ===== epilogue warps 0..3: TMEM lane = pixel =====
+  } else if (warp != 7) {
+    // ===== epilogue warps 0..3 (group 0) and 8..11 (group 1): TMEM lane = pixel; the two groups split the columns =====
     uint32_t tl = 0;
-    const int px = warp * 32 + lane;
+    const int wq = warp & 3, eg = warp >> 3;
+    const int px = wq * 32 + lane;
+    const int nj = (Npad + 15) >> 4;
     float *exch = reinterpret_cast<float *>(sh + 1);  // x-fold exchange buffer [128][kExchPitch] / stats [2][128]
     float acc_s[8], acc_q[8];  // fused InstanceNorm statistics: this lane's channel (16*j + lane/2), all tiles
 #pragma unroll
@@ -442,39 +457,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tc_fence_after();
       if (job.dbg & 8) { tc_fence_before(); mbar_arrive(&sh->t_empty[as]); continue; }
       if (job.pf) {
-        // 4 phase blocks of pf_cout columns: block k -> output pixel (2y + a, 2x + b), (a,b) = (0,0),(0,1),(1,1),(1,0)
+        // 4 phase blocks of pf_cout columns: block k -> output pixel (2y + a, 2x + b), (a,b) = (0,0),(0,1),(1,1),(1,0).
+        // Epilogue group eg owns output row a = eg; a thread stores the b = 0 / b = 1 pixels of one channel quad as 32
+        // contiguous bytes.
         const int yi = yu;  // mt == 1
         const bool valid = x < job.Wo && yi < job.Ho && !(job.dbg & 1);
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 256u;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(wq * 32) << 16) + as * 256u;
         const int C = job.pf_cout;
-        for (int blk = 0; blk < 4; ++blk) {
-          const int a = blk >> 1, b = (blk == 1 || blk == 2) ? 1 : 0;
-          const int yo = 2 * yi + a, xo = 2 * x + b;
+        const int a = eg, yo = 2 * yi + a;
+        const uint32_t col_b0 = (uint32_t)((a ? 3 : 0) * C), col_b1 = (uint32_t)((a ? 2 : 1) * C);
 #pragma unroll
-          for (int jc = 0; jc < 4; ++jc) {
-            const int c0 = jc * 16;
-            if (c0 >= C) break;
-            uint32_t r[16];
-            tmem_ld16(taddr0 + (uint32_t)(blk * C + c0), r);
-            float v[16];
+        for (int jc = 0; jc < 4; ++jc) {
+          const int c0 = jc * 16;
+          if (c0 >= C) break;
+          uint32_t r0[16], r1[16];
+          tmem_ld16_nowait(taddr0 + col_b0 + (uint32_t)c0, r0);
+          tmem_ld16(taddr0 + col_b1 + (uint32_t)c0, r1);
+          float v0[16], v1[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 bq4 = __ldg(reinterpret_cast<const float4 *>(job.bias + c0) + q);
+            v0[4 * q] = __uint_as_float(r0[4 * q]) + bq4.x; v0[4 * q + 1] = __uint_as_float(r0[4 * q + 1]) + bq4.y;
+            v0[4 * q + 2] = __uint_as_float(r0[4 * q + 2]) + bq4.z; v0[4 * q + 3] = __uint_as_float(r0[4 * q + 3]) + bq4.w;
+            v1[4 * q] = __uint_as_float(r1[4 * q]) + bq4.x; v1[4 * q + 1] = __uint_as_float(r1[4 * q + 1]) + bq4.y;
+            v1[4 * q + 2] = __uint_as_float(r1[4 * q + 2]) + bq4.z; v1[4 * q + 3] = __uint_as_float(r1[4 * q + 3]) + bq4.w;
+          }
+          if (valid) {
+            float4 *rp = reinterpret_cast<float4 *>(job.raw) + (((int64_t)yo * job.raw_Cq + (c0 >> 2)) * job.raw_Wp + 2 * x);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 bq4 = __ldg(reinterpret_cast<const float4 *>(job.bias + c0) + q);
-              v[4 * q] = __uint_as_float(r[4 * q]) + bq4.x; v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bq4.y;
-              v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bq4.z; v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bq4.w;
+              rp[(int64_t)q * job.raw_Wp] = make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]);
+              rp[(int64_t)q * job.raw_Wp + 1] = make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]);
             }
-            if (valid) {
-              float4 *rp = reinterpret_cast<float4 *>(job.raw) + (((int64_t)yo * job.raw_Cq + (c0 >> 2)) * job.raw_Wp + xo);
+          }
+          if (job.stats && !(job.dbg & 64)) {
+            float sv[16], sq[16];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) rp[(int64_t)q * job.raw_Wp] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            for (int i = 0; i < 16; ++i) {
+              const float e0 = valid ? v0[i] : 0.f, e1 = valid ? v1[i] : 0.f;
+              sv[i] = e0 + e1; sq[i] = e0 * e0 + e1 * e1;
             }
-            if (job.stats) {
-              float sq[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
-              acc_s[jc] += warp_reduce16(v, lane);
-              acc_q[jc] += warp_reduce16(sq, lane);
-            }
+            acc_s[jc] += warp_reduce16(sv, lane);
+            acc_q[jc] += warp_reduce16(sq, lane);
           }
         }
         tc_fence_before();
@@ -483,13 +507,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       for (int t = 0; t < job.mt; ++t) {
       const int y = yu * job.mt + t;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 256u +
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * 256u +
                              (uint32_t)t * (job.rf_R ? (uint32_t)job.rf_nblk : 128u);
       const int yo = y * job.oy_mul + job.oy_off, xo = x * job.ox_mul + job.ox_off;
       const bool valid = x < job.Wo && y < job.Ho && !(job.dbg & 1);
       if (job.xfold_kw) {
         // partial sums Q[pixel][kx*Cout + co] -> shared memory, then out[x][co] = sum_kx Q[x + kx][kx*Cout + co]
         for (int c0 = 0; c0 < Npad; c0 += 16) {
+          if ((nj >= 2 ? ((c0 >> 4) & 1) : 0) != eg) continue;  // the groups split the column chunks
           uint32_t r[16];
           tmem_ld16(taddr + (uint32_t)c0, r);
 #pragma unroll
@@ -499,22 +524,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           tc_fence_before();
           mbar_arrive(&sh->t_empty[as]);  // TMEM stage drained: the next tile's MMAs may start
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (px < job.tile_dx && valid) {
-          for (int k = 0; k < job.Cout; ++k) {
+          for (int k = eg; k < job.Cout; k += 2) {
             float s = __ldg(job.bias + k);
             for (int kx = 0; kx < job.xfold_kw; ++kx) s += exch[(px + kx) * kExchPitch + kx * job.Cout + k];
             job.out3[((int64_t)(job.final_mode == 2 ? 2 - k : k) * job.Ho + yo) * job.Wo + xo] =
                 tc_final_value(s, k, job.final_mode, job.tanh_c);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // exch is rewritten by the next tile
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // exch is rewritten by the next tile
         continue;  // next output row of the unit
       }
 #pragma unroll
       for (int jc = 0; jc < 8; ++jc) {
         const int c0 = jc * 16;
         if (c0 >= Npad) break;
+        if ((nj >= 2 ? ((jc + t) & 1) : (t & 1)) != eg) continue;  // work split between the two epilogue groups
         uint32_t r[16];
         tmem_ld16(taddr + (uint32_t)c0, r);
         if (job.final_mode == 0) {
@@ -531,7 +557,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int q = 0; q < 4; ++q)
               if (c0 + 4 * q < job.Cout) rp[(int64_t)q * job.raw_Wp] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
-          if (job.stats) {
+          if (job.stats && !(job.dbg & 64)) {
             // per-channel sums over the warp's 32 pixels: butterfly transpose-reduce, 16 shuffles per quantity;
             // afterwards lane L holds channel c0 + (L >> 1)
             float sq[16];
@@ -557,20 +583,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (job.stats) {
       // 4 warps -> shared memory in per-warp slots, summed in a FIXED order (deterministic per CTA: the tile ->
       // CTA assignment is static), then one double atomic per channel and quantity per CTA
-      float *slot = exch + 256;  // [4 warps][2][128]
+      float *slot = exch + 256;  // [8 warps][2][128]
+      const int ws = eg * 4 + wq;
       if ((lane & 1) == 0) {
 #pragma unroll
         for (int jc = 0; jc < 8; ++jc)
           if (jc * 16 < (job.pf ? job.pf_cout : Npad)) {
-            slot[(warp * 2 + 0) * 128 + jc * 16 + (lane >> 1)] = acc_s[jc];
-            slot[(warp * 2 + 1) * 128 + jc * 16 + (lane >> 1)] = acc_q[jc];
+            slot[(ws * 2 + 0) * 128 + jc * 16 + (lane >> 1)] = acc_s[jc];
+            slot[(ws * 2 + 1) * 128 + jc * 16 + (lane >> 1)] = acc_q[jc];
           }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (px < job.Cout) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (eg == 0 && px < job.Cout) {
         float ssum = 0.f, qsum = 0.f;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) { ssum += slot[(w * 2 + 0) * 128 + px]; qsum += slot[(w * 2 + 1) * 128 + px]; }
+        for (int w = 0; w < 8; ++w) { ssum += slot[(w * 2 + 0) * 128 + px]; qsum += slot[(w * 2 + 1) * 128 + px]; }
         atomicAdd(job.stats + px, (double)ssum);
         atomicAdd(job.stats + job.Cout + px, (double)qsum);
       }
@@ -588,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
 static size_t tc_fixed_smem(const ConvJob &job) {
   return (size_t)job.a_stages * 2 * job.stage16 * 16 + sizeof(TcShared) + 128 +
-         (job.xfold_kw ? (size_t)kTileM * kExchPitch * 4 : (size_t)(256 + 4 * 2 * 128) * 4);
+         (job.xfold_kw ? (size_t)kTileM * kExchPitch * 4 : (size_t)(256 + 8 * 2 * 128) * 4);
 }
 size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
 
