@@ -160,10 +160,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // Two-row units (mt = 2) are issued by TWO warps, one accumulator row each: a single warp sustains only ~1 UTCHMMA per
+  // 80-100 cycles on this loop (tools/mma_bench3.cu), two warps reach the 64-cycle tensor-pipe floor.
+  const bool dual = job.mt == 2 && !job.rf_R && !job.pf;
+  const uint32_t nissue = dual ? 2u : 1u;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], 1); mbar_init(&sh->a_empty[i], 1); }
-    for (int i = 0; i < kMaxB; ++i) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], 1); mbar_init(&sh->t_empty[i], 256); }
+    for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], 1); mbar_init(&sh->a_empty[i], nissue); }
+    for (int i = 0; i < kMaxB; ++i) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], nissue); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], nissue); mbar_init(&sh->t_empty[i], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 6) {
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
     __syncwarp();
-  } else if (warp == 6) {
+  } else if (warp == 6 || (warp == 7 && dual)) {
     // ===== MMA issuer: the whole warp runs the (warp-uniform) control flow so that descriptors live in uniform
     // registers and the UTCHMMAs issue back to back; one elected lane executes the tcgen05 instructions =====
     uint32_t leader;
@@ -262,7 +266,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t a_tile16 = (uint32_t)(job.CbG * job.pslab16);  // mt = 2: second output row = one patch row lower
     const uint32_t a_stage16 = (uint32_t)job.stage16;
     const uint32_t *steps32 = reinterpret_cast<const uint32_t *>(job.steps);
-    const bool two = job.mt == 2;
+    const uint32_t drow = dual ? (uint32_t)(warp - 6) : 0u;  // dual issue: this warp's accumulator row
+    const bool two = false;  // (mt = 2 units are split between the two issuing warps)
     // NOTE: no runtime integer division / modulo on this warp: ~150 cycles each on the issue path (measured with
     // tools/mma_bench.cu); ring positions are wrap counters.
     uint32_t sa = 0, aph = 0, tl = 0, sb = 0, bph = 0;
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t as = tl & 1, tph = (tl >> 1) & 1;
       mbar_wait(&sh->t_empty[as], tph ^ 1);
       tc_fence_after();
-      const uint32_t d0 = tmem_base + as * 256u, d1 = d0 + 128u;
+      const uint32_t d0 = tmem_base + as * 256u + drow * 128u, d1 = d0 + 128u;
       if (job.rf_R) {
         // ===== row-fold issue loop (conv.cuh): patch row iy feeds output rows r_min..r_max in ONE MMA per K step =====
         const int KH = job.rf_kh, R = job.rf_R;
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int g = 0; g < ngroups; ++g) {
         if (!dbg_nowait) mbar_wait(&sh->a_full[sa], aph);
         tc_fence_after();
-        const uint32_t a_hi16 = smem_u32(a_base + sa * 2 * a_stage_bytes) >> 4, a_lo16 = a_hi16 + a_stage16;
+        const uint32_t a_hi16 = (smem_u32(a_base + sa * 2 * a_stage_bytes) >> 4) + drow * a_tile16, a_lo16 = a_hi16 + a_stage16;
         int sidx = 0;
         for (int c = 0; c < nchunks; ++c) {
           // ring: slot sb, phase bph.  resident: slot = chunk index, filled once (parity 0 stays satisfied afterwards)

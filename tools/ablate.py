@@ -10,7 +10,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     for _ in range(3): prof = net.profile(x)
     torch.cuda.synchronize(); print(json.dumps({p["name"]: round(p["ms"] * 1e3, 1) for p in prof if p["kind"] == "conv"}))
 else:
-    for dbg, nofold in ((0, ""), (64, ""), (65, "")):
+    for dbg, nofold in ((0, ""), (8, "")):
         env = dict(os.environ, FAV_DBG=str(dbg))
         cbg = nofold
         if nofold: env["FAV_NO_FOLD"] = "1"

@@ -99,6 +99,19 @@ int main() {
       {"N128 no pollers",                      {128, 0, 130, 8, 128, 8, 4096, 1, 4096, 0, 8, 0, 4096}},
       {"N128 6 warps polling (32 lanes)",      {128, 0, 130, 8, 128, 8, 4096, 1, 4096, 0, 8 | 16, 0, 4096}},
       {"N128 6 warps polling + nanosleep",     {128, 0, 130, 8, 128, 8, 4096, 1, 4096, 0, 8 | 16 | 64, 0, 4096}},
+      {"N128 A start +16B steps",              {128, 0, 130, 8, 128, 8, 4096, 1, 16, 0, 8, 0, 4096}},
+      {"N128 A start +32B steps",              {128, 0, 130, 8, 128, 8, 4096, 1, 32, 0, 8, 0, 4096}},
+      {"N128 A start +64B steps",              {128, 0, 130, 8, 128, 8, 4096, 1, 64, 0, 8, 0, 4096}},
+      {"N128 A start +128B steps",             {128, 0, 130, 8, 128, 8, 4096, 1, 128, 0, 8, 0, 4096}},
+      {"N128 A start +2080B steps",            {128, 0, 130, 8, 128, 8, 4096, 1, 2080, 0, 8, 0, 4096}},
+      {"N128 A lbo 128 (aligned) +4096",       {128, 0, 128, 8, 128, 8, 4096, 1, 4096, 0, 8, 0, 4096}},
+      {"N128 A lbo 128, +16B steps",           {128, 0, 128, 8, 128, 8, 4096, 1, 16, 0, 8, 0, 4096}},
+      {"N128 two accumulators, +16B",          {128, 0, 130, 8, 128, 8, 4096, 0, 16, 0, 8, 0, 4096}},
+      {"N128 B start +16B steps",              {128, 0, 130, 8, 128, 8, 4096, 1, 4096, 0, 8, 0, 16}},
+      {"N256 A +4096",                         {256, 0, 130, 8, 256, 8, 4096, 1, 4096, 0, 8, 0, 0}},
+      {"N256 A +16B steps",                    {256, 0, 130, 8, 256, 8, 4096, 1, 16, 0, 8, 0, 0}},
+      {"N160 A +16B steps",                    {160, 0, 130, 8, 160, 8, 4096, 1, 16, 0, 8, 0, 0}},
+      {"N160 aligned",                         {160, 0, 128, 8, 160, 8, 4096, 1, 4096, 0, 8, 0, 0}},
   };
   for (int g = 148; g <= 148; g += 147) {
     for (auto &e : cfgs) {
