@@ -272,9 +272,11 @@ def run_ours(args):
     for i in range(K):
         j = (i + 1 + Wm) % POOL
         sess.run_next_image_flows(hf[j], hbw[j], hfw[j], hout[i & 1], 7)
+    t_enqueue = time.perf_counter() - t0  # host time to enqueue K frames (copies + launches are asynchronous)
     sess.sync()
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
+    gpu_ms_last = sess.last_gpu_ms()
     e2e = world * K / t_e2e
     h2d = (3 + 2 + 2) * H * W * 4
     d2h = 3 * H * W * 4
@@ -334,7 +336,8 @@ def run_ours(args):
                        "parallelism": f"replicas x{world} (independent clips, no data-path collective)",
                        "precision": "outputs within 1e-3 of the fp64 oracle (measured ~1e-5, tests/test_gpu_net.py)"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * t_e2e / K,
+                    "ms_per_step": 1e3 * t_e2e / K, "host_enqueue_ms_per_step": 1e3 * t_enqueue / K,
+                    "gpu_ms_last_frame": gpu_ms_last,
                     "note": "fav_session_run_next_image_flows: frame + bw/fw flow from pinned host memory, occlusion "
                             "mask + min filter + warp + net on the GPU, stylized frame back to pinned host memory"},
             "gpu_launches": launches,

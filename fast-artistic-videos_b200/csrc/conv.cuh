@@ -64,6 +64,7 @@ struct ConvJob {
   // pf_col = first accumulator column); the patch is loaded once for all phases and each thread stores 2x2 pixels.
   int pf;
   int pf_n[4], pf_col[4], pf_len16[4], pf_src16[4], pf_grp16, pf_cout;
+  int ksplit;          // 1: two issuing warps take alternate K steps into two accumulators (columns +0 / +128)
   // timing ablations (env FAV_DBG, diagnostics only; results are wrong when non-zero): 1 = no epilogue stores/stats,
   // 2 = 16-byte weight copies, 4 = 16-byte patch copies, 8 = epilogue skips the TMEM loads too
   int dbg;

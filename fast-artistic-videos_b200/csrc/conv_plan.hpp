@@ -170,7 +170,12 @@ static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
     ph.CbG = c.Cb; ph.nchg = 1;  // a row stage holds every channel block of the patch row
     bool consecutive = true;
     for (size_t i = 1; i < ph.rows.size(); ++i) consecutive = consecutive && ph.rows[i] == ph.rows[i - 1] + 1;
-    const int R = 4, total_rows = R + nrows - 1;
+    // R output rows per unit: the patch-row re-read factor is (R + KH - 1) / R.  The wide-input x-fold layer (final conv)
+    // is bound by that L2 -> SM traffic, so it takes R = 8 (8 x 32 = 256 accumulator columns, still double buffered);
+    // conv1 (one channel block) is issue bound and keeps R = 4 so that the unit can be K-split between two warps.
+    int R = (ph.kind == 3 && 8 * ph.Npad <= 256) ? 8 : 4;
+    if (const char *e = getenv(ph.kind == 3 ? "FAV_RF_R3" : "FAV_RF_R1")) R = atoi(e);
+    const int total_rows = R + nrows - 1;
     const int row_bytes = ph.CbG * ph.pslab16 * 32;  // hi + lo of one patch row
     int rps = 0;
     for (int d = total_rows; d >= 1; --d)
@@ -461,6 +466,13 @@ static inline int fill_conv_job(const ConvDef &c, const ConvPhase &ph, const Ope
     j.pf_grp16 = src;
     j.chunk16 = j.pf_len16[0];  // slot size = largest chunk (tap (0,0): all four phases)
     j.oy_mul = j.ox_mul = 2; j.oy_off = j.ox_off = 0;
+  }
+  // K-split between the two issuing warps (conv_tc.cu): one-row units whose accumulator needs <= 128 columns
+  {
+    const int cols = ph.rf_R ? ph.rf_R * ph.Npad : ph.Npad;
+    const bool ok = j.mt == 1 || ph.rf_R;
+    j.ksplit = (ok && cols <= 128 && (!ph.pf || ph.spc % 2 == 0) && !getenv("FAV_NO_KSPLIT")) ? 1 : 0;
+    if (!ph.rf_R && !ph.pf && (int)ph.steps.size() * ph.nrg * ph.nchg < 2) j.ksplit = 0;
   }
   j.oy_mul = c.out_mul; j.ox_mul = c.out_mul; j.oy_off = ph.oy_off; j.ox_off = ph.ox_off;
   // every bulk copy must stay inside the operand allocation

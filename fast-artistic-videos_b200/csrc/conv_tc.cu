@@ -107,12 +107,32 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {  // completed by the next tmem_ld16
+// two 16-column loads in flight, one wait (single asm statement: no use of the registers can be scheduled before the wait)
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, uint32_t (&r)[16], uint32_t (&q)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(q[0]), "=r"(q[1]),
+        "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]), "=r"(q[9]), "=r"(q[10]),
+        "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(ta), "r"(tb)
+      : "memory");
+}
+// accumulator columns [taddr, taddr+16) as floats; K-split jobs add the second issuing warp's partial sums (+128 columns)
+__device__ __forceinline__ void tmem_ld16_acc(uint32_t taddr, bool ksplit, float (&v)[16]) {
+  uint32_t r[16];
+  if (ksplit) {
+    uint32_t q[16];
+    tmem_ld16x2(taddr, taddr + 128u, r, q);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
+  } else {
+    tmem_ld16(taddr, r);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  }
 }
 
 // sum over the 32 lanes of each of 16 per-lane values; lane L returns the total of value index (L >> 1)
@@ -162,7 +182,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   // Two-row units (mt = 2) are issued by TWO warps, one accumulator row each: a single warp sustains only ~1 UTCHMMA per
   // 80-100 cycles on this loop (tools/mma_bench3.cu), two warps reach the 64-cycle tensor-pipe floor.
-  const bool dual = job.mt == 2 && !job.rf_R && !job.pf;
+  // Other units may be K-split (job.ksplit): the two warps take alternate K steps (patch rows for row-fold) into two
+  // accumulators (columns +0 / +128) that the epilogue adds.
+  const bool dual_rows = job.mt == 2 && !job.rf_R && !job.pf, ksplit = job.ksplit != 0;
+  const bool dual = dual_rows || ksplit;
   const uint32_t nissue = dual ? 2u : 1u;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], 1); mbar_init(&sh->a_empty[i], nissue); }
@@ -295,7 +318,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               const int r_min = iy - (KH - 1) > 0 ? iy - (KH - 1) : 0, r_max = iy < R - 1 ? iy : R - 1;
               const uint32_t nb = (uint32_t)(r_max - r_min + 1);
               const uint32_t blk0 = (uint32_t)(KH - 1 - (iy - r_min));  // first weight block of the slice (ky = iy - r_min)
-              const bool fresh = iy < R;                               // output row r = iy receives its first product (ky = 0)
+              if (ksplit && (uint32_t)(iy & 1) != drow) continue;      // K-split: this warp owns patch rows of its parity
+              // rows this warp touches for the first time (overwrite): r = iy (ky = 0) and, K-split, r = iy - 1 as well
+              const uint32_t nf = (uint32_t)(iy < R) + (uint32_t)(ksplit && iy >= 1 && iy - 1 < R);
               const uint32_t arow = (uint32_t)ri * (uint32_t)job.rf_row16;
               for (int st = 0; st < job.rf_steps; ++st) {
                 const uint32_t dls = steps32[st];
@@ -304,14 +329,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const uint32_t bq = (b16 + (uint32_t)st * (uint32_t)job.chunk16 + blk0 * nblk) | (NR << 16);
                 const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | bq, bd_lo = ((uint64_t)desc_hi << 32) | (bq + 2u * NR);
                 const uint32_t dcol = d0 + (uint32_t)r_min * nblk;
-                if (st == 0 && fresh) {
-                  if (nb > 1) {  // rows that already hold partial sums
-                    const uint32_t idn = idesc_base | ((((nb - 1) * nblk) >> 3) << 17);
+                if (st == 0 && nf) {
+                  if (nb > nf) {  // rows that already hold partial sums
+                    const uint32_t idn = idesc_base | ((((nb - nf) * nblk) >> 3) << 17);
                     tc_mma_f16(dcol, ad_hi, bd_hi, idn, 1);
                     tc_mma_f16(dcol, ad_lo, bd_hi, idn, 1);
                     tc_mma_f16(dcol, ad_hi, bd_lo, idn, 1);
                   }
-                  const uint32_t idn = idesc_base | ((nblk >> 3) << 17), off = (nb - 1) * nblk;  // the new row: overwrite
+                  const uint32_t idn = idesc_base | (((nf * nblk) >> 3) << 17), off = (nb - nf) * nblk;  // new rows: overwrite
                   tc_mma_f16(dcol + off, ad_hi, bd_hi + off, idn, 0);
                   tc_mma_f16(dcol + off, ad_lo, bd_hi + off, idn, 1);
                   tc_mma_f16(dcol + off, ad_hi, bd_lo + off, idn, 1);
@@ -350,6 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t blo = (uint32_t)spc * 2u * n;                                     // lo image follows the hi image
             if (leader) {
               for (int j = 0; j < spc; ++j) {
+                if (ksplit && (uint32_t)(j & 1) != drow) continue;  // K-split (spc is even)
                 const uint32_t dls = steps32[c * spc + j];
                 const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + dls), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + dls);
                 const uint32_t bs = bq + (uint32_t)j * 2u * n;
@@ -370,12 +396,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (leader) tc_commit(&sh->t_full[as]);
         continue;
       }
-      uint32_t accumulate = 0;
+      uint32_t accumulate = 0, sc = 0;  // sc: K-step counter of the unit (K-split parity)
       const bool dbg_nowait = job.dbg & 16, dbg_one = job.dbg & 32;
       for (int g = 0; g < ngroups; ++g) {
         if (!dbg_nowait) mbar_wait(&sh->a_full[sa], aph);
         tc_fence_after();
-        const uint32_t a_hi16 = (smem_u32(a_base + sa * 2 * a_stage_bytes) >> 4) + drow * a_tile16, a_lo16 = a_hi16 + a_stage16;
+        const uint32_t a_hi16 = (smem_u32(a_base + sa * 2 * a_stage_bytes) >> 4) + (dual_rows ? drow * a_tile16 : 0u), a_lo16 = a_hi16 + a_stage16;
         int sidx = 0;
         for (int c = 0; c < nchunks; ++c) {
           // ring: slot sb, phase bph.  resident: slot = chunk index, filled once (parity 0 stays satisfied afterwards)
@@ -391,7 +417,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               const uint32_t bs = bh + (uint32_t)st * b_step16;
               const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + dls), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + dls);
               const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | bs, bd_lo = ((uint64_t)desc_hi << 32) | (bs + b_lo16);
-              if (leader) {
+              const bool mine = !ksplit || ((sc + (uint32_t)st) & 1u) == drow;
+              if (leader && mine) {
                 tc_mma_f16(d0, ad_hi, bd_hi, idesc, accumulate);
                 if (!dbg_one) {
                 tc_mma_f16(d0, ad_lo, bd_hi, idesc, 1);
@@ -405,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                   }
                 }
               }
-              accumulate = 1;
+              if (mine) accumulate = 1;
             }
           } else {
           // All descriptors of the chunk are formed first (uniform datapath), then the elected lane issues every MMA of
@@ -415,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (leader) {
 #pragma unroll
               for (int st = 0; st < kMaxSpc; ++st) {
-                if (st < spc) {
+                if (st < spc && (!ksplit || ((sc + (uint32_t)st) & 1u) == drow)) {
                   const uint32_t bs = bh + (uint32_t)st * b_step16;
                   const uint32_t dls = steps32[sidx + st];
                   const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + dls), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + dls);
@@ -434,7 +461,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             sidx += spc;
           }
-          accumulate = 1;
+          if (!ksplit || spc >= 2 || (sc & 1u) == drow) accumulate = 1;  // this warp issued at least one step of the chunk
+          sc += (uint32_t)spc;
           if (!job.b_resident && leader) tc_commit(&sh->b_empty[sb]);  // frees the weight slot when the MMAs retire
           if (++sb == nslots) { sb = 0; bph ^= 1; }
         }
@@ -450,6 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int wq = warp & 3, eg = warp >> 3;
     const int px = wq * 32 + lane;
     const int nj = (Npad + 15) >> 4;
+    const bool ks = job.ksplit != 0;
     float *exch = reinterpret_cast<float *>(sh + 1);  // x-fold exchange buffer [128][kExchPitch] / stats [2][128]
     float acc_s[8], acc_q[8];  // fused InstanceNorm statistics: this lane's channel (16*j + lane/2), all tiles
 #pragma unroll
@@ -476,16 +505,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const int c0 = jc * 16;
           if (c0 >= C) break;
           uint32_t r0[16], r1[16];
-          tmem_ld16_nowait(taddr0 + col_b0 + (uint32_t)c0, r0);
-          tmem_ld16(taddr0 + col_b1 + (uint32_t)c0, r1);
+          tmem_ld16x2(taddr0 + col_b0 + (uint32_t)c0, taddr0 + col_b1 + (uint32_t)c0, r0, r1);
           float v0[16], v1[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(r0[i]); v1[i] = __uint_as_float(r1[i]); }
+          if (ks) {  // second issuing warp's partial sums
+            tmem_ld16x2(taddr0 + 128u + col_b0 + (uint32_t)c0, taddr0 + 128u + col_b1 + (uint32_t)c0, r0, r1);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { v0[i] += __uint_as_float(r0[i]); v1[i] += __uint_as_float(r1[i]); }
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 bq4 = __ldg(reinterpret_cast<const float4 *>(job.bias + c0) + q);
-            v0[4 * q] = __uint_as_float(r0[4 * q]) + bq4.x; v0[4 * q + 1] = __uint_as_float(r0[4 * q + 1]) + bq4.y;
-            v0[4 * q + 2] = __uint_as_float(r0[4 * q + 2]) + bq4.z; v0[4 * q + 3] = __uint_as_float(r0[4 * q + 3]) + bq4.w;
-            v1[4 * q] = __uint_as_float(r1[4 * q]) + bq4.x; v1[4 * q + 1] = __uint_as_float(r1[4 * q + 1]) + bq4.y;
-            v1[4 * q + 2] = __uint_as_float(r1[4 * q + 2]) + bq4.z; v1[4 * q + 3] = __uint_as_float(r1[4 * q + 3]) + bq4.w;
+            v0[4 * q] += bq4.x; v0[4 * q + 1] += bq4.y; v0[4 * q + 2] += bq4.z; v0[4 * q + 3] += bq4.w;
+            v1[4 * q] += bq4.x; v1[4 * q + 1] += bq4.y; v1[4 * q + 2] += bq4.z; v1[4 * q + 3] += bq4.w;
           }
           if (valid) {
             float4 *rp = reinterpret_cast<float4 *>(job.raw) + (((int64_t)yo * job.raw_Cq + (c0 >> 2)) * job.raw_Wp + 2 * x);
@@ -517,28 +550,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int yo = y * job.oy_mul + job.oy_off, xo = x * job.ox_mul + job.ox_off;
       const bool valid = x < job.Wo && y < job.Ho && !(job.dbg & 1);
       if (job.xfold_kw) {
-        // partial sums Q[pixel][kx*Cout + co] -> shared memory, then out[x][co] = sum_kx Q[x + kx][kx*Cout + co]
-        for (int c0 = 0; c0 < Npad; c0 += 16) {
-          if ((nj >= 2 ? ((c0 >> 4) & 1) : 0) != eg) continue;  // the groups split the column chunks
-          uint32_t r[16];
-          tmem_ld16(taddr + (uint32_t)c0, r);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) exch[px * kExchPitch + c0 + i] = __uint_as_float(r[i]);
+        // partial sums Q[pixel][kx*Cout + co] -> shared memory, then out[x][co] = sum_kx Q[x + kx][kx*Cout + co].
+        // Epilogue group eg owns the output rows t = eg (mod 2) of the unit: its own exchange buffer and named barrier.
+        const int last_t = ((job.mt - 1 - eg) & ~1) + eg;  // last row of this group (< 0: none)
+        if (t == 0 && last_t < 0) {
+          tc_fence_before();
+          mbar_arrive(&sh->t_empty[as]);
         }
-        if (t == job.mt - 1) {
+        if ((t & 1) != eg) continue;
+        float *ex = exch + eg * (kTileM * kExchPitch);
+        for (int c0 = 0; c0 < Npad; c0 += 16) {
+          float r[16];
+          tmem_ld16_acc(taddr + (uint32_t)c0, ks, r);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ex[px * kExchPitch + c0 + i] = r[i];
+        }
+        if (t == last_t) {
           tc_fence_before();
           mbar_arrive(&sh->t_empty[as]);  // TMEM stage drained: the next tile's MMAs may start
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (eg) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
         if (px < job.tile_dx && valid) {
-          for (int k = eg; k < job.Cout; k += 2) {
-            float s = __ldg(job.bias + k);
-            for (int kx = 0; kx < job.xfold_kw; ++kx) s += exch[(px + kx) * kExchPitch + kx * job.Cout + k];
-            job.out3[((int64_t)(job.final_mode == 2 ? 2 - k : k) * job.Ho + yo) * job.Wo + xo] =
-                tc_final_value(s, k, job.final_mode, job.tanh_c);
+          const float *q = ex + px * kExchPitch;
+          if (job.xfold_kw == 9 && job.Cout == 3) {
+            float s0 = __ldg(job.bias), s1 = __ldg(job.bias + 1), s2 = __ldg(job.bias + 2);
+#pragma unroll
+            for (int kx = 0; kx < 9; ++kx) {
+              const float *e = q + kx * (kExchPitch + 3);
+              s0 += e[0]; s1 += e[1]; s2 += e[2];
+            }
+            const int64_t plane = (int64_t)job.Ho * job.Wo, o = (int64_t)yo * job.Wo + xo;
+            const bool flip = job.final_mode == 2;
+            job.out3[(flip ? 2 : 0) * plane + o] = tc_final_value(s0, 0, job.final_mode, job.tanh_c);
+            job.out3[plane + o] = tc_final_value(s1, 1, job.final_mode, job.tanh_c);
+            job.out3[(flip ? 0 : 2) * plane + o] = tc_final_value(s2, 2, job.final_mode, job.tanh_c);
+          } else {
+            for (int k = 0; k < job.Cout; ++k) {
+              float sum = __ldg(job.bias + k);
+              for (int kx = 0; kx < job.xfold_kw; ++kx) sum += q[kx * (kExchPitch + job.Cout) + k];
+              job.out3[((int64_t)(job.final_mode == 2 ? 2 - k : k) * job.Ho + yo) * job.Wo + xo] =
+                  tc_final_value(sum, k, job.final_mode, job.tanh_c);
+            }
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // exch is rewritten by the next tile
+        if (eg) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");  // ex is rewritten
         continue;  // next output row of the unit
       }
 #pragma unroll
@@ -546,15 +601,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int c0 = jc * 16;
         if (c0 >= Npad) break;
         if ((nj >= 2 ? ((jc + t) & 1) : (t & 1)) != eg) continue;  // work split between the two epilogue groups
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c0, r);
+        float v[16];
+        tmem_ld16_acc(taddr + (uint32_t)c0, ks, v);
         if (job.final_mode == 0) {
-          float v[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 bq = __ldg(reinterpret_cast<const float4 *>(job.bias + c0) + q);
-            v[4 * q] = __uint_as_float(r[4 * q]) + bq.x; v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bq.y;
-            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bq.z; v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bq.w;
+            v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
           }
           if (valid) {
             float4 *rp = reinterpret_cast<float4 *>(job.raw) + (((int64_t)yo * job.raw_Cq + (c0 >> 2)) * job.raw_Wp + xo);
@@ -576,7 +629,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int k = 0; k < 3; ++k)
             if (k < job.Cout)
               job.out3[((int64_t)(job.final_mode == 2 ? 2 - k : k) * job.Ho + yo) * job.Wo + xo] =
-                  tc_final_value(__uint_as_float(r[k]) + __ldg(job.bias + k), k, job.final_mode, job.tanh_c);
+                  tc_final_value(v[k] + __ldg(job.bias + k), k, job.final_mode, job.tanh_c);
         }
       }
       }  // t
@@ -620,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
 static size_t tc_fixed_smem(const ConvJob &job) {
   return (size_t)job.a_stages * 2 * job.stage16 * 16 + sizeof(TcShared) + 128 +
-         (job.xfold_kw ? (size_t)kTileM * kExchPitch * 4 : (size_t)(256 + 8 * 2 * 128) * 4);
+         (job.xfold_kw ? (size_t)2 * kTileM * kExchPitch * 4 : (size_t)(256 + 8 * 2 * 128) * 4);
 }
 size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
 

@@ -69,7 +69,14 @@ struct Plan {
   float *in7 = nullptr, *out3 = nullptr;  // scratch for run_image / run_next_image
   std::vector<PlanStep> steps;
   std::map<int, int> layer_operand;  // arch token index -> operand holding its output
+  // CUDA graphs of the whole per-frame kernel sequence (run_[next_]image), one per destination buffer: a frame is ~40
+  // launches and the host needs ~1.1 ms to enqueue them one by one (measured, bench e2e), about the GPU time itself
+  struct GraphEntry { float *out3; cudaGraphExec_t exec; uint64_t launches, last_use; };
+  std::vector<GraphEntry> graphs;
+  uint64_t use_clock = 0;
+  int eager_runs = 0;
   ~Plan() {
+    for (GraphEntry &g : graphs) cudaGraphExecDestroy(g.exec);
     for (void *p : allocs) cudaFree(p);
   }
 };
@@ -90,12 +97,14 @@ struct fav_net {
   bool finalized = false;
   int conv_impl = 0;
   int num_sms = 148;
+  cudaStream_t cap_stream = nullptr;  // graph capture happens here (the caller's stream may be the legacy default stream)
   int device = 0;
   std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
   Plan *last_plan = nullptr;
   std::vector<void *> allocs;
   ~fav_net() {
     plans.clear();
+    if (cap_stream) cudaStreamDestroy(cap_stream);
     for (void *p : allocs) cudaFree(p);
   }
 };
@@ -418,6 +427,56 @@ static int run_plan(fav_net *net, Plan &pl, const float *in7, float *out3, int f
   return FAV_OK;
 }
 
+// run_[next_]image: the network part of a frame (input = pl.in7, fused deprocess) as one graph launch
+static int run_plan_frame(fav_net *net, Plan &pl, float *out3, cudaStream_t st) {
+  static const bool no_graph = getenv("FAV_NO_GRAPH") != nullptr;
+  if (no_graph || net->conv_impl != 0) return run_plan(net, pl, pl.in7, out3, 2, st);
+  for (Plan::GraphEntry &g : pl.graphs)
+    if (g.out3 == out3) {
+      g.last_use = ++pl.use_clock;
+      FAV_TRY(check_cuda(cudaGraphLaunch(g.exec, st), "cudaGraphLaunch"));
+      g_launches.fetch_add(g.launches, std::memory_order_relaxed);
+      return FAV_OK;
+    }
+  if (pl.eager_runs < 1) {  // one-time lazy initialisation (function attributes) must happen outside a capture
+    ++pl.eager_runs;
+    return run_plan(net, pl, pl.in7, out3, 2, st);
+  }
+  if (!net->cap_stream)
+    FAV_TRY(check_cuda(cudaStreamCreateWithFlags(&net->cap_stream, cudaStreamNonBlocking), "cudaStreamCreate(capture)"));
+  const uint64_t l0 = g_launches.load();
+  FAV_TRY(check_cuda(cudaStreamBeginCapture(net->cap_stream, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture"));
+  const int rc = run_plan(net, pl, pl.in7, out3, 2, net->cap_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(net->cap_stream, &graph);
+  const uint64_t n = g_launches.load() - l0;
+  g_launches.fetch_sub(n, std::memory_order_relaxed);  // captured, not executed
+  if (rc != FAV_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc != FAV_OK) return rc;
+    return run_plan(net, pl, pl.in7, out3, 2, st);
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    cudaGetLastError();
+    return run_plan(net, pl, pl.in7, out3, 2, st);
+  }
+  if (pl.graphs.size() >= 8) {  // evict the least recently used destination
+    size_t v = 0;
+    for (size_t i = 1; i < pl.graphs.size(); ++i)
+      if (pl.graphs[i].last_use < pl.graphs[v].last_use) v = i;
+    cudaGraphExecDestroy(pl.graphs[v].exec);
+    pl.graphs.erase(pl.graphs.begin() + v);
+  }
+  pl.graphs.push_back(Plan::GraphEntry{out3, exec, n, ++pl.use_clock});
+  FAV_TRY(check_cuda(cudaGraphLaunch(exec, st), "cudaGraphLaunch"));
+  g_launches.fetch_add(n, std::memory_order_relaxed);
+  return FAV_OK;
+}
+
 }  // namespace fav
 
 // =============================================================================================================
@@ -616,7 +675,7 @@ int fav_run_image(fav_net_t *net, const float *content, const float *fill, int H
   FAV_TRY(build_plan(net, H, W, &pl));
   cudaStream_t st = (cudaStream_t)stream;
   FAV_TRY(launch_temporal_input(content, nullptr, nullptr, nullptr, fill, nullptr, pl->in7, H, W, 0, true, st));
-  return run_plan(net, *pl, pl->in7, out_rgb, 2, st);  // deprocess fused into the last epilogue (core.lua:149)
+  return run_plan_frame(net, *pl, out_rgb, st);  // deprocess fused into the last epilogue (core.lua:149)
 }
 
 int fav_run_next_image(fav_net_t *net, const float *content, const float *prev_rgb, const float *flow,
@@ -630,6 +689,6 @@ int fav_run_next_image(fav_net_t *net, const float *content, const float *prev_r
   FAV_TRY(build_plan(net, H, W, &pl));
   cudaStream_t st = (cudaStream_t)stream;
   FAV_TRY(launch_temporal_input(content, prev_rgb, flow, cert, fill, flow_mask, pl->in7, H, W, border_mode, false, st));
-  return run_plan(net, *pl, pl->in7, out_rgb, 2, st);  // core.lua:172-173
+  return run_plan_frame(net, *pl, out_rgb, st);  // core.lua:172-173
 }
 }

@@ -23,7 +23,7 @@ void set_error(const char *fmt, ...) {
 std::atomic<uint64_t> g_launches{0};
 // mirror of conv_tc.cu: kNA = 2 patch stages, up to 16 weight slots (resident when every chunk fits)
 static size_t tc_fixed_smem(const ConvJob &job) {
-  return (size_t)job.a_stages * 2 * job.stage16 * 16 + 640 + (job.xfold_kw ? (size_t)128 * 33 * 4 : (size_t)(256 + 2048) * 4);
+  return (size_t)job.a_stages * 2 * job.stage16 * 16 + 640 + (job.xfold_kw ? (size_t)2 * 128 * 33 * 4 : (size_t)(256 + 2048) * 4);
 }
 size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
 void conv_tc_choose_slots(ConvJob &job) {
@@ -93,9 +93,16 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
     const int Npad = j.Npad;
     std::vector<uint16_t> st_hi((size_t)j.stage16 * 8), st_lo((size_t)j.stage16 * 8);
     std::vector<double> acc(j.rf_R ? (size_t)kTileM * 512 : (size_t)2 * kTileM * Npad);
+    std::vector<double> acc2(acc.size());  // K-split: the second issuing warp's accumulator (TMEM columns +128)
+    if (j.ksplit && (j.rf_R ? j.rf_R * j.rf_nblk : Npad) > 128) { set_error("ksplit needs <= 128 columns"); return 10; }
+    if (j.ksplit && j.mt != 1 && !j.rf_R) { set_error("ksplit with mt = 2"); return 10; }
     for (int tile = 0; tile < j.ntiles; ++tile) {
       const int y = (tile / j.tiles_x) * j.mt, x0 = (tile % j.tiles_x) * j.tile_dx;
-      std::fill(acc.begin(), acc.end(), j.rf_R ? 1e30 : 0.0);  // row-fold: stale TMEM must be overwritten, not accumulated
+      const double poison = (j.rf_R || j.ksplit) ? 1e30 : 0.0;  // stale TMEM must be overwritten, not accumulated
+      std::fill(acc.begin(), acc.end(), poison);
+      std::fill(acc2.begin(), acc2.end(), poison);
+      bool first_w[2] = {true, true};  // K-split: first MMA of each issuing warp in the unit (accumulate = 0)
+      int sc = 0;                       // K-step counter of the unit
       for (int g = 0; g < j.ngroups; ++g) {
         // A producer
         std::fill(st_hi.begin(), st_hi.end(), (uint16_t)0x7e00);  // NaN poison: reading an unloaded byte is a bug
@@ -118,13 +125,15 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
           const int KH = j.rf_kh, R = j.rf_R, nblk = j.rf_nblk, NR = KH * nblk;
           for (int ri = 0; ri < j.nrows; ++ri) {
             const int iy = g * j.nrows + ri;
+            std::vector<double> &accw = (j.ksplit && (iy & 1)) ? acc2 : acc;  // K-split: patch rows by parity
+            const int nf = (iy < R ? 1 : 0) + ((j.ksplit && iy >= 1 && iy - 1 < R) ? 1 : 0);
             const int r_min = std::max(0, iy - (KH - 1)), r_max = std::min(R - 1, iy);
             const int nb = r_max - r_min + 1, blk0 = KH - 1 - (iy - r_min);
             for (int st = 0; st < j.rf_steps; ++st) {
               const KStep ks = j.steps[st];
               const uint16_t *chunk = pk.data() + (size_t)st * j.chunk16 * 8;   // [hi: 2 x NR rows][lo: 2 x NR rows]
-              const bool fresh = (st == 0 && iy < R);
-              mma_count += 3 * (fresh && nb > 1 ? 2 : 1);
+              const bool fresh = (st == 0 && nf > 0);
+              mma_count += 3 * (fresh && nb > nf ? 2 : 1);
               for (int m = 0; m < kTileM; ++m)
                 for (int u = 0; u < 2; ++u) {
                   int64_t a16 = (int64_t)ri * j.rf_row16 + ks.a_off16 + (int64_t)u * ks.lbo16 + m;
@@ -137,8 +146,8 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
                       double bh = h2f_bits(chunk[((int64_t)u * NR + brow) * 8 + i]);
                       double bl = h2f_bits(chunk[((int64_t)(2 + u) * NR + brow) * 8 + i]);
                       size_t col = (size_t)r_min * nblk + n;               // accumulator column
-                      double &d = acc[(size_t)m * 512 + col];
-                      const bool overwrite = fresh && (n >= (nb - 1) * nblk) && u == 0 && i == 0;
+                      double &d = accw[(size_t)m * 512 + col];
+                      const bool overwrite = fresh && (n >= (nb - nf) * nblk) && u == 0 && i == 0;
                       if (overwrite) d = 0;                                  // accumulate = 0 on the first MMA of the new row
                       d += ah * bh + al * bh + ah * bl;
                     }
@@ -158,6 +167,13 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
             for (int st = 0; st < j.spc; ++st) {
               const KStep ks = j.steps[ch * j.spc + st];
               mma_count += 3;
+              const int w = j.ksplit ? (st & 1) : 0;
+              std::vector<double> &accw = w ? acc2 : acc;
+              if (j.ksplit && first_w[w]) {  // accumulate = 0: must cover every column
+                if (j.pf_col[ch] != 0 || n_ != Npad) { set_error("pf ksplit: first MMA does not cover all columns"); return 6; }
+                for (int m = 0; m < kTileM; ++m) for (int n = 0; n < n_; ++n) accw[(size_t)m * Npad + n] = 0;
+                first_w[w] = false;
+              }
               for (int m = 0; m < kTileM; ++m)
                 for (int u = 0; u < 2; ++u) {
                   int64_t a16 = (int64_t)ks.a_off16 + (int64_t)u * ks.lbo16 + m;
@@ -168,7 +184,7 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
                       int64_t b16 = (int64_t)st * 2 * n_ + (int64_t)u * n_ + n;
                       if ((b16 + 1) > j.pf_len16[ch] / 2) { set_error("B desc OOB (pf)"); return 6; }
                       double bh = h2f_bits(b_hi[b16 * 8 + i]), bl = h2f_bits(b_lo[b16 * 8 + i]);
-                      acc[(size_t)m * Npad + j.pf_col[ch] + n] += ah * bh + al * bh + ah * bl;
+                      accw[(size_t)m * Npad + j.pf_col[ch] + n] += ah * bh + al * bh + ah * bl;
                     }
                   }
                 }
@@ -182,6 +198,9 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
           for (int st = 0; st < j.spc; ++st) {
             const KStep ks = j.steps[ch * j.spc + st];
             mma_count += 3 * j.mt;
+            const int w = j.ksplit ? ((sc + st) & 1) : 0;
+            std::vector<double> &accw = w ? acc2 : acc;
+            if (j.ksplit && first_w[w]) { std::fill(accw.begin(), accw.end(), 0.0); first_w[w] = false; }
             for (int t = 0; t < j.mt; ++t)
             for (int m = 0; m < kTileM; ++m)
               for (int u = 0; u < 2; ++u) {
@@ -193,13 +212,17 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
                   for (int n = 0; n < Npad; ++n) {
                     int64_t b16 = (int64_t)st * 2 * Npad + (int64_t)u * Npad + n;
                     double bh = h2f_bits(b_hi[b16 * 8 + i]), bl = h2f_bits(b_lo[b16 * 8 + i]);
-                    acc[((size_t)t * kTileM + m) * Npad + n] += ah * bh + al * bh + ah * bl;
+                    accw[((size_t)t * kTileM + m) * Npad + n] += ah * bh + al * bh + ah * bl;
                   }
                 }
               }
           }
+          sc += j.spc;
         }
       }
+      // epilogue: K-split units add the second warp's accumulator
+      if (j.ksplit)
+        for (size_t i = 0; i < acc.size(); ++i) acc[i] += acc2[i];
       // epilogue placement
       if (j.rf_R) {
         const int nblk = j.rf_nblk;

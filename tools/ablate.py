@@ -13,6 +13,6 @@ else:
     for dbg, nofold in ((0, ""), (8, "")):
         env = dict(os.environ, FAV_DBG=str(dbg))
         cbg = nofold
-        if nofold: env["FAV_NO_FOLD"] = "1"
+        if nofold: env["FAV_RF_" + nofold.split("=")[0]] = nofold.split("=")[1]
         out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-        print("FAV_DBG=%2d NO_FOLD=%s" % (dbg, cbg), "\n".join(out.stdout.strip().splitlines()[-24:]) if out.stdout.strip() else out.stderr[-300:], flush=True)
+        print("FAV_DBG=%2d RF=%s" % (dbg, cbg), "\n".join(out.stdout.strip().splitlines()[-24:]) if out.stdout.strip() else out.stderr[-300:], flush=True)
