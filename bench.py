@@ -44,7 +44,7 @@ ARCHS = {"default": "c9s1-32,d64,d128,R128,R128,R128,R128,R128,u64,u32,c9s1-3",
 POOL = 8  # distinct input frames cycled: 8 x 29.5 MB of inputs per rank > 126 MB L2
 CONV_GFLOP_720P = 274.3  # logical-channel conv FLOPs per 720p frame, default arch (variant u)
 FRONT_BYTES_PER_PX = 64  # fused temporal-input kernel, all-fp32 I/O
-NCU_RES_CONV_DRAM_BYTES = 40398080 + 1050624  # one residual conv launch, ncu --set full (profiles/r01_conv_tc_res_v6.ncu-rep)
+NCU_RES_CONV_DRAM_BYTES = 40013056 + 1452288  # one residual conv launch, ncu --set full (profiles/r01_conv_tc_res_v8.ncu-rep)
 NCU_FRONT_DRAM_BYTES = 33188608 + 271872      # temporal_input_kernel @720p (profiles/r01_temporal_input_v6.ncu-rep)
 
 
@@ -290,7 +290,7 @@ def run_ours(args):
         prof = net.profile(x7)
     conv_ms = sum(p["ms"] for p in prof if p["kind"] == "conv")
     conv_flop = sum(p["work"] for p in prof if p["kind"] == "conv")
-    n_conv_launch = sum(4 if (p["name"] in ("l8", "l9") and args.arch == "default") else 1 for p in prof if p["kind"] == "conv")
+    n_conv_launch = sum(1 for p in prof if p["kind"] == "conv")  # one launch per conv layer (transposed convs: phase-fold)
     stats_ms = sum(p["ms"] for p in prof if p["kind"] == "in_stats")
     apply_ms = sum(p["ms"] for p in prof if p["kind"] == "in_apply")
     pack_ms = sum(p["ms"] for p in prof if p["kind"] == "pack")
@@ -343,11 +343,11 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor",
-                         "kernel": "conv_tc_kernel, residual-block launches (128->128 3x3; 10 of the 22 conv launches per "
+                         "kernel": "conv_tc_kernel, residual-block launches (128->128 3x3; 10 of the %d conv launches per " % n_conv_launch +
                                    "frame, the largest share of the step)",
                          "achieved": res_tfs, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": res_tfs / pk["tf_sust"],
                          "traffic": NCU_RES_CONV_DRAM_BYTES,
-                         "traffic_source": "profiles/r01_conv_tc_res_v6.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum, "
+                         "traffic_source": "profiles/r01_conv_tc_res_v8.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum, "
                                            "one launch; algorithmic bytes of that launch 68.5 MB: the raw output stays in L2)",
                          "peak_source": pk["src"] + ", bf16 sustained (kernel timed inside the step)",
                          "algorithmic_flop_per_launch": res_flop / max(1, res_n), "us_per_launch": 1e3 * res_ms / max(1, res_n),
