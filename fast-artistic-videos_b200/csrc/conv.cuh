@@ -65,6 +65,11 @@ struct ConvJob {
   int pf;
   int pf_n[4], pf_col[4], pf_len16[4], pf_src16[4], pf_grp16, pf_cout;
   int ksplit;          // 1: two issuing warps take alternate K steps into two accumulators (columns +0 / +128)
+  // norm-on-load: the input is the RAW output of the previous convolution; InstanceNorm (+ReLU) and the fp16 hi/lo split
+  // happen in the producer warps while the patch is staged (replaces a separate in_apply pass + operand round trip)
+  int nl;
+  const float4 *nl_raw; int nl_Cq, nl_Wp, nl_H, nl_W, nl_padT, nl_padL, nl_relu, nl_C;
+  const double *nl_sums; const float *nl_gamma, *nl_beta; double nl_inv_count, nl_eps;
   // timing ablations (env FAV_DBG, diagnostics only; results are wrong when non-zero): 1 = no epilogue stores/stats,
   // 2 = 16-byte weight copies, 4 = 16-byte patch copies, 8 = epilogue skips the TMEM loads too
   int dbg;

@@ -31,7 +31,11 @@ constexpr int kMaxA = 4;  // patch stages
 constexpr int kMaxSpc = 8;  // K16 steps per weight chunk (conv_plan.hpp caps spc at this)
 constexpr int kMaxB = 16;  // weight slots (ring or resident)
 constexpr int kTmemCols = 512;  // 2 accumulator stages x mt (<= 2) tiles x Npad (<= 128) columns
-constexpr int kThreads = 384;  // warps 0-3 + 8-11 epilogue (TMEM lane quarter = warp % 4), 4 A producer, 5 B producer, 6 MMA issuer, 7 idle
+constexpr int kThreads = 480;  // warps 0-3 + 8-11 epilogue (TMEM lane quarter = warp % 4), 4 A producer, 5 B producer, 6/7 MMA issuers,
+                                // 12..14 extra patch producers of norm-on-load jobs
+constexpr int kNlWarps = 8;     // warps 4, 8..11 (the second epilogue group turns producer), 12, 13, 14
+constexpr int kNlPx = 5;        // pixels in flight per lane (5 x 32 >= the 130-pixel patch row)
+constexpr int kNlMaxC = 256;
 constexpr int kExchPitch = 33;  // fp32 words per pixel in the x-fold exchange buffer (odd: conflict-free)
 
 struct __align__(16) TcShared {
@@ -188,9 +192,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const bool dual = dual_rows || ksplit;
   const uint32_t nissue = dual ? 2u : 1u;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], 1); mbar_init(&sh->a_empty[i], nissue); }
+    for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], job.nl ? kNlWarps : 1); mbar_init(&sh->a_empty[i], nissue); }
     for (int i = 0; i < kMaxB; ++i) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], nissue); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], nissue); mbar_init(&sh->t_empty[i], 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], nissue); mbar_init(&sh->t_empty[i], job.nl ? 128 : 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 6) {
@@ -199,6 +203,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // norm-on-load: mean / gamma*rstd / beta per input channel from the producer conv's fused statistics (same arithmetic
+  // as in_apply_kernel: biased variance, eps inside the sqrt, InstanceNormalization.lua:39-50)
+  float *nl_tab = reinterpret_cast<float *>(sh + 1) + (256 + 8 * 2 * 128);
+  if (job.nl && (int)threadIdx.x < job.nl_C) {
+    const int c = threadIdx.x;
+    const double mean = job.nl_sums[c] * job.nl_inv_count;
+    double var = job.nl_sums[job.nl_C + c] * job.nl_inv_count - mean * mean;
+    if (var < 0) var = 0;
+    nl_tab[c] = (float)mean;
+    nl_tab[kNlMaxC + c] = (float)((double)job.nl_gamma[c] / sqrt(var + job.nl_eps));
+    nl_tab[2 * kNlMaxC + c] = job.nl_beta[c];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -206,7 +222,73 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   const int ngroups = job.ngroups, nchunks = job.nchunks, spc = job.spc, Npad = job.Npad;
 
-  if (warp == 4) {
+  if (job.nl && (warp == 4 || (warp >= 8 && warp <= 14))) {
+    // ===== norm-on-load patch producers: raw fp32 -> InstanceNorm (+ReLU) -> fp16 hi/lo -> MMA-ready stage =====
+    // A warp owns whole (patch row, channel block) slabs: lanes run along x (coalesced 512-byte loads), up to
+    // kNlPx float4 pairs in flight per lane, no per-pixel index arithmetic.
+    const int pw = warp == 4 ? 0 : warp - 7;  // 0 .. kNlWarps-1
+    const int pslab = job.pslab16, nslabs = job.nrows * job.CbG;
+    uint32_t s = 0, ph = 0;
+    for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
+      const int yu = tile / job.tiles_x, x0 = (tile - yu * job.tiles_x) * job.tile_dx;
+      const int y = yu * job.mt;
+      const int xb = job.seg_src16[0] + x0 - job.nl_padL;  // raw column of patch pixel 0
+      for (int g = 0; g < ngroups; ++g) {
+        mbar_wait(&sh->a_empty[s], ph ^ 1);
+        uint8_t *stage = a_base + s * 2 * a_stage_bytes;
+        for (int rc = pw; rc < nslabs; rc += kNlWarps) {
+          const int ri = rc / job.CbG, cbi = rc - ri * job.CbG;
+          const int ry = job.row_mul * y + job.grp_row[g][ri] - job.nl_padT, cb = job.grp_cb0[g] + cbi;
+          const bool row_ok = ry >= 0 && ry < job.nl_H;
+          const float4 *rp = job.nl_raw + ((int64_t)(row_ok ? ry : 0) * job.nl_Cq + 2 * cb) * job.nl_Wp;
+          float tm[8], ts[8], tb[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { tm[i] = nl_tab[cb * 8 + i]; ts[i] = nl_tab[kNlMaxC + cb * 8 + i]; tb[i] = nl_tab[2 * kNlMaxC + cb * 8 + i]; }
+          uint8_t *drow = stage + (uint32_t)(rc * pslab) * 16u;
+          for (int pb = 0; pb < pslab; pb += 32 * kNlPx) {
+            float4 va[kNlPx], vb[kNlPx];
+            uint32_t okm = 0;
+#pragma unroll
+            for (int k = 0; k < kNlPx; ++k) {
+              const int p = pb + k * 32 + lane, x = xb + p;
+              const bool ok = row_ok && p < pslab && x >= 0 && x < job.nl_W;
+              va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok) { va[k] = __ldg(rp + x); vb[k] = __ldg(rp + job.nl_Wp + x); okm |= 1u << k; }
+            }
+#pragma unroll
+            for (int k = 0; k < kNlPx; ++k) {
+              const int p = pb + k * 32 + lane;
+              if (p >= pslab) continue;
+              float v[8] = {va[k].x, va[k].y, va[k].z, va[k].w, vb[k].x, vb[k].y, vb[k].z, vb[k].w};
+              if (okm & (1u << k)) {  // pixels outside the image stay zero (never normalised)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float t = (v[i] - tm[i]) * ts[i] + tb[i];
+                  v[i] = job.nl_relu ? fmaxf(t, 0.f) : t;
+                }
+              }
+              uint32_t h[4], l[4];  // same values as split_store8 (net_kernels.cu), packed two per conversion
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float a = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
+                const __half2 hh = __floats2half2_rn(a, b);
+                const float2 hf = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+                h[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                l[i] = *reinterpret_cast<const uint32_t *>(&ll);
+              }
+              *reinterpret_cast<uint4 *>(drow + (uint32_t)p * 16u) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4 *>(drow + a_stage_bytes + (uint32_t)p * 16u) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->a_full[s]);
+        if (++s == nstages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 4) {
     // ===== A producer: the input patch of each (tile, channel group) =====
     const int per_row = job.CbG * job.nseg * 2;  // copies per patch row (x2: hi, lo)
     const int ncopies = job.nrows * per_row;
@@ -472,10 +554,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (leader) tc_commit(&sh->t_full[as]);  // accumulator complete -> epilogue
     }
     __syncwarp();
-  } else if (warp != 7) {
+  } else if (warp < 4 || (warp >= 8 && warp < 12 && !job.nl)) {
     // ===== epilogue warps 0..3 (group 0) and 8..11 (group 1): TMEM lane = pixel; the two groups split the columns =====
     uint32_t tl = 0;
     const int wq = warp & 3, eg = warp >> 3;
+    const int neg = job.nl ? 1 : 2;  // norm-on-load jobs: the second group works as patch producers
     const int px = wq * 32 + lane;
     const int nj = (Npad + 15) >> 4;
     const bool ks = job.ksplit != 0;
@@ -600,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int jc = 0; jc < 8; ++jc) {
         const int c0 = jc * 16;
         if (c0 >= Npad) break;
-        if ((nj >= 2 ? ((jc + t) & 1) : (t & 1)) != eg) continue;  // work split between the two epilogue groups
+        if (neg == 2 && (nj >= 2 ? ((jc + t) & 1) : (t & 1)) != eg) continue;  // work split between the two epilogue groups
         float v[16];
         tmem_ld16_acc(taddr + (uint32_t)c0, ks, v);
         if (job.final_mode == 0) {
@@ -651,11 +734,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             slot[(ws * 2 + 1) * 128 + jc * 16 + (lane >> 1)] = acc_q[jc];
           }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (neg == 2) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
       if (eg == 0 && px < job.Cout) {
         float ssum = 0.f, qsum = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { ssum += slot[(w * 2 + 0) * 128 + px]; qsum += slot[(w * 2 + 1) * 128 + px]; }
+        for (int w = 0; w < 4 * neg; ++w) { ssum += slot[(w * 2 + 0) * 128 + px]; qsum += slot[(w * 2 + 1) * 128 + px]; }
         atomicAdd(job.stats + px, (double)ssum);
         atomicAdd(job.stats + job.Cout + px, (double)qsum);
       }
@@ -673,7 +756,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
 static size_t tc_fixed_smem(const ConvJob &job) {
   return (size_t)job.a_stages * 2 * job.stage16 * 16 + sizeof(TcShared) + 128 +
-         (job.xfold_kw ? (size_t)2 * kTileM * kExchPitch * 4 : (size_t)(256 + 8 * 2 * 128) * 4);
+         (job.xfold_kw ? (size_t)2 * kTileM * kExchPitch * 4 : (size_t)(256 + 8 * 2 * 128) * 4) + (job.nl ? (size_t)3 * kNlMaxC * 4 : 0);
 }
 size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
 

@@ -56,13 +56,14 @@ struct PlanStep {
   std::vector<SimtJob> simt;
   int stats_off = 0;
   int layer_index = -1;  // arch token index whose output this step completes (for fav_net_layer_output)
+  bool fused_nl = false; // kind 1: the tcgen05 consumer normalises on load (conv_tc.cu), this pass is skipped
 };
 
 struct Plan {
   int H = 0, W = 0;
   std::vector<Operand> ops;
   std::vector<void *> allocs;
-  float *raw_buf = nullptr;
+  float *raw_buf = nullptr, *raw_buf2 = nullptr;  // consecutive convolutions alternate (norm-on-load reads one, writes the other)
   double *stats = nullptr;
   size_t stats_bytes = 0;
   float *msb = nullptr;
@@ -277,6 +278,7 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
     }
   }
   FAV_TRY(alloc_zero(*pl, (void **)&pl->raw_buf, raw_max * sizeof(float) + 4096));
+  FAV_TRY(alloc_zero(*pl, (void **)&pl->raw_buf2, raw_max * sizeof(float) + 4096));
   pl->stats_bytes = std::max(1, stats_slots) * sizeof(double);
   FAV_TRY(alloc_zero(*pl, (void **)&pl->stats, pl->stats_bytes));
   FAV_TRY(alloc_zero(*pl, (void **)&pl->msb, std::max(1, stats_slots) * 2 * sizeof(float)));
@@ -317,10 +319,30 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
       cs.kind = 0; cs.conv = op.conv[i]; cs.src = cur;
       int ho, wo;
       conv_out_size(c, pl->ops[cur].H, pl->ops[cur].W, &ho, &wo);
-      cs.raw.p = pl->raw_buf; cs.raw.C = c.cout; cs.raw.Cq = round_up(c.cout, 4) / 4; cs.raw.H = ho; cs.raw.W = wo;
+      cs.raw.p = (pos & 1) ? pl->raw_buf2 : pl->raw_buf; cs.raw.C = c.cout; cs.raw.Cq = round_up(c.cout, 4) / 4; cs.raw.H = ho; cs.raw.W = wo;
       cs.raw.Hp = ho + 2; cs.raw.Wp = round_up(wo, kTileM);
       const bool last = op.last && i == n - 1;
       FAV_TRY(build_conv_jobs(net, *pl, cs, c, last, nullptr));
+      // second conv of a residual block: fold the preceding InstanceNorm + ReLU pass into its patch producers
+      if (op.kind == 1 && i == 1 && !pl->steps.empty() && pl->steps.back().kind == 1 && !getenv("FAV_NO_NL")) {
+        PlanStep &ap = pl->steps.back();
+        const InDef &n = net->inorms[ap.inorm];
+        const Operand &in = pl->ops[cs.src];
+        bool ok = ap.skip < 0 && n.C <= 256 && cs.tc.size() == 1;
+        if (ok) {
+          ConvJob &j = cs.tc[0];
+          ok = !j.rf_R && !j.pf && !j.xfold_kw && j.nseg == 1 && j.seg_dst16[0] == 0 && j.seg_len16[0] == j.pslab16 && j.row_mul == 1;
+          if (ok) {
+            ConvJob t = j;
+            t.nl = 1; t.nl_raw = reinterpret_cast<const float4 *>(ap.raw.p); t.nl_Cq = ap.raw.Cq; t.nl_Wp = ap.raw.Wp;
+            t.nl_H = ap.raw.H; t.nl_W = ap.raw.W; t.nl_padT = in.padT; t.nl_padL = in.padL; t.nl_relu = ap.relu; t.nl_C = n.C;
+            t.nl_sums = pl->stats + ap.stats_off; t.nl_gamma = n.d_gamma; t.nl_beta = n.d_beta;
+            t.nl_inv_count = 1.0 / ((double)ap.raw.H * ap.raw.W); t.nl_eps = 1e-5;
+            conv_tc_choose_slots(t);
+            if (conv_tc_smem_bytes(t) <= 227 * 1024 && (t.b_resident || t.b_slots >= 2)) { j = t; ap.fused_nl = true; }
+          }
+        }
+      }
       if (last) { cs.layer_index = (int)oi; pl->steps.push_back(std::move(cs)); break; }
       RawTensor raw = cs.raw;
       pl->steps.push_back(std::move(cs));
@@ -409,6 +431,7 @@ static int run_plan(fav_net *net, Plan &pl, const float *in7, float *out3, int f
       FAV_TRY(launch_up_in(src, pl.stats + s.stats_off, n.d_gamma, n.d_beta, 1e-5f, s.relu, s.scale, pl.ops[s.dst], st));
       FAV_TRY(end());
     } else {
+      if (s.fused_nl && net->conv_impl == 0) continue;  // the consumer conv normalises while it loads (norm-on-load)
       const InDef &n = net->inorms[s.inorm];
       double *sums = pl.stats + s.stats_off;
       const double elems = (double)n.C * s.raw.H * s.raw.W;

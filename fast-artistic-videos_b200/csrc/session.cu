@@ -114,6 +114,20 @@ static int session_step(fav_session *s, int mode, const float *content_host, con
     FAV_TRY(check_cuda(cudaMemcpyAsync(in.flow, flow_a + HW, HW * 4, cudaMemcpyHostToDevice, s->s_h2d), "H2D flow v"));
     FAV_TRY(check_cuda(cudaMemcpyAsync(in.flow_fw, flow_b, 2 * HW * 4, cudaMemcpyHostToDevice, s->s_h2d), "H2D flow fw"));
   }
+  // The occlusion mask and its min filter depend on this frame's uploads only, not on the previous stylized frame: they
+  // run on the upload stream and overlap the network of the previous frame.
+  const float *cert_dev = in.cert_raw;
+  if (mode != 0) {
+    if (mode == 2) {
+      // flow1 = backward flow (u at flow+HW, v at flow), flow2 = forward flow; 3-argument mode
+      FAV_TRY(launch_consistency(in.flow + HW, in.flow, in.flow_fw, in.flow_fw + HW, nullptr, nullptr, 0.f, nullptr,
+                                 in.cert_raw, W, H, s->s_h2d));
+    }
+    if (min_filter_r > 1) {  // utils.min_filter(cert, opt.occlusions_min_filter)  core.lua:207
+      FAV_TRY(launch_min_filter(in.cert_raw, in.cert, 1, H, W, min_filter_r, s->s_h2d));
+      cert_dev = in.cert;
+    }
+  }
   FAV_TRY(check_cuda(cudaEventRecord(in.uploaded, s->s_h2d), "cudaEventRecord"));
   // ---- compute
   FAV_TRY(check_cuda(cudaStreamWaitEvent(s->s_comp, in.uploaded, 0), "cudaStreamWaitEvent"));
@@ -123,17 +137,7 @@ static int session_step(fav_session *s, int mode, const float *content_host, con
   if (mode == 0) {
     FAV_TRY(fav_run_image(s->net, in.content, nullptr, H, W, s->out[so], s->s_comp));
   } else {
-    const float *cert = in.cert_raw;
-    if (mode == 2) {
-      // flow1 = backward flow (u at flow+HW, v at flow), flow2 = forward flow; 3-argument mode
-      FAV_TRY(launch_consistency(in.flow + HW, in.flow, in.flow_fw, in.flow_fw + HW, nullptr, nullptr, 0.f, nullptr,
-                                 in.cert_raw, W, H, s->s_comp));
-    }
-    if (min_filter_r > 1) {  // utils.min_filter(cert, opt.occlusions_min_filter)  core.lua:207
-      FAV_TRY(launch_min_filter(in.cert_raw, in.cert, 1, H, W, min_filter_r, s->s_comp));
-      cert = in.cert;
-    }
-    FAV_TRY(fav_run_next_image(s->net, in.content, s->out[so ^ 1], in.flow, cert, nullptr, nullptr, H, W, border_mode,
+    FAV_TRY(fav_run_next_image(s->net, in.content, s->out[so ^ 1], in.flow, cert_dev, nullptr, nullptr, H, W, border_mode,
                                s->out[so], s->s_comp));
   }
   FAV_TRY(check_cuda(cudaEventRecord(s->t1, s->s_comp), "cudaEventRecord"));

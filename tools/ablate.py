@@ -1,4 +1,4 @@
-"""Timing ablations of conv_tc_kernel (FAV_DBG bits; diagnostics only)."""
+"""Timing ablations of the conv / apply kernels (env knobs: FAV_DBG bits, FAV_NO_NL, FAV_NO_KSPLIT, FAV_NO_FOLD; diagnostics only)."""
 import os, sys, subprocess, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if len(sys.argv) > 1 and sys.argv[1] == "child":
@@ -8,11 +8,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     net = models_video.synthetic_model("candy")
     x = torch.randn(1, 7, 720, 1280, device="cuda") * 50
     for _ in range(3): prof = net.profile(x)
-    torch.cuda.synchronize(); print(json.dumps({p["name"]: round(p["ms"] * 1e3, 1) for p in prof if p["kind"] == "conv"}))
+    torch.cuda.synchronize()
+    print(json.dumps({p["name"]: round(p["ms"] * 1e3, 1) for p in prof}), "total", round(sum(p["ms"] for p in prof) * 1e3, 1))
 else:
-    for dbg, nofold in ((0, ""), (8, "")):
-        env = dict(os.environ, FAV_DBG=str(dbg))
-        cbg = nofold
-        if nofold: env["FAV_RF_" + nofold.split("=")[0]] = nofold.split("=")[1]
-        out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-        print("FAV_DBG=%2d RF=%s" % (dbg, cbg), "\n".join(out.stdout.strip().splitlines()[-24:]) if out.stdout.strip() else out.stderr[-300:], flush=True)
+    variants = [dict(), dict(FAV_NO_NL="1")] if len(sys.argv) < 2 else [dict(kv.split("=") for kv in a.split(",") if kv) for a in sys.argv[1:]]
+    for v in variants:
+        out = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, **v), capture_output=True, text=True)
+        print(v, "\n".join(out.stdout.strip().splitlines()[-2:]) if out.stdout.strip() else out.stderr[-400:], flush=True)
