@@ -344,7 +344,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor",
                          "kernel": "conv_tc_kernel, residual-block launches (128->128 3x3; 10 of the %d conv launches per " % n_conv_launch +
-                                   "frame, the largest share of the step)",
+                                   "frame, the largest share of the step; the second conv of each block also normalises its input on load)",
                          "achieved": res_tfs, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": res_tfs / pk["tf_sust"],
                          "traffic": NCU_RES_CONV_DRAM_BYTES,
                          "traffic_source": "profiles/r01_conv_tc_res_v8.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum, "
