@@ -327,3 +327,19 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
   if (n_mma) *n_mma = mma_count;
   return 0;
 }
+
+// planner decisions for one layer (first job): {mt, ksplit, pf, rf_R, xfold_kw, b_resident, a_stages, b_slots, ntiles, Npad}
+extern "C" int emu_plan_info(int cin, int cout, int k, int stride, int pad, int transposed, int adj, int H, int W, int *out10) {
+  ConvDef c;
+  init_conv_def(c, "emu", cin, cout, k, stride, pad, transposed != 0, adj);
+  build_phases(c);
+  Operand op = operand_geometry(cin, H, W, &c);
+  ConvPhase &ph = c.has_fold ? c.fold : c.phases[0];
+  if (!ph.pf && build_phase_tables(c, ph) != FAV_OK) return 1;
+  ConvJob j;
+  if (fill_conv_job(c, ph, op, j) != FAV_OK) return 2;
+  conv_tc_choose_slots(j);
+  const int v[10] = {j.mt, j.ksplit, j.pf, j.rf_R, j.xfold_kw, j.b_resident, j.a_stages, j.b_slots, j.ntiles, j.Npad};
+  for (int i = 0; i < 10; ++i) out10[i] = v[i];
+  return 0;
+}

@@ -36,6 +36,12 @@ CASES = [  # cin, cout, k, stride, pad, transposed, adj, H, W
     (128, 64, 3, 1, 1, 0, 0, 5, 130),    # c3s1-64 of the paper arch
     (3, 32, 9, 1, 4, 0, 0, 9, 20),       # image model first layer, frame narrower than one tile
     (128, 128, 3, 1, 0, 0, 0, 3, 3),     # 1x1 output
+    (32, 3, 9, 1, 4, 0, 0, 19, 250),     # final conv: R = 8 row-fold, partial last unit, 3 x-fold tiles (120-px stride)
+    (7, 32, 9, 1, 4, 0, 0, 13, 300),     # conv1: R = 4 row-fold + K-split, partial last unit, 3 tiles
+    (32, 64, 3, 2, 1, 0, 0, 14, 260),    # d64, K-split over 18 steps, odd tile remainder
+    (128, 128, 3, 1, 0, 0, 0, 7, 320),   # residual conv: odd row count (last two-row unit half empty), 318-px rows
+    (128, 64, 3, 2, 1, 1, 1, 4, 140),    # u64 phase-fold (N = 256, single issuer), two tiles
+    (64, 32, 3, 2, 1, 1, 1, 3, 129),     # u32 phase-fold + K-split, one-pixel second tile
 ]
 
 
@@ -46,3 +52,26 @@ def test_emulated_kernel_addressing_matches_direct_conv(emu, case):
     assert rc == 0, emu.emu_last_error().decode()
     assert me.value <= 2e-6 * max(mr.value, 1.0), (me.value, mr.value)  # ~2^-21: hi*hi + lo*hi + hi*lo
     assert sm.value <= 227 * 1024
+
+
+def plan(emu, *case):
+    out = (C.c_int * 10)()
+    assert emu.emu_plan_info(*case, out) == 0, emu.emu_last_error().decode()
+    return dict(zip(("mt", "ksplit", "pf", "rf_R", "xfold_kw", "b_resident", "a_stages", "b_slots", "ntiles", "Npad"), out))
+
+
+def test_planner_decisions_for_the_720p_layers(emu):
+    """The plans DESIGN.md section 4.1 describes, at the sizes of the 720p frame."""
+    res = plan(emu, 128, 128, 3, 1, 0, 0, 0, 180, 320)
+    assert res["mt"] == 2 and not res["ksplit"] and not res["b_resident"]            # two-row units, one issuing warp per row
+    conv1 = plan(emu, 7, 32, 9, 1, 4, 0, 0, 800, 1360)
+    assert conv1["rf_R"] == 4 and conv1["ksplit"] and conv1["b_resident"]            # row-fold + K-split
+    final = plan(emu, 32, 3, 9, 1, 4, 0, 0, 720, 1280)
+    assert final["rf_R"] == 8 and final["xfold_kw"] == 9 and not final["ksplit"]     # x-fold + 8-row fold (256 columns)
+    u64 = plan(emu, 128, 64, 3, 2, 1, 1, 1, 180, 320)
+    assert u64["pf"] and u64["Npad"] == 256 and not u64["ksplit"]                    # phase-fold, N = 4 x 64
+    u32 = plan(emu, 64, 32, 3, 2, 1, 1, 1, 360, 640)
+    assert u32["pf"] and u32["Npad"] == 128 and u32["ksplit"] and u32["b_resident"]
+    for case in ((32, 64, 3, 2, 1, 0, 0, 800, 1360), (64, 128, 3, 2, 1, 0, 0, 400, 680)):
+        d = plan(emu, *case)
+        assert d["mt"] == 1 and d["ksplit"]
