@@ -14,6 +14,7 @@
 // All arithmetic uses explicit round-to-nearest intrinsics in the reference's evaluation order (no
 // FMA contraction), which makes the output bit-identical to the CPU restatement.
 #include "fav_common.cuh"
+#include "net_layout.cuh"
 
 namespace fav {
 
@@ -168,11 +169,13 @@ static int launch_warp(const float *img, const int64_t isz[4], const int64_t ist
 
 // ---- a-8 / a-9: fused temporal input ---------------------------------------------------------------
 // out7: [7,H,W] fp32.  VEC pixels per thread.
-template <int VEC, bool FIRST>
+// PACK: instead of the 7 fp32 planes, write the network's first operand directly (fp16 hi/lo, 8th channel zero) including
+// the nn.SpatialReflectionPadding(R) copies (train_video.lua:319-324) -- what pack_input_kernel would produce from out7.
+template <int VEC, bool FIRST, bool PACK = false>
 __global__ void __launch_bounds__(256) temporal_input_kernel(
     const float *__restrict__ content, const float *__restrict__ prev, const float *__restrict__ flow,
     const float *__restrict__ cert, const float *__restrict__ fill, const float *__restrict__ flow_mask,
-    float *__restrict__ out7, int H, int W, int border_mode) {
+    float *__restrict__ out7, int H, int W, int border_mode, Operand dst = Operand(), int R = 0) {
   int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x0 >= W || y >= H) return;
@@ -242,6 +245,31 @@ __global__ void __launch_bounds__(256) temporal_input_kernel(
 #pragma unroll
       for (int i = 0; i < VEC; ++i) res[3 + k][i] = __fadd_rn(0.0f, res[3 + k][i]);  // torch.add(zeros, x)
   }
+  if (PACK) {
+    // padded row / column indices fed by source index i: i itself, -i (1 <= i <= R) and 2(n-1)-i (n-1-R <= i <= n-2)
+    int ry[3], nry = 0;
+    ry[nry++] = y;
+    if (y >= 1 && y <= R) ry[nry++] = -y;
+    if (y <= H - 2 && y >= H - 1 - R) ry[nry++] = 2 * (H - 1) - y;
+    uint4 *hi = reinterpret_cast<uint4 *>(dst.hi), *lo = reinterpret_cast<uint4 *>(dst.lo);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int x = x0 + i;
+      const float v[8] = {res[0][i], res[1][i], res[2][i], res[3][i], res[4][i], res[5][i], res[6][i], 0.f};
+      uint4 h, l;
+      split_store8(v, &h, &l);
+      int cx[3], ncx = 0;
+      cx[ncx++] = x;
+      if (x >= 1 && x <= R) cx[ncx++] = -x;
+      if (x <= W - 2 && x >= W - 1 - R) cx[ncx++] = 2 * (W - 1) - x;
+      for (int a = 0; a < nry; ++a)
+        for (int b = 0; b < ncx; ++b) {
+          const int64_t q = dst.off16(dst.padT + R + ry[a], 0, dst.padL + R + cx[b]);
+          hi[q] = h; lo[q] = l;
+        }
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < 7; ++k) {
     if (VEC == 4)
@@ -249,6 +277,29 @@ __global__ void __launch_bounds__(256) temporal_input_kernel(
     else
       out7[k * HW + o] = res[k][0];
   }
+}
+
+// run_[next_]image: the fused input written straight into the first operand of the network (no out7 round trip)
+int launch_temporal_input_packed(const float *content, const float *prev, const float *flow, const float *cert,
+                                 const float *fill, const float *flow_mask, const Operand &dst, int R, int H, int W,
+                                 int border_mode, bool first, cudaStream_t st) {
+  const bool vec = (W % 4 == 0) && aligned16(content) && (first || (aligned16(flow) && aligned16(cert))) &&
+                   (!flow_mask || aligned16(flow_mask)) && (!fill || aligned16(fill));
+  dim3 block(32, 8);
+  if (vec) {
+    dim3 grid(ceil_div(W / 4, 32), ceil_div(H, 8));
+    if (first)
+      temporal_input_kernel<4, true, true><<<grid, block, 0, st>>>(content, prev, flow, cert, fill, flow_mask, nullptr, H, W, border_mode, dst, R);
+    else
+      temporal_input_kernel<4, false, true><<<grid, block, 0, st>>>(content, prev, flow, cert, fill, flow_mask, nullptr, H, W, border_mode, dst, R);
+  } else {
+    dim3 grid(ceil_div(W, 32), ceil_div(H, 8));
+    if (first)
+      temporal_input_kernel<1, true, true><<<grid, block, 0, st>>>(content, prev, flow, cert, fill, flow_mask, nullptr, H, W, border_mode, dst, R);
+    else
+      temporal_input_kernel<1, false, true><<<grid, block, 0, st>>>(content, prev, flow, cert, fill, flow_mask, nullptr, H, W, border_mode, dst, R);
+  }
+  return post_launch(first ? "first_frame_input" : "temporal_input");
 }
 
 int launch_temporal_input(const float *content, const float *prev, const float *flow, const float *cert,

@@ -19,6 +19,9 @@ namespace fav {
 int launch_temporal_input(const float *content, const float *prev, const float *flow, const float *cert,
                           const float *fill, const float *flow_mask, float *out7, int H, int W, int border_mode,
                           bool first, cudaStream_t st);
+int launch_temporal_input_packed(const float *content, const float *prev, const float *flow, const float *cert,
+                                 const float *fill, const float *flow_mask, const Operand &dst, int R, int H, int W,
+                                 int border_mode, bool first, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------
 struct Param {
@@ -383,6 +386,7 @@ struct ProfRec {
   cudaEvent_t e0, e1;
 };
 
+// in7 == nullptr: the caller has already written the first operand (fused temporal input, run_plan_frame)
 static int run_plan(fav_net *net, Plan &pl, const float *in7, float *out3, int final_mode, cudaStream_t st,
                     std::vector<ProfRec> *prof = nullptr) {
   auto begin = [&](int kind, double work, const std::string &name) -> int {
@@ -401,9 +405,11 @@ static int run_plan(fav_net *net, Plan &pl, const float *in7, float *out3, int f
     return check_cuda(cudaEventRecord(prof->back().e1, st), "cudaEventRecord");
   };
   FAV_TRY(check_cuda(cudaMemsetAsync(pl.stats, 0, pl.stats_bytes, st), "cudaMemsetAsync(stats)"));
-  FAV_TRY(begin(0, (double)pl.ops[0].H * pl.ops[0].W * (4.0 * net->in_dim + 32.0), "pack_input"));
-  FAV_TRY(launch_pack_input(in7, net->in_dim, pl.H, pl.W, net->reflect_pad, pl.ops[0], st));
-  FAV_TRY(end());
+  if (in7) {
+    FAV_TRY(begin(0, (double)pl.ops[0].H * pl.ops[0].W * (4.0 * net->in_dim + 32.0), "pack_input"));
+    FAV_TRY(launch_pack_input(in7, net->in_dim, pl.H, pl.W, net->reflect_pad, pl.ops[0], st));
+    FAV_TRY(end());
+  }
   for (PlanStep &s : pl.steps) {
     if (s.kind == 0) {
       {
@@ -451,9 +457,9 @@ static int run_plan(fav_net *net, Plan &pl, const float *in7, float *out3, int f
 }
 
 // run_[next_]image: the network part of a frame (input = pl.in7, fused deprocess) as one graph launch
-static int run_plan_frame(fav_net *net, Plan &pl, float *out3, cudaStream_t st) {
+static int run_plan_frame(fav_net *net, Plan &pl, const float *src7, float *out3, cudaStream_t st) {
   static const bool no_graph = getenv("FAV_NO_GRAPH") != nullptr;
-  if (no_graph || net->conv_impl != 0) return run_plan(net, pl, pl.in7, out3, 2, st);
+  if (no_graph || net->conv_impl != 0) return run_plan(net, pl, src7, out3, 2, st);
   for (Plan::GraphEntry &g : pl.graphs)
     if (g.out3 == out3) {
       g.last_use = ++pl.use_clock;
@@ -463,13 +469,13 @@ static int run_plan_frame(fav_net *net, Plan &pl, float *out3, cudaStream_t st) 
     }
   if (pl.eager_runs < 1) {  // one-time lazy initialisation (function attributes) must happen outside a capture
     ++pl.eager_runs;
-    return run_plan(net, pl, pl.in7, out3, 2, st);
+    return run_plan(net, pl, src7, out3, 2, st);
   }
   if (!net->cap_stream)
     FAV_TRY(check_cuda(cudaStreamCreateWithFlags(&net->cap_stream, cudaStreamNonBlocking), "cudaStreamCreate(capture)"));
   const uint64_t l0 = g_launches.load();
   FAV_TRY(check_cuda(cudaStreamBeginCapture(net->cap_stream, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture"));
-  const int rc = run_plan(net, pl, pl.in7, out3, 2, net->cap_stream);
+  const int rc = run_plan(net, pl, src7, out3, 2, net->cap_stream);
   cudaGraph_t graph = nullptr;
   const cudaError_t ce = cudaStreamEndCapture(net->cap_stream, &graph);
   const uint64_t n = g_launches.load() - l0;
@@ -478,14 +484,14 @@ static int run_plan_frame(fav_net *net, Plan &pl, float *out3, cudaStream_t st) 
     if (graph) cudaGraphDestroy(graph);
     cudaGetLastError();
     if (rc != FAV_OK) return rc;
-    return run_plan(net, pl, pl.in7, out3, 2, st);
+    return run_plan(net, pl, src7, out3, 2, st);
   }
   cudaGraphExec_t exec = nullptr;
   const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
   cudaGraphDestroy(graph);
   if (ie != cudaSuccess) {
     cudaGetLastError();
-    return run_plan(net, pl, pl.in7, out3, 2, st);
+    return run_plan(net, pl, src7, out3, 2, st);
   }
   if (pl.graphs.size() >= 8) {  // evict the least recently used destination
     size_t v = 0;
@@ -697,8 +703,13 @@ int fav_run_image(fav_net_t *net, const float *content, const float *fill, int H
   Plan *pl;
   FAV_TRY(build_plan(net, H, W, &pl));
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool fuse_pack = getenv("FAV_NO_FUSEPACK") == nullptr;
+  if (fuse_pack) {
+    FAV_TRY(launch_temporal_input_packed(content, nullptr, nullptr, nullptr, fill, nullptr, pl->ops[0], net->reflect_pad, H, W, 0, true, st));
+    return run_plan_frame(net, *pl, nullptr, out_rgb, st);
+  }
   FAV_TRY(launch_temporal_input(content, nullptr, nullptr, nullptr, fill, nullptr, pl->in7, H, W, 0, true, st));
-  return run_plan_frame(net, *pl, out_rgb, st);  // deprocess fused into the last epilogue (core.lua:149)
+  return run_plan_frame(net, *pl, pl->in7, out_rgb, st);  // deprocess fused into the last epilogue (core.lua:149)
 }
 
 int fav_run_next_image(fav_net_t *net, const float *content, const float *prev_rgb, const float *flow,
@@ -711,7 +722,13 @@ int fav_run_next_image(fav_net_t *net, const float *content, const float *prev_r
   Plan *pl;
   FAV_TRY(build_plan(net, H, W, &pl));
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool fuse_pack = getenv("FAV_NO_FUSEPACK") == nullptr;
+  if (fuse_pack) {
+    FAV_TRY(launch_temporal_input_packed(content, prev_rgb, flow, cert, fill, flow_mask, pl->ops[0], net->reflect_pad, H, W,
+                                         border_mode, false, st));
+    return run_plan_frame(net, *pl, nullptr, out_rgb, st);
+  }
   FAV_TRY(launch_temporal_input(content, prev_rgb, flow, cert, fill, flow_mask, pl->in7, H, W, border_mode, false, st));
-  return run_plan_frame(net, *pl, out_rgb, st);  // core.lua:172-173
+  return run_plan_frame(net, *pl, pl->in7, out_rgb, st);  // core.lua:172-173
 }
 }

@@ -12,20 +12,6 @@ namespace fav {
 constexpr int kStatRows = 8;
 constexpr int kApplyIter = 4;  // pixels per thread in the apply kernels: amortises the per-block finalisation
 
-__device__ __forceinline__ void split_store8(const float v[8], uint4 *hi_dst, uint4 *lo_dst) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float a = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
-    __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-    __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
-    h[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
-    l[i] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
-  }
-  *hi_dst = make_uint4(h[0], h[1], h[2], h[3]);
-  *lo_dst = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
 __device__ __forceinline__ void load_join8(const uint4 *hi_src, const uint4 *lo_src, float v[8]) {
   uint4 h = __ldg(hi_src), l = __ldg(lo_src);
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};

@@ -17,6 +17,7 @@
 //           coalesced across the 32 lanes of a warp.
 #pragma once
 #include "fav_common.cuh"
+#include <cuda_fp16.h>
 
 namespace fav {
 
@@ -35,6 +36,24 @@ struct Operand {
     return base + (parity ? (int64_t)(xs & 1) * Ws2 + (xs >> 1) : xs);
   }
 };
+
+#ifdef __CUDACC__
+// 8 fp32 channels of one pixel -> fp16 hi / lo halves (x ~= hi + lo), 16 bytes each
+__device__ __forceinline__ void split_store8(const float v[8], uint4 *hi_dst, uint4 *lo_dst) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
+    __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+    __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
+    h[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+    l[i] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+  }
+  *hi_dst = make_uint4(h[0], h[1], h[2], h[3]);
+  *lo_dst = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+#endif
 
 struct RawTensor {
   float *p = nullptr;

@@ -12,7 +12,7 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
                ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
-struct Cfg { int N; int layout; uint32_t a_lbo16, a_sbo16, b_lbo16, b_sbo16; int n_mma; int same_acc; int a_stride_bytes; int every; int what; int shift; int b_stride_bytes; };
+struct Cfg { int N; int layout; uint32_t a_lbo16, a_sbo16, b_lbo16, b_sbo16; int n_mma; int same_acc; int a_stride_bytes; int every; int what; int shift; int b_stride_bytes; int M; };
 
 __global__ void __launch_bounds__(224, 1) bench(Cfg c, long long *out) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(224, 1) bench(Cfg c, long long *out) {
   if (threadIdx.x < 32) {  // whole warp runs the loop (uniform control flow); one elected lane issues
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(c.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(c.N >> 3) << 17) | ((uint32_t)((c.M ? c.M : 128) >> 4) << 24);
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 100 * 1024);
     auto desc = [&](uint32_t addr, uint32_t lbo, uint32_t sbo) {
       return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(lbo & 0x3FFF) << 16) | ((uint64_t)(sbo & 0x3FFF) << 32) |
@@ -112,6 +112,10 @@ int main() {
       {"N256 A +16B steps",                    {256, 0, 130, 8, 256, 8, 4096, 1, 16, 0, 8, 0, 0}},
       {"N160 A +16B steps",                    {160, 0, 130, 8, 160, 8, 4096, 1, 16, 0, 8, 0, 0}},
       {"N160 aligned",                         {160, 0, 128, 8, 160, 8, 4096, 1, 4096, 0, 8, 0, 0}},
+      {"M64 N128",                             {128, 0, 130, 8, 128, 8, 4096, 1, 4096, 0, 8, 0, 4096, 64}},
+      {"M64 N256",                             {256, 0, 130, 8, 256, 8, 4096, 1, 4096, 0, 8, 0, 0, 64}},
+      {"M64 N64",                              {64, 0, 130, 8, 64, 8, 4096, 1, 4096, 0, 8, 0, 0, 64}},
+      {"M64 N128 two accumulators",            {128, 0, 130, 8, 128, 8, 4096, 0, 4096, 0, 8, 0, 4096, 64}},
   };
   for (int g = 148; g <= 148; g += 147) {
     for (auto &e : cfgs) {
