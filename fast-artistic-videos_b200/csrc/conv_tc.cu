@@ -192,9 +192,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const bool dual = dual_rows || ksplit;
   const uint32_t nissue = dual ? 2u : 1u;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], job.nl ? kNlWarps : 1); mbar_init(&sh->a_empty[i], nissue); }
+    for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], job.nl == 1 ? kNlWarps : (job.nl == 2 ? 4 : 1)); mbar_init(&sh->a_empty[i], nissue); }
     for (int i = 0; i < kMaxB; ++i) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], nissue); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], nissue); mbar_init(&sh->t_empty[i], job.nl ? 128 : 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], nissue); mbar_init(&sh->t_empty[i], job.nl == 1 ? 128 : 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 6) {
@@ -222,11 +222,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   const int ngroups = job.ngroups, nchunks = job.nchunks, spc = job.spc, Npad = job.Npad;
 
-  if (job.nl && (warp == 4 || (warp >= 8 && warp <= 14))) {
+  if (job.nl && (warp == 4 || (warp >= 12 && warp <= 14) || (job.nl == 1 && warp >= 8 && warp <= 11))) {
     // ===== norm-on-load patch producers: raw fp32 -> InstanceNorm (+ReLU) -> fp16 hi/lo -> MMA-ready stage =====
     // A warp owns whole (patch row, channel block) slabs: lanes run along x (coalesced 512-byte loads), up to
     // kNlPx float4 pairs in flight per lane, no per-pixel index arithmetic.
-    const int pw = warp == 4 ? 0 : warp - 7;  // 0 .. kNlWarps-1
+    // nl == 1: 8 producer warps (4, 8..14; one epilogue group); nl == 2: 4 producer warps (4, 12..14; two epilogue groups)
+    const int nlw = job.nl == 1 ? kNlWarps : 4;
+    const int pw = warp == 4 ? 0 : (job.nl == 1 ? warp - 7 : warp - 11);
     const int pslab = job.pslab16, nslabs = job.nrows * job.CbG;
     uint32_t s = 0, ph = 0;
     for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int g = 0; g < ngroups; ++g) {
         mbar_wait(&sh->a_empty[s], ph ^ 1);
         uint8_t *stage = a_base + s * 2 * a_stage_bytes;
-        for (int rc = pw; rc < nslabs; rc += kNlWarps) {
+        for (int rc = pw; rc < nslabs; rc += nlw) {
           const int ri = rc / job.CbG, cbi = rc - ri * job.CbG;
           const int ry = job.row_mul * y + job.grp_row[g][ri] - job.nl_padT, cb = job.grp_cb0[g] + cbi;
           const bool row_ok = ry >= 0 && ry < job.nl_H;
@@ -252,15 +254,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int k = 0; k < kNlPx; ++k) {
               const int p = pb + k * 32 + lane, x = xb + p;
               const bool ok = row_ok && p < pslab && x >= 0 && x < job.nl_W;
-              va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ok) { va[k] = __ldg(rp + x); vb[k] = __ldg(rp + job.nl_Wp + x); okm |= 1u << k; }
+              // unconditional loads from a clamped (always valid) address: all 2 * kNlPx requests are issued back to back
+              const int xc = x < 0 ? 0 : (x < job.nl_Wp ? x : job.nl_Wp - 1);
+              va[k] = __ldg(rp + xc); vb[k] = __ldg(rp + job.nl_Wp + xc);
+              if (ok) okm |= 1u << k;
             }
 #pragma unroll
             for (int k = 0; k < kNlPx; ++k) {
               const int p = pb + k * 32 + lane;
               if (p >= pslab) continue;
               float v[8] = {va[k].x, va[k].y, va[k].z, va[k].w, vb[k].x, vb[k].y, vb[k].z, vb[k].w};
-              if (okm & (1u << k)) {  // pixels outside the image stay zero (never normalised)
+              if (!(okm & (1u << k))) {  // pixels outside the image are zero (never normalised)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+              } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const float t = (v[i] - tm[i]) * ts[i] + tb[i];
@@ -554,11 +561,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (leader) tc_commit(&sh->t_full[as]);  // accumulator complete -> epilogue
     }
     __syncwarp();
-  } else if (warp < 4 || (warp >= 8 && warp < 12 && !job.nl)) {
+  } else if (warp < 4 || (warp >= 8 && warp < 12 && job.nl != 1)) {
     // ===== epilogue warps 0..3 (group 0) and 8..11 (group 1): TMEM lane = pixel; the two groups split the columns =====
     uint32_t tl = 0;
     const int wq = warp & 3, eg = warp >> 3;
-    const int neg = job.nl ? 1 : 2;  // norm-on-load jobs: the second group works as patch producers
+    const int neg = job.nl == 1 ? 1 : 2;  // norm-on-load (8-producer mode): the second group works as patch producers
     const int px = wq * 32 + lane;
     const int nj = (Npad + 15) >> 4;
     const bool ks = job.ksplit != 0;

@@ -337,7 +337,9 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
           ok = !j.rf_R && !j.pf && !j.xfold_kw && j.nseg == 1 && j.seg_dst16[0] == 0 && j.seg_len16[0] == j.pslab16 && j.row_mul == 1;
           if (ok) {
             ConvJob t = j;
-            t.nl = 1; t.nl_raw = reinterpret_cast<const float4 *>(ap.raw.p); t.nl_Cq = ap.raw.Cq; t.nl_Wp = ap.raw.Wp;
+            t.nl = 1;
+            if (const char *e = getenv("FAV_NL_MODE")) t.nl = atoi(e) == 2 ? 2 : 1;
+            t.nl_raw = reinterpret_cast<const float4 *>(ap.raw.p); t.nl_Cq = ap.raw.Cq; t.nl_Wp = ap.raw.Wp;
             t.nl_H = ap.raw.H; t.nl_W = ap.raw.W; t.nl_padT = in.padT; t.nl_padL = in.padL; t.nl_relu = ap.relu; t.nl_C = n.C;
             t.nl_sums = pl->stats + ap.stats_off; t.nl_gamma = n.d_gamma; t.nl_beta = n.d_beta;
             t.nl_inv_count = 1.0 / ((double)ap.raw.H * ap.raw.W); t.nl_eps = 1e-5;
