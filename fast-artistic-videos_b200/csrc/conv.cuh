@@ -6,6 +6,7 @@ namespace fav {
 
 constexpr int kMaxTaps = 81;
 constexpr int kMaxSteps = 168;
+constexpr int kMaxRfRows = 24;  // row-fold: R + KH - 1 patch rows per unit
 constexpr int kMaxRows = 10;
 constexpr int kMaxGroups = 12;
 constexpr int kTileM = 128;  // output pixels per MMA tile = TMEM lanes
@@ -65,6 +66,10 @@ struct ConvJob {
   int pf;
   int pf_n[4], pf_col[4], pf_len16[4], pf_src16[4], pf_grp16, pf_cout;
   int ksplit;          // 1: two issuing warps take alternate K steps into two accumulators (columns +0 / +128)
+  // row-fold: per patch row iy (host-computed, keeps the issue loop free of index arithmetic): accumulator column of
+  // the first output row it feeds, weight-row offset of its slice, instruction descriptors for all / old / new rows
+  uint32_t rf_dcol[kMaxRfRows], rf_boff[kMaxRfRows], rf_idn_all[kMaxRfRows], rf_idn_acc[kMaxRfRows], rf_idn_new[kMaxRfRows],
+      rf_off_new[kMaxRfRows];
   // norm-on-load: the input is the RAW output of the previous convolution; InstanceNorm (+ReLU) and the fp16 hi/lo split
   // happen in the producer warps while the patch is staged (replaces a separate in_apply pass + operand round trip)
   int nl;

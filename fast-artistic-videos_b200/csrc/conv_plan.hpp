@@ -474,6 +474,21 @@ static inline int fill_conv_job(const ConvDef &c, const ConvPhase &ph, const Ope
     j.ksplit = (ok && cols <= 128 && (!ph.pf || ph.spc % 2 == 0) && !getenv("FAV_NO_KSPLIT")) ? 1 : 0;
     if (!ph.rf_R && !ph.pf && (int)ph.steps.size() * ph.nrg * ph.nchg < 2) j.ksplit = 0;
   }
+  if (ph.rf_R) {  // per-patch-row issue table (conv_tc.cu, row-fold loop)
+    const int KH = j.rf_kh, R = j.rf_R, nblk = j.rf_nblk;
+    if (j.rf_total_rows > kMaxRfRows) { set_error("conv %s: row-fold unit too tall", c.name.c_str()); return FAV_ERR_UNSUPPORTED; }
+    const uint32_t idesc_base = (1u << 4) | ((uint32_t)(kTileM >> 4) << 24);
+    auto idn = [&](int rows) { return rows > 0 ? idesc_base | ((uint32_t)((rows * nblk) >> 3) << 17) : 0u; };
+    for (int iy = 0; iy < j.rf_total_rows; ++iy) {
+      const int r_min = iy - (KH - 1) > 0 ? iy - (KH - 1) : 0, r_max = iy < R - 1 ? iy : R - 1;
+      const int nb = r_max - r_min + 1, blk0 = KH - 1 - (iy - r_min);
+      // rows this issuing warp touches for the first time: r = iy (ky = 0) and, K-split, r = iy - 1 as well
+      const int nf = (iy < R ? 1 : 0) + ((j.ksplit && iy >= 1 && iy - 1 < R) ? 1 : 0);
+      j.rf_dcol[iy] = (uint32_t)(r_min * nblk); j.rf_boff[iy] = (uint32_t)(blk0 * nblk);
+      j.rf_idn_all[iy] = idn(nb); j.rf_idn_acc[iy] = idn(nb - nf); j.rf_idn_new[iy] = idn(nf);
+      j.rf_off_new[iy] = (uint32_t)((nb - nf) * nblk);
+    }
+  }
   j.oy_mul = c.out_mul; j.ox_mul = c.out_mul; j.oy_off = ph.oy_off; j.ox_off = ph.ox_off;
   // every bulk copy must stay inside the operand allocation
   int64_t max_row = (int64_t)j.row_mul * (ceil_div(pHo, j.mt) * j.mt - 1) + in.padT + ph.rows.back();

@@ -404,36 +404,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (leader) {
             for (int ri = 0; ri < job.nrows; ++ri) {
               const int iy = g * job.nrows + ri;
-              const int r_min = iy - (KH - 1) > 0 ? iy - (KH - 1) : 0, r_max = iy < R - 1 ? iy : R - 1;
-              const uint32_t nb = (uint32_t)(r_max - r_min + 1);
-              const uint32_t blk0 = (uint32_t)(KH - 1 - (iy - r_min));  // first weight block of the slice (ky = iy - r_min)
               if (ksplit && (uint32_t)(iy & 1) != drow) continue;      // K-split: this warp owns patch rows of its parity
-              // rows this warp touches for the first time (overwrite): r = iy (ky = 0) and, K-split, r = iy - 1 as well
-              const uint32_t nf = (uint32_t)(iy < R) + (uint32_t)(ksplit && iy >= 1 && iy - 1 < R);
+              // host-computed per-row table (conv_plan.hpp): columns, weight slice and descriptors of the rows fed
+              const uint32_t dcol = d0 + job.rf_dcol[iy], boff = job.rf_boff[iy];
+              const uint32_t idn_all = job.rf_idn_all[iy], idn_acc = job.rf_idn_acc[iy], idn_new = job.rf_idn_new[iy];
+              const uint32_t off_new = job.rf_off_new[iy];
               const uint32_t arow = (uint32_t)ri * (uint32_t)job.rf_row16;
               for (int st = 0; st < job.rf_steps; ++st) {
                 const uint32_t dls = steps32[st];
                 const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + arow + dls), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + arow + dls);
                 // weight chunk st: [hi: 2 k-halves x NR rows][lo: ...]; LBO = NR rows
-                const uint32_t bq = (b16 + (uint32_t)st * (uint32_t)job.chunk16 + blk0 * nblk) | (NR << 16);
+                const uint32_t bq = (b16 + (uint32_t)st * (uint32_t)job.chunk16 + boff) | (NR << 16);
                 const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | bq, bd_lo = ((uint64_t)desc_hi << 32) | (bq + 2u * NR);
-                const uint32_t dcol = d0 + (uint32_t)r_min * nblk;
-                if (st == 0 && nf) {
-                  if (nb > nf) {  // rows that already hold partial sums
-                    const uint32_t idn = idesc_base | ((((nb - nf) * nblk) >> 3) << 17);
-                    tc_mma_f16(dcol, ad_hi, bd_hi, idn, 1);
-                    tc_mma_f16(dcol, ad_lo, bd_hi, idn, 1);
-                    tc_mma_f16(dcol, ad_hi, bd_lo, idn, 1);
+                if (st == 0 && idn_new) {
+                  if (idn_acc) {  // rows that already hold partial sums
+                    tc_mma_f16(dcol, ad_hi, bd_hi, idn_acc, 1);
+                    tc_mma_f16(dcol, ad_lo, bd_hi, idn_acc, 1);
+                    tc_mma_f16(dcol, ad_hi, bd_lo, idn_acc, 1);
                   }
-                  const uint32_t idn = idesc_base | (((nf * nblk) >> 3) << 17), off = (nb - nf) * nblk;  // new rows: overwrite
-                  tc_mma_f16(dcol + off, ad_hi, bd_hi + off, idn, 0);
-                  tc_mma_f16(dcol + off, ad_lo, bd_hi + off, idn, 1);
-                  tc_mma_f16(dcol + off, ad_hi, bd_lo + off, idn, 1);
+                  // rows this warp touches for the first time (r = iy; K-split: r = iy - 1 as well): overwrite
+                  tc_mma_f16(dcol + off_new, ad_hi, bd_hi + off_new, idn_new, 0);
+                  tc_mma_f16(dcol + off_new, ad_lo, bd_hi + off_new, idn_new, 1);
+                  tc_mma_f16(dcol + off_new, ad_hi, bd_lo + off_new, idn_new, 1);
                 } else {
-                  const uint32_t idn = idesc_base | (((nb * nblk) >> 3) << 17);
-                  tc_mma_f16(dcol, ad_hi, bd_hi, idn, 1);
-                  tc_mma_f16(dcol, ad_lo, bd_hi, idn, 1);
-                  tc_mma_f16(dcol, ad_hi, bd_lo, idn, 1);
+                  tc_mma_f16(dcol, ad_hi, bd_hi, idn_all, 1);
+                  tc_mma_f16(dcol, ad_lo, bd_hi, idn_all, 1);
+                  tc_mma_f16(dcol, ad_hi, bd_lo, idn_all, 1);
                 }
               }
             }

@@ -129,6 +129,13 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
             const int nf = (iy < R ? 1 : 0) + ((j.ksplit && iy >= 1 && iy - 1 < R) ? 1 : 0);
             const int r_min = std::max(0, iy - (KH - 1)), r_max = std::min(R - 1, iy);
             const int nb = r_max - r_min + 1, blk0 = KH - 1 - (iy - r_min);
+            {  // the kernel reads these from the host-computed per-row table
+              const uint32_t ib = (1u << 4) | ((uint32_t)(kTileM >> 4) << 24);
+              auto idn = [&](int rows) { return rows > 0 ? ib | ((uint32_t)((rows * nblk) >> 3) << 17) : 0u; };
+              if (j.rf_dcol[iy] != (uint32_t)(r_min * nblk) || j.rf_boff[iy] != (uint32_t)(blk0 * nblk) ||
+                  j.rf_idn_all[iy] != idn(nb) || j.rf_idn_acc[iy] != idn(nb - nf) || j.rf_idn_new[iy] != idn(nf) ||
+                  j.rf_off_new[iy] != (uint32_t)((nb - nf) * nblk)) { set_error("row-fold table mismatch at row %d", iy); return 11; }
+            }
             for (int st = 0; st < j.rf_steps; ++st) {
               const KStep ks = j.steps[st];
               const uint16_t *chunk = pk.data() + (size_t)st * j.chunk16 * 8;   // [hi: 2 x NR rows][lo: 2 x NR rows]
