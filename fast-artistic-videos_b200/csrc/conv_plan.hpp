@@ -173,13 +173,16 @@ static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
     // R output rows per unit: the patch-row re-read factor is (R + KH - 1) / R.  The wide-input x-fold layer (final conv)
     // is bound by that L2 -> SM traffic, so it takes R = 8 (8 x 32 = 256 accumulator columns, still double buffered);
     // conv1 (one channel block) is issue bound and keeps R = 4 so that the unit can be K-split between two warps.
-    int R = (ph.kind == 3 && 8 * ph.Npad <= 256) ? 8 : 4;
-    if (const char *e = getenv(ph.kind == 3 ? "FAV_RF_R3" : "FAV_RF_R1")) R = atoi(e);
-    const int total_rows = R + nrows - 1;
+    // (With 64 input channels -- paper arch -- a patch row is 35 KB and only R = 4 fits the stage / group limits.)
+    int cand[2] = {(ph.kind == 3 && 8 * ph.Npad <= 256) ? 8 : 4, 4};
+    if (const char *e = getenv(ph.kind == 3 ? "FAV_RF_R3" : "FAV_RF_R1")) cand[0] = cand[1] = atoi(e);
     const int row_bytes = ph.CbG * ph.pslab16 * 32;  // hi + lo of one patch row
-    int rps = 0;
-    for (int d = total_rows; d >= 1; --d)
-      if (total_rows % d == 0 && total_rows / d <= kMaxGroups && d <= kMaxRows && d * row_bytes <= 36 * 1024) { rps = d; break; }
+    int R = 0, rps = 0, total_rows = 0;
+    for (int ci = 0; ci < 2 && rps == 0; ++ci) {
+      R = cand[ci]; total_rows = R + nrows - 1;
+      for (int d = total_rows; d >= 1; --d)
+        if (total_rows % d == 0 && total_rows / d <= kMaxGroups && d <= kMaxRows && d * row_bytes <= 36 * 1024) { rps = d; break; }
+    }
     if (consecutive && rps > 0) {
       ph.rf_R = R; ph.rf_rps = rps;
       // K steps of ONE patch row; units hold (tap column or channel block) only -- the filter row comes from iy - r
