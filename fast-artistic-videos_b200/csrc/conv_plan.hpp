@@ -165,7 +165,8 @@ static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
   // ---- row-fold for tall filters with a narrow N block (see conv.cuh) -------------------------------------------
   ph.rf_R = 0;
   if ((ph.kind == 1 || ph.kind == 3) && !c.transposed && c.in_stride == 1 && nrows >= 5 && ph.Npad <= 32 &&
-      nrows * ph.Npad <= 512 && c.Cb <= 8) {
+      nrows * ph.Npad <= 512 && c.Cb <= 4) {  // Cb = 8 (64-channel final conv of the paper arch): a 35 KB patch row per
+                                              // stage leaves 12 MMAs per stage -- latency bound, 359 us vs 156 us unfolded (measured)
     const int saveCbG = ph.CbG, saveNchg = ph.nchg;
     ph.CbG = c.Cb; ph.nchg = 1;  // a row stage holds every channel block of the patch row
     bool consecutive = true;
@@ -173,7 +174,6 @@ static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
     // R output rows per unit: the patch-row re-read factor is (R + KH - 1) / R.  The wide-input x-fold layer (final conv)
     // is bound by that L2 -> SM traffic, so it takes R = 8 (8 x 32 = 256 accumulator columns, still double buffered);
     // conv1 (one channel block) is issue bound and keeps R = 4 so that the unit can be K-split between two warps.
-    // (With 64 input channels -- paper arch -- a patch row is 35 KB and only R = 4 fits the stage / group limits.)
     int cand[2] = {(ph.kind == 3 && 8 * ph.Npad <= 256) ? 8 : 4, 4};
     if (const char *e = getenv(ph.kind == 3 ? "FAV_RF_R3" : "FAV_RF_R1")) cand[0] = cand[1] = atoi(e);
     const int row_bytes = ph.CbG * ph.pslab16 * 32;  // hi + lo of one patch row

@@ -42,7 +42,7 @@ CASES = [  # cin, cout, k, stride, pad, transposed, adj, H, W
     (128, 128, 3, 1, 0, 0, 0, 7, 320),   # residual conv: odd row count (last two-row unit half empty), 318-px rows
     (128, 64, 3, 2, 1, 1, 1, 4, 140),    # u64 phase-fold (N = 256, single issuer), two tiles
     (64, 32, 3, 2, 1, 1, 1, 3, 129),     # u32 phase-fold + K-split, one-pixel second tile
-    (64, 3, 9, 1, 4, 0, 0, 11, 140),     # paper-arch final conv (64 channels): row-fold falls back to R = 4
+    (64, 3, 9, 1, 4, 0, 0, 11, 140),     # paper-arch final conv (64 channels): x-fold without row-fold
 ]
 
 
@@ -74,7 +74,7 @@ def test_planner_decisions_for_the_720p_layers(emu):
     u32 = plan(emu, 64, 32, 3, 2, 1, 1, 1, 360, 640)
     assert u32["pf"] and u32["Npad"] == 128 and u32["ksplit"] and u32["b_resident"]
     final64 = plan(emu, 64, 3, 9, 1, 4, 0, 0, 720, 1280)                             # paper arch: 64 input channels
-    assert final64["rf_R"] == 4 and final64["xfold_kw"] == 9 and final64["ksplit"]   # 35 KB patch rows: R = 4 (+ K-split)
+    assert final64["rf_R"] == 0 and final64["xfold_kw"] == 9                         # 35 KB patch rows: x-fold only (row-fold measured 2.3x slower)
     for case in ((32, 64, 3, 2, 1, 0, 0, 800, 1360), (64, 128, 3, 2, 1, 0, 0, 400, 680)):
         d = plan(emu, *case)
         assert d["mt"] == 1 and d["ksplit"]

@@ -5,11 +5,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "fast-artistic-videos_b200"))
     import torch
     from fav_b200 import models_video
-    net = models_video.synthetic_model("candy")
+    from fav_b200 import synth
+    net = models_video.synthetic_model("candy", synth.PAPER_ARCH if os.environ.get("FAV_ABL_ARCH") == "paper" else synth.DEFAULT_ARCH)
     x = torch.randn(1, 7, 720, 1280, device="cuda") * 50
     for _ in range(3): prof = net.profile(x)
     torch.cuda.synchronize()
-    print(json.dumps({p["name"]: round(p["ms"] * 1e3, 1) for p in prof}), "total", round(sum(p["ms"] for p in prof) * 1e3, 1))
+    keep = os.environ.get("FAV_ABL_ONLY")
+    print(json.dumps({p["name"]: round(p["ms"] * 1e3, 1) for p in prof if not keep or p["name"] in keep.split("+")}), "total", round(sum(p["ms"] for p in prof) * 1e3, 1))
 else:
     variants = [dict(), dict(FAV_NO_NL="1")] if len(sys.argv) < 2 else [dict(kv.split("=") for kv in a.split(",") if kv) for a in sys.argv[1:]]
     for v in variants:
