@@ -759,7 +759,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
 static size_t tc_fixed_smem(const ConvJob &job) {
   return (size_t)job.a_stages * 2 * job.stage16 * 16 + sizeof(TcShared) + 128 +
-         (job.xfold_kw ? (size_t)2 * kTileM * kExchPitch * 4 : (size_t)(256 + 8 * 2 * 128) * 4) + (job.nl ? (size_t)3 * kNlMaxC * 4 : 0);
+         (job.xfold_kw ? (size_t)(job.mt >= 2 ? 2 : 1) * kTileM * kExchPitch * 4 :  // one exchange buffer per epilogue group that owns rows
+          (size_t)(256 + 8 * 2 * 128) * 4) + (job.nl ? (size_t)3 * kNlMaxC * 4 : 0);
 }
 size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
 

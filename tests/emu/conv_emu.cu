@@ -23,7 +23,7 @@ void set_error(const char *fmt, ...) {
 std::atomic<uint64_t> g_launches{0};
 // mirror of conv_tc.cu: kNA = 2 patch stages, up to 16 weight slots (resident when every chunk fits)
 static size_t tc_fixed_smem(const ConvJob &job) {
-  return (size_t)job.a_stages * 2 * job.stage16 * 16 + 640 + (job.xfold_kw ? (size_t)2 * 128 * 33 * 4 : (size_t)(256 + 2048) * 4);
+  return (size_t)job.a_stages * 2 * job.stage16 * 16 + 640 + (job.xfold_kw ? (size_t)(job.mt >= 2 ? 2 : 1) * 128 * 33 * 4 : (size_t)(256 + 2048) * 4);
 }
 size_t conv_tc_smem_bytes(const ConvJob &job) { return tc_fixed_smem(job) + (size_t)job.b_slots * job.chunk16 * 16; }
 void conv_tc_choose_slots(ConvJob &job) {
