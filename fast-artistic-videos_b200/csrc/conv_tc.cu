@@ -16,13 +16,19 @@
 // layout (net_layout.cuh), every filter tap reuses the same shared-memory patch: the UMMA matrix descriptor
 // just starts 16 B * dx further.  Weights stream through a ring of pre-packed chunks.
 //
-// Warp roles (224 threads, 1 CTA / SM, persistent over tiles):
-//   warps 0-3  epilogue: tcgen05.ld TMEM -> registers -> +bias -> float4 stores (or tanh/deprocess, last layer)
-//   warp  4    A producer (bulk copies of the patch, all lanes issue)
-//   warp  5    B producer (bulk copies of weight chunks)
-//   warp  6    TMEM allocator + single-thread MMA issuer
-// Pipelines: A stages (kNA) and weight slots (ring, or resident for small layers) with full/empty mbarriers; TMEM accumulator double-buffered so
-// the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles (480 threads = 15 warps, 1 CTA / SM, persistent over work units):
+//   warps 0-3, 8-11  epilogue (TMEM lane quarter = warp % 4; the two groups split column chunks / output rows):
+//                    tcgen05.ld TMEM -> registers -> +bias -> float4 stores + fused InstanceNorm statistics
+//                    (or x-fold reduction + tanh/deprocess for the last layer)
+//   warp  4          A producer (bulk copies of the patch, all lanes issue)
+//   warp  5          B producer (bulk copies of weight chunks; resident when the layer's weights fit)
+//   warps 6, 7       MMA issuers (6 also allocates TMEM): one accumulator row each for two-row units, alternate K steps
+//                    (K-split, accumulators at columns +0 / +128, summed by the epilogue) for one-row units
+//   warps 12-14      extra patch producers of norm-on-load jobs (with warp 4 and 8-11: raw fp32 -> InstanceNorm + ReLU ->
+//                    fp16 hi/lo staged for the MMA, replacing a separate in_apply pass)
+// Plans per layer family (conv_plan.hpp): generic, stride-2 parity split, tap pairing (Cin = 8), x-fold, row-fold, phase-fold.
+// Pipelines: A stages and weight slots (ring, or resident for small layers) with full/empty mbarriers; TMEM accumulator
+// double-buffered so the epilogue of unit i overlaps the MMAs of unit i+1.
 #include "conv.cuh"
 
 namespace fav {
@@ -30,7 +36,7 @@ namespace fav {
 constexpr int kMaxA = 4;  // patch stages
 constexpr int kMaxSpc = 8;  // K16 steps per weight chunk (conv_plan.hpp caps spc at this)
 constexpr int kMaxB = 16;  // weight slots (ring or resident)
-constexpr int kTmemCols = 512;  // 2 accumulator stages x mt (<= 2) tiles x Npad (<= 128) columns
+constexpr int kTmemCols = 512;  // 2 accumulator stages x 256 columns (two rows / two K-split halves x <= 128, or one x 256)
 constexpr int kThreads = 480;  // warps 0-3 + 8-11 epilogue (TMEM lane quarter = warp % 4), 4 A producer, 5 B producer, 6/7 MMA issuers,
                                 // 12..14 extra patch producers of norm-on-load jobs
 constexpr int kNlWarps = 8;     // warps 4, 8..11 (the second epilogue group turns producer), 12, 13, 14
