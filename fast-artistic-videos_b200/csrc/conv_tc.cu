@@ -305,6 +305,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ===== A producer: the input patch of each (tile, channel group) =====
     const int per_row = job.CbG * job.nseg * 2;  // copies per patch row (x2: hi, lo)
     const int ncopies = job.nrows * per_row;
+    uint32_t ucopy_leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ucopy_leader));
     uint32_t stage_tx = 0;
     for (int s = 0; s < job.nseg; ++s) stage_tx += (job.dbg & 4) ? 16u : (uint32_t)job.seg_len16[s] * 16u;
     stage_tx *= (uint32_t)(job.nrows * job.CbG * 2);
@@ -317,6 +319,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (lane == 0) mbar_arrive_expect_tx(&sh->a_full[s], stage_tx);
         __syncwarp();
         uint8_t *stage = a_base + s * 2 * a_stage_bytes;
+        if (job.ucopy) {
+          // Experimental: with per-lane copy parameters ptxas serialises the 32 lanes through
+          // an ELECT/R2UR/BRA.U.ANY waterfall (~88 cycles per copy, measured).  Here ONE elected lane walks the copies of
+          // the stage; every operand is warp-uniform, so the UBLKCPs issue from uniform registers without a waterfall.
+          if (ucopy_leader) {
+            for (int ri = 0; ri < job.nrows; ++ri)
+              for (int cbi = 0; cbi < job.CbG; ++cbi) {
+                const int64_t row16 = ((int64_t)(job.row_mul * y + job.grp_row[g][ri]) * job.a_Cb + job.grp_cb0[g] + cbi) *
+                                          job.a_slab16 + x0;
+                uint8_t *drow = stage + (uint32_t)((ri * job.CbG + cbi) * job.pslab16) * 16u;
+                for (int seg = 0; seg < job.nseg; ++seg) {
+                  const uint32_t bytes = (job.dbg & 4) ? 16u : (uint32_t)job.seg_len16[seg] * 16u;
+                  const int64_t s16 = row16 + job.seg_src16[seg];
+                  uint8_t *d = drow + (uint32_t)job.seg_dst16[seg] * 16u;
+                  bulk_g2s(d, job.a_hi + s16, bytes, &sh->a_full[s]);
+                  bulk_g2s(d + a_stage_bytes, job.a_lo + s16, bytes, &sh->a_full[s]);
+                }
+              }
+          }
+          __syncwarp();
+          if (++s == nstages) { s = 0; ph ^= 1; }
+          continue;
+        }
         for (int c = lane; c < ncopies; c += 32) {
           int ri = c / per_row, r = c - ri * per_row;
           int cbi = r / (job.nseg * 2);
