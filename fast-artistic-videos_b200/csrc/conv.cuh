@@ -73,6 +73,7 @@ struct ConvJob {
   // norm-on-load: the input is the RAW output of the previous convolution; InstanceNorm (+ReLU) and the fp16 hi/lo split
   // happen in the producer warps while the patch is staged (replaces a separate in_apply pass + operand round trip)
   int ucopy;           // experimental (FAV_UCOPY=1): one elected lane issues the patch copies with warp-uniform operands
+  int aprod;           // experimental (FAV_APROD=4): warps 4, 12, 13, 14 share the patch copies of a stage (0/1: warp 4 alone)
   int nl;
   const float4 *nl_raw; int nl_Cq, nl_Wp, nl_H, nl_W, nl_padT, nl_padL, nl_relu, nl_C;
   const double *nl_sums; const float *nl_gamma, *nl_beta; double nl_inv_count, nl_eps;

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const bool dual = dual_rows || ksplit;
   const uint32_t nissue = dual ? 2u : 1u;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], job.nl == 1 ? kNlWarps : (job.nl == 2 ? 4 : 1)); mbar_init(&sh->a_empty[i], nissue); }
+    for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], job.nl == 1 ? kNlWarps : (job.nl == 2 ? 4 : (job.aprod == 4 ? 4 : 1))); mbar_init(&sh->a_empty[i], nissue); }
     for (int i = 0; i < kMaxB; ++i) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], nissue); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], nissue); mbar_init(&sh->t_empty[i], job.nl == 1 ? 128 : 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -301,8 +301,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (++s == nstages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 4 || (job.aprod == 4 && !job.nl && warp >= 12 && warp <= 14)) {
     // ===== A producer: the input patch of each (tile, channel group) =====
+    // (experimental FAV_APROD=4: warps 4, 12, 13, 14 each issue a quarter of the copies of a stage -- the bulk-copy
+    // instruction itself costs ~88 issue cycles)
+    const int npw = job.aprod == 4 ? 4 : 1, pw = warp == 4 ? 0 : warp - 11;
     const int per_row = job.CbG * job.nseg * 2;  // copies per patch row (x2: hi, lo)
     const int ncopies = job.nrows * per_row;
     uint32_t ucopy_leader;
@@ -316,10 +319,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int y = yu * job.mt;
       for (int g = 0; g < ngroups; ++g) {
         mbar_wait(&sh->a_empty[s], ph ^ 1);
-        if (lane == 0) mbar_arrive_expect_tx(&sh->a_full[s], stage_tx);
+        if (npw == 1) {
+          if (lane == 0) mbar_arrive_expect_tx(&sh->a_full[s], stage_tx);
+        } else {  // this warp's share of the stage's bytes: copies pw*32 + lane + 128*k
+          uint32_t my = 0;
+          for (int c = pw * 32 + lane; c < ncopies; c += 32 * npw) {
+            const int r = c % per_row, seg = (r % (job.nseg * 2)) >> 1;
+            my += (job.dbg & 4) ? 16u : (uint32_t)job.seg_len16[seg] * 16u;
+          }
+          my = __reduce_add_sync(0xffffffffu, my);
+          if (lane == 0) mbar_arrive_expect_tx(&sh->a_full[s], my);
+        }
         __syncwarp();
         uint8_t *stage = a_base + s * 2 * a_stage_bytes;
-        if (job.ucopy) {
+        if (job.ucopy && npw == 1) {
           // Experimental: with per-lane copy parameters ptxas serialises the 32 lanes through
           // an ELECT/R2UR/BRA.U.ANY waterfall (~88 cycles per copy, measured).  Here ONE elected lane walks the copies of
           // the stage; every operand is warp-uniform, so the UBLKCPs issue from uniform registers without a waterfall.
@@ -342,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (++s == nstages) { s = 0; ph ^= 1; }
           continue;
         }
-        for (int c = lane; c < ncopies; c += 32) {
+        for (int c = pw * 32 + lane; c < ncopies; c += 32 * npw) {
           int ri = c / per_row, r = c - ri * per_row;
           int cbi = r / (job.nseg * 2);
           r -= cbi * job.nseg * 2;
