@@ -91,6 +91,19 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
     smem_max = std::max(smem_max, conv_tc_smem_bytes(j));
     if (conv_tc_smem_bytes(j) > 227 * 1024) { set_error("smem budget"); return 3; }
     const int Npad = j.Npad;
+    {  // FAV_APROD=4 (four producer warps): the per-warp expect_tx shares must add up to the bytes of a stage
+      const int per_row = j.CbG * j.nseg * 2, ncopies = j.nrows * per_row;
+      uint64_t stage_tx = 0, shares = 0;
+      for (int sg = 0; sg < j.nseg; ++sg) stage_tx += (uint64_t)j.seg_len16[sg] * 16u;
+      stage_tx *= (uint64_t)(j.nrows * j.CbG * 2);
+      for (int pw = 0; pw < 4; ++pw)
+        for (int lane = 0; lane < 32; ++lane)
+          for (int cc = pw * 32 + lane; cc < ncopies; cc += 128) {
+            const int r = cc % per_row, sg = (r % (j.nseg * 2)) >> 1;
+            shares += (uint64_t)j.seg_len16[sg] * 16u;
+          }
+      if (shares != stage_tx) { set_error("producer byte shares do not add up"); return 12; }
+    }
     std::vector<uint16_t> st_hi((size_t)j.stage16 * 8), st_lo((size_t)j.stage16 * 8);
     std::vector<double> acc(j.rf_R ? (size_t)kTileM * 512 : (size_t)2 * kTileM * Npad);
     std::vector<double> acc2(acc.size());  // K-split: the second issuing warp's accumulator (TMEM columns +128)
