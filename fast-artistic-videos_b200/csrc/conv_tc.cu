@@ -87,6 +87,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// 4-D tiled tensor copy (TMA): coordinates innermost first = (channel-in-block, pixel, channel block, row)
+__device__ __forceinline__ void tma_load4(void *dst, const TmaMap *map, int c0, int c1, int c2, int c3, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -332,6 +340,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         __syncwarp();
         uint8_t *stage = a_base + s * 2 * a_stage_bytes;
+        if (job.tma && npw == 1) {
+          // Experimental: the whole stage = one 4-D box per plane; out-of-range parts of the
+          // box are zero-filled by the TMA unit and still count towards the transaction bytes.
+          if (lane == 0) {
+            const int row = job.row_mul * y + job.grp_row[g][0], px = job.seg_src16[0] + x0;
+            tma_load4(stage, &job.tm_hi, 0, px, job.grp_cb0[g], row, &sh->a_full[s]);
+            tma_load4(stage + a_stage_bytes, &job.tm_lo, 0, px, job.grp_cb0[g], row, &sh->a_full[s]);
+          }
+          __syncwarp();
+          if (++s == nstages) { s = 0; ph ^= 1; }
+          continue;
+        }
         if (job.ucopy && npw == 1) {
           // Experimental: with per-lane copy parameters ptxas serialises the 32 lanes through
           // an ELECT/R2UR/BRA.U.ANY waterfall (~88 cycles per copy, measured).  Here ONE elected lane walks the copies of
