@@ -176,7 +176,10 @@ FAV_API int fav_net_layer_output(fav_net_t *net, int index, float *out, int *C, 
                                  void *stream);
 
 /* a-9  run_image (frame 1, model_img == nil)    fast_artistic_video_core.lua:121-158
- * content [3,H,W] RGB [0,1] -> out_rgb [3,H,W] = deprocess(model_vid(...))[1]. */
+ * content [3,H,W] RGB [0,1] -> out_rgb [3,H,W] = deprocess(model_vid(...))[1].
+ * fav_run_image / fav_run_next_image enqueue the fused input kernel plus ONE CUDA-graph launch of the network (captured on
+ * the second call for each distinct out_rgb pointer, 8 graphs cached per frame size): ping-pong a few output buffers.
+ * One stream at a time per net (it owns the activation buffers), like model:forward in the reference. */
 FAV_API int fav_run_image(fav_net_t *net, const float *content, const float *fill, int H, int W,
                           float *out_rgb, void *stream);
 /* a-8  run_next_image                           fast_artistic_video_core.lua:161-180
