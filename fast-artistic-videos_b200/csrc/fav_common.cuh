@@ -48,6 +48,20 @@ int require_device();  // FAV_ERR_NO_DEVICE when no GPU: there is no CPU fallbac
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+#ifdef __CUDACC__
+// The bilinear blend of BilinearSamplerBDHW.cu:103-106 exactly as nvcc (12.9, default -fmad=true, sm_100a) compiles the
+// reference kernel: the TR product is rounded, every other term is fused into the running sum (SASS: FMUL,FMUL,FMUL,FFMA,
+// FMUL,FMUL,FFMA,FFMA).  Pinned bit-for-bit against the reference's own kernel body compiled from /root/reference
+// (oracle/ref_warp/, tests/test_gpu_refwarp.py).  wx, wy = weights of the top-left corner, omx = 1 - wx, omy = 1 - wy.
+__device__ __forceinline__ float bilinear_ref_blend(float wx, float wy, float omx, float omy, float vtl, float vtr,
+                                                    float vbl, float vbr) {
+  float v = __fmul_rn(__fmul_rn(omx, wy), vtr);
+  v = __fmaf_rn(__fmul_rn(wx, wy), vtl, v);
+  v = __fmaf_rn(__fmul_rn(wx, omy), vbl, v);
+  return __fmaf_rn(__fmul_rn(omx, omy), vbr, v);
+}
+#endif
+
 // VGG mean, BGR order (fast_artistic_video/preprocess.lua:48)
 #define FAV_MEAN_B 103.939f
 #define FAV_MEAN_G 116.779f

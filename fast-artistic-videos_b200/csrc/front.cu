@@ -11,8 +11,9 @@
 // kernel maps lanes to x-stride-16 addresses and re-reads the flow once per channel).  The 4
 // bilinear taps are scalar read-only loads; for real optical flow neighbouring lanes gather
 // neighbouring addresses, so they coalesce in L1/L2 and each source sector is fetched from HBM once.
-// All arithmetic uses explicit round-to-nearest intrinsics in the reference's evaluation order (no
-// FMA contraction), which makes the output bit-identical to the CPU restatement.
+// All arithmetic uses explicit round-to-nearest intrinsics in the reference's evaluation order.  The bilinear
+// blend reproduces the FMA contraction nvcc applies to the reference kernel (bilinear_ref_blend, fav_common.cuh), so the
+// warp is bit-identical to the reference's own CUDA kernel compiled for sm_100a (oracle/ref_warp) and to the CPU oracle.
 #include "fav_common.cuh"
 #include "net_layout.cuh"
 
@@ -67,13 +68,9 @@ __device__ __forceinline__ float sample_plane(const Sample &s, const float *__re
   if (s.bl) vbl = __ldg(p + (int64_t)s.y1 * sy + (int64_t)s.x0 * sx);
   if (s.br) vbr = __ldg(p + (int64_t)s.y1 * sy + (int64_t)s.x1 * sx);
   if (border_mode == FAV_BORDER_PER_TAP) {
-    // BilinearSamplerBDHW.cu:103-106, left to right
+    // BilinearSamplerBDHW.cu:103-106 with the FMA contraction of the compiled reference kernel (fav_common.cuh)
     float omx = __fsub_rn(1.0f, s.wx), omy = __fsub_rn(1.0f, s.wy);
-    float v = __fmul_rn(__fmul_rn(s.wx, s.wy), vtl);
-    v = __fadd_rn(v, __fmul_rn(__fmul_rn(omx, s.wy), vtr));
-    v = __fadd_rn(v, __fmul_rn(__fmul_rn(s.wx, omy), vbl));
-    v = __fadd_rn(v, __fmul_rn(__fmul_rn(omx, omy), vbr));
-    return v;
+    return bilinear_ref_blend(s.wx, s.wy, omx, omy, vtl, vtr, vbl, vbr);
   } else {
     if (s.off) return 0.0f;
     float omx = __fsub_rn(1.0f, s.wx), omy = __fsub_rn(1.0f, s.wy);

@@ -48,6 +48,7 @@ struct BlendArgs {
   const float *base;      // [3,S,S]
   const float *div;       // [S,S] mask_all_div
   const float *mask;      // [S,S] blend mask (grad_mask_all)
+  const float *anti;      // [S,S] 1 - grad_mask_all as the reference casts it from double (:456), or null
   float *out;             // [3,S,S]
   int S;
 };
@@ -86,15 +87,12 @@ __global__ void __launch_bounds__(256) vr_blend_kernel(const __grid_constant__ B
       float vtr = (xin1 && yin0) ? rot_fetch(a.s[i].img, a.s[i].rot, c, y0, x0 + 1, S) : 0.f;
       float vbl = (xin0 && yin1) ? rot_fetch(a.s[i].img, a.s[i].rot, c, y0 + 1, x0, S) : 0.f;
       float vbr = (xin1 && yin1) ? rot_fetch(a.s[i].img, a.s[i].rot, c, y0 + 1, x0 + 1, S) : 0.f;
-      float v = __fmul_rn(__fmul_rn(wx, wy), vtl);
-      v = __fadd_rn(v, __fmul_rn(__fmul_rn(omx, wy), vtr));
-      v = __fadd_rn(v, __fmul_rn(__fmul_rn(wx, omy), vbl));
-      v = __fadd_rn(v, __fmul_rn(__fmul_rn(omx, omy), vbr));
+      float v = bilinear_ref_blend(wx, wy, omx, omy, vtl, vtr, vbl, vbr);
       float q = __fdiv_rn(v, dv);                      // torch.cdiv(side, divisor)   (combineSides :147-151)
       acc[c] = i == 0 ? q : __fadd_rn(acc[c], q);
     }
   }
-  const float am = __fsub_rn(1.0f, m);                 // anti_mask = 1 - grad_mask_all  (:456)
+  const float am = a.anti ? __ldg(a.anti + o) : __fsub_rn(1.0f, m);  // anti_mask = 1 - grad_mask_all  (:456)
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float b = __ldg(a.base + c * SS + o);
@@ -122,7 +120,7 @@ int fav_median_filter(const float *in, float *out, int C, int H, int W, int r, v
 }
 
 int fav_vr_blend_sides(const float *base, const float *const sides[4], const float *const maps[4], const int rot[4],
-                       const float *div, const float *mask, float *out, int S, void *stream) {
+                       const float *div, const float *mask, const float *anti_mask, float *out, int S, void *stream) {
   FAV_REQUIRE(base && sides && maps && rot && div && mask && out, "vr_blend_sides: null argument");
   FAV_REQUIRE(S > 1, "vr_blend_sides: empty face");
   BlendArgs a;
@@ -130,7 +128,7 @@ int fav_vr_blend_sides(const float *base, const float *const sides[4], const flo
     FAV_REQUIRE(sides[i] && maps[i] && rot[i] >= 0 && rot[i] <= 3, "vr_blend_sides: bad side %d", i);
     a.s[i].img = sides[i]; a.s[i].map = maps[i]; a.s[i].rot = rot[i];
   }
-  a.base = base; a.div = div; a.mask = mask; a.out = out; a.S = S;
+  a.base = base; a.div = div; a.mask = mask; a.anti = anti_mask; a.out = out; a.S = S;
   FAV_TRY(require_device());
   dim3 block(32, 8), grid(ceil_div(S, 32), ceil_div(S, 8));
   vr_blend_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a);

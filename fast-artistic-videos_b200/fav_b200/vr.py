@@ -6,7 +6,8 @@ Every warp goes through nn.BilinearSamplerBDHW's replacement (fav_bilinear_sampl
 re-blend is ONE fused kernel per face (fav_vr_blend_sides: 4 rotated gathers + combineSides + blend) instead of
 4 warps + 4 rotations + 10 elementwise passes; the median runs on the GPU.  Mask algebra that happens once per stream
 (init, :164-198) or on single-channel masks uses torch elementwise ops as plumbing.
--evaluate is out of scope (needs VGG-16 weights)."""
+-evaluate is out of scope (needs VGG-16 weights).  -invert_occlusions / -fix_occlusions are parsed and ignored, exactly as
+in the reference (its VR func_load_cert, :204-237, never reads them)."""
 from __future__ import annotations
 
 import argparse
@@ -99,6 +100,7 @@ class VRDriver:
         g["all"] = np.maximum(np.maximum(g["left"], g["right"]), np.maximum(g["top"], g["bottom"]))
         g["left_right"] = np.maximum(g["left"], g["right"])
         self.grad = {k: f32(v)[None] for k, v in g.items()}
+        self.anti_all = f32(1.0 - g["all"])  # csub(ones, grad_mask_all) in DOUBLE, then :type(dtype)  (:456)
         if opt.out_equi:
             r = opt.median_filter // 2
             self.equi_map = f32(vr_helper.make_cube_to_equirectangular_map(hplus - 2 * r, wplus - 2 * r, opt.overlap_pixel_w - r,
@@ -171,7 +173,12 @@ class VRDriver:
                 result = last_frame_warped * (1.0 - mask) + border * mask                  # :289-290
         else:
             result = border
-        if opt.smooth_certainty and gradMask is not None:  # :296-297
+        if opt.smooth_certainty and gradMask is None:
+            # :297 indexes gradMask, which is nil for face 6 (mode 0) and with -create_inconsistent_border: the reference
+            # raises a Lua error here, i.e. -smooth_certainty only works together with -create_inconsistent
+            raise _lib.FavError(_lib.FAV_ERR_INVALID, "-smooth_certainty: no gradient mask for this face (gradMask is nil, "
+                                "fast_artistic_video_vr.lua:245,297); use it with -create_inconsistent")
+        if opt.smooth_certainty:  # :296-297
             return result, torch.clamp(torch.sign(torch.clamp(gradMask - 0.5, min=0.0)), min=0.25)
         return result
 
@@ -194,7 +201,8 @@ class VRDriver:
             maps = (C.c_void_p * 4)(*[self.map[m].data_ptr() for _, m, _ in sides])
             rots = (C.c_int * 4)(*[_ROT[r] for _, _, r in sides])
             _lib.check(_lib.lib.fav_vr_blend_sides(_lib.dptr(ls[face]), imgs, maps, rots, _lib.dptr(self.mask_all_div),
-                                                   _lib.dptr(self.grad["all"]), _lib.dptr(o), S, _lib.stream_ptr()))
+                                                   _lib.dptr(self.grad["all"]), _lib.dptr(self.anti_all), _lib.dptr(o), S,
+                                                   _lib.stream_ptr()))
             out[face] = o
         return out
 
@@ -217,7 +225,9 @@ class VRDriver:
             res["equi"] = utils.warp_image(strip.contiguous(), self.equi_map)
             save_image("%s-%05d_equi.png" % (opt.output_prefix, file_idx), res["equi"])
         if opt.out_cubemap:
-            crop = lambda t: t[:, oh:t.shape[1] - oh, ow:t.shape[2] - ow]
+            # :548-553: {oversize+1, hplus-oversize} index the MEDIAN-FILTERED face (already 2*(r//2) smaller), so each
+            # face comes out (hplus - overlap + 2*(r//2)) wide -- the reference's own (asymmetric) crop, kept as is
+            crop = lambda t: t[:, oh:self.hplus - oh, ow:self.wplus - ow]
             res["cubemap"] = torch.cat([crop(sides[4]), crop(sides[1]), rotate90(crop(sides[5])), rotateMinus90(crop(sides[6])),
                                         crop(sides[3]), crop(sides[2])], 2)
             save_image("%s-%05d_cubemap.png" % (opt.output_prefix, file_idx), res["cubemap"])
@@ -232,6 +242,13 @@ def main(argv=None, model_vid=None):
         raise SystemExit("Must give -flow_pattern and -occlusions_pattern")
     opt.num_frames = opt.num_frames * 6  # :574
     opt.scale_factor = 1
+    if opt.continue_with > 1:
+        # :576-584 reloads prev_last_segments from "<prefix><n>_<mode>.png", files whose image.save is commented out in
+        # the reference itself (:524-526): the branch cannot work there either.
+        raise _lib.FavError(_lib.FAV_ERR_UNSUPPORTED, "-continue_with > 1: the reference reloads per-face PNGs it never "
+                            "writes (fast_artistic_video_vr.lua:524-526,576-584)")
+    if opt.overlap_pixel_w % 2 or opt.overlap_pixel_h % 2:
+        raise _lib.FavError(_lib.FAV_ERR_INVALID, "overlap_pixel_w/h must be even (the reference slices with overlap/2, :515-516)")
     d = VRDriver(opt)
     core.run_fast_neural_video(opt, d.func_load_image, d.func_load_cert, None, d.func_make_last_frame_warped,
                                d.func_is_single_image, d.func_save_image, model_vid=model_vid)

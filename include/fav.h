@@ -126,12 +126,14 @@ FAV_API int fav_compute_corners(const float *image, int Z, int W, int H, float r
  * fused 4-way border blend of one cube face         fast_artistic_video_vr.lua:146-152,454-509
  *   out = base*(1-mask) + mask * sum_i warp(rot_i(sides[i]), maps[i]) / div      (combineSides + blend)
  *   base, sides[i], out [3,S,S]; maps[i] [2,S,S] (dy,dx; sentinel 99999 outside the strip); div, mask [S,S];
+ *   anti_mask [S,S] or NULL: the reference forms 1 - grad_mask_all in DOUBLE and casts it to the tensor type (:456);
+ *   pass that tensor for bit parity, NULL = 1 - mask evaluated in fp32;
  *   rot[i]: 0 none, 1 rotate90, 2 rotateMinus90, 3 rotate180 (:134-144).
  * ------------------------------------------------------------------------------------------- */
 FAV_API int fav_median_filter(const float *in, float *out, int C, int H, int W, int r, void *stream);
 FAV_API int fav_vr_blend_sides(const float *base, const float *const sides[4], const float *const maps[4],
-                               const int rot[4], const float *div, const float *mask, float *out, int S,
-                               void *stream);
+                               const int rot[4], const float *div, const float *mask, const float *anti_mask,
+                               float *out, int S, void *stream);
 
 /* a-3 / a-13  Middlebury .flo (HOST side)          flowFileLoader.lua:17-37, consistencyChecker.cpp:16-36
  * layout 0: [dy,dx] (Lua loader order); layout 1: [u,v] (checker order). out: host [2,H,W]. */

@@ -13,7 +13,12 @@
  *     oracle/Makefile compiles unmodified into oracle/_ref/ (see
  *     tests/test_oracle_pinning.py and tests/golden/).
  *   - orc_warp_bdhw restates stnbdhw/BilinearSamplerBDHW.cu:13-32,58-108 line
- *     by line (the CUDA source cannot be built here: it needs THC/luaT headers).
+ *     by line, including the FMA contraction nvcc applies to :103-106.  Pinned: the
+ *     reference's kernel body, extracted from /root/reference at build time and
+ *     compiled for sm_100a by oracle/Makefile (oracle/_ref/libref_warp.so), is
+ *     bit-identical to the CUDA product on the GPU box (tests/test_gpu_refwarp.py),
+ *     and its outputs on seeded inputs are committed as tests/golden/warp_ref_*.npz,
+ *     which this restatement reproduces bit for bit (tests/test_oracle.py).
  *   - vgg pre/deprocess, min_filter, temporal-input assembly restate Lua code
  *     whose arithmetic lives in un-vendored, unpinned Torch7 rocks
  *     ("parity unpinned" at those third-party boundaries).
@@ -52,7 +57,7 @@ static inline int orc_between(int v, int lo, int hi) { return v >= lo && v <= hi
  * img   : B x C x Hin x Win, element strides is[4]
  * grid  : B x 2 x Hout x Wout (channel 0 = dy, 1 = dx; pixel offsets), gs[4]
  * out   : B x C x Hout x Wout, os[4]
- * Arithmetic order is that of BilinearSamplerBDHW.cu:72-108 (fp32, no FMA).
+ * Arithmetic order is that of BilinearSamplerBDHW.cu:72-108 (fp32; blend contracted as the compiled kernel).
  */
 ORC_API void orc_warp_bdhw(const float *img, const int64_t is[4], const float *grid,
                            const int64_t gs[4], float *out, const int64_t os[4], int B,
@@ -81,11 +86,14 @@ ORC_API void orc_warp_bdhw(const float *img, const int64_t is[4], const float *g
           if (tr) vtr = p[(int64_t)y0 * is[2] + (int64_t)(x0 + 1) * is[3]];       /* :99 */
           if (bl) vbl = p[(int64_t)(y0 + 1) * is[2] + (int64_t)x0 * is[3]];       /* :100 */
           if (br) vbr = p[(int64_t)(y0 + 1) * is[2] + (int64_t)(x0 + 1) * is[3]]; /* :101 */
-          /* :103-106, left-to-right fp32 */
-          float v = wx * wy * vtl;
-          v = v + (1 - wx) * wy * vtr;
-          v = v + wx * (1 - wy) * vbl;
-          v = v + (1 - wx) * (1 - wy) * vbr;
+          /* :103-106 as nvcc contracts it (12.9, default -fmad=true, sm_100a; SASS of the reference kernel body:
+           * FMUL,FMUL,FMUL,FFMA,FMUL,FMUL,FFMA,FFMA): the TR product is rounded, the other three terms are fused
+           * into the running sum.  Pinned against the compiled reference kernel (oracle/ref_warp, tests/golden/warp_ref_*). */
+          float omx = 1 - wx, omy = 1 - wy;
+          float v = (omx * wy) * vtr;
+          v = fmaf(wx * wy, vtl, v);
+          v = fmaf(wx * omy, vbl, v);
+          v = fmaf(omx * omy, vbr, v);
           out[b * os[0] + ch * os[1] + yOut * os[2] + xOut * os[3]] = v; /* :108 */
         }
       }
