@@ -48,6 +48,14 @@ NCU_RES_CONV_DRAM_BYTES = 40013056 + 1452288  # one residual conv launch, ncu --
 NCU_FRONT_DRAM_BYTES = 33188608 + 271872      # temporal_input_kernel @720p (profiles/r01_temporal_input_v6.ncu-rep)
 
 
+WORKLOAD = "1280x720 clip (BASELINE.json configs[1]), candy (seeded random-init weights), one step = one frame of run_next_image"
+
+
+def config_for(arch_key):
+    """Identical in both arms (the driver compares the two `config` dicts)."""
+    return {"workload": WORKLOAD, "arch": ARCHS[arch_key], "frame": [H, W], "model": "candy (synthetic weights)"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -167,8 +175,7 @@ def run_reference(args):
     line = {"metric": "stylized frames/sec at 1280x720", "impl": "reference", "value": r["value"], "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "1280x720 clip, candy (seeded random-init) model, run_next_image per frame",
-                       "arch": ARCHS[args.arch]},
+            "config": config_for(args.arch),
             "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -231,30 +238,50 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- (1) device-resident throughput --------------------------------------------------------------------
+    # Timed regions: each is EXACTLY K steps bracketed by barrier + synchronize; regions repeat until >= 1 s of device time
+    # has been measured (so that short driver runs still amortise pipeline fill and give the clock sampler samples) and the
+    # MEDIAN region is reported.
+    def n_regions(t_first):
+        return max(1, min(60, int(1.0 / max(t_first, 1e-4)) + 1))
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    tw0 = time.time()
+
+    # ---- (1) device-resident throughput: certainty precomputed, frame = fused temporal input + net ---------------------
     prev = net.run_image(frames[0])
     for i in range(Wm):
         j = (i + 1) % POOL
         prev = net.run_next_image(frames[j], prev, flows[j], certs[j])
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    l0 = _lib.lib.fav_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tw0 = time.time()
-    e0.record()
-    for i in range(K):
-        j = (i + 1 + Wm) % POOL
-        prev = net.run_next_image(frames[j], prev, flows[j], certs[j])
-    e1.record()
-    barrier()
-    tw1 = time.time()
-    launches = int(_lib.lib.fav_launch_count() - l0)
-    t_dev = max_over_ranks(e0.elapsed_time(e1) / 1e3)
-    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+
+    def region_dev(full):
+        nonlocal prev
+        barrier()
+        l0 = _lib.lib.fav_launch_count()
+        e0.record()
+        for i in range(K):
+            j = (i + 1 + Wm) % POOL
+            if full:  # the whole north-star path: occlusion test from the flow pair + 7x7 min filter + warp + net
+                _, c = consistencyChecker.check(bw[j], fw[j], want_cert=True)
+                c = utils.min_filter(c, 7)
+            else:
+                c = certs[j]
+            prev = net.run_next_image(frames[j], prev, flows[j], c)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / 1e3), int(_lib.lib.fav_launch_count() - l0)
+
+    t_first, launches = region_dev(False)
+    regions = n_regions(t_first)
+    t_list = sorted([t_first] + [region_dev(False)[0] for _ in range(regions - 1)])
+    t_dev = t_list[len(t_list) // 2]
     checksum = float(prev.double().sum().item())
     value = world * K / t_dev
+    tf_list = sorted(region_dev(True)[0] for _ in range(regions))
+    t_full = tf_list[len(tf_list) // 2]
+    value_full = world * K / t_full
 
     # ---- (2) end to end through the host-buffer API ------------------------------------------------------------
     sess = session.Session(net, H, W)
@@ -267,15 +294,22 @@ def run_ours(args):
         j = (i + 1) % POOL
         sess.run_next_image_flows(hf[j], hbw[j], hfw[j], hout[i & 1], 7)
     sess.sync()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        j = (i + 1 + Wm) % POOL
-        sess.run_next_image_flows(hf[j], hbw[j], hfw[j], hout[i & 1], 7)
-    t_enqueue = time.perf_counter() - t0  # host time to enqueue K frames (copies + launches are asynchronous)
-    sess.sync()
-    barrier()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
+
+    def region_e2e():
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            j = (i + 1 + Wm) % POOL
+            sess.run_next_image_flows(hf[j], hbw[j], hfw[j], hout[i & 1], 7)
+        t_enq = time.perf_counter() - t0  # host time to enqueue K frames (copies + launches are asynchronous)
+        sess.sync()
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0), t_enq
+
+    e_list = sorted(region_e2e() for _ in range(regions))
+    t_e2e, t_enqueue = e_list[len(e_list) // 2]
+    tw1 = time.time()
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     gpu_ms_last = sess.last_gpu_ms()
     e2e = world * K / t_e2e
     h2d = (3 + 2 + 2) * H * W * 4
@@ -309,6 +343,36 @@ def run_ours(args):
         torch.cuda.synchronize()
     front_ms = f0.elapsed_time(f1) / nf
     front_gbs = FRONT_BYTES_PER_PX * H * W / (front_ms * 1e-3) / 1e9
+    # standalone warp op (metric half 2: warp-kernel HBM GB/s, 32 B/px) and the kernel to beat: the reference's own CUDA
+    # kernel compiled for sm_100a (oracle/_ref/libref_warp.so, original 32x16 blocks), same inputs, real and stress flows
+    warp = {}
+    if rank == 0:
+        from oracle import refwarp
+
+        stress = torch.from_numpy(np.stack([synth.stress_flow(H, W, seed=7 + i) for i in range(POOL)])).to(dev)
+        wout = torch.empty((1, 3, H, W), device=dev)
+        imgs4, flows4, stress4 = frames[:, None], flows[:, None], stress[:, None]
+
+        def time_warp(fn, fl):
+            for rep in range(2):
+                f0.record()
+                for i in range(nf):
+                    fn(imgs4[i % POOL], fl[(i + 3) % POOL])
+                f1.record()
+                torch.cuda.synchronize()
+            return f0.elapsed_time(f1) / nf
+
+        ours = lambda im, fl: _lib.check(_lib.lib.fav_warp_image(_lib.dptr(im), 3, H, W, _lib.dptr(fl), H, W, _lib.dptr(wout), 0,
+                                                                 _lib.stream_ptr()))
+        have_ref = refwarp.available()
+        theirs = (lambda im, fl: refwarp.warp(im, fl, wout)) if have_ref else None
+        wbytes = 32 * H * W
+        for kind, fl in (("real", flows4), ("stress", stress4)):
+            ms_o = time_warp(ours, fl)
+            ms_r = time_warp(theirs, fl) if have_ref else None
+            warp[kind] = {"ms": ms_o, "gbs": wbytes / (ms_o * 1e-3) / 1e9,
+                          "original_kernel_ms": ms_r, "original_kernel_gbs": (wbytes / (ms_r * 1e-3) / 1e9) if ms_r else None,
+                          "vs_original_kernel": (ms_r / ms_o) if ms_r else None}
     conv_tfs = conv_flop / (conv_ms * 1e-3) / 1e12
     res = [p for p in prof if p["kind"] == "conv" and (".c1" in p["name"] or ".c2" in p["name"])]
     res_ms, res_flop, res_n = sum(p["ms"] for p in res), sum(p["work"] for p in res), len(res)
@@ -325,16 +389,18 @@ def run_ours(args):
         dist.all_gather(gathered, cs)  # "gather outputs": one checksum per clip
     if rank == 0:
         line = {
-            "metric": "stylized frames/sec at 1280x720", "value": value, "unit": "frames/s", "n_gpus": world,
+            "metric": "stylized frames/sec at 1280x720", "value": value, "value_full": value_full, "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16x2 (fp16 hi/lo operand pairs, 3 tcgen05 MMAs per product, fp32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": f"{W}x{H} clip, candy (seeded random-init weights), arch {arch}; "
-                                   "one step = one frame of run_next_image",
-                       "l2": f"inputs cycle through a pool of {POOL} distinct frames ({POOL * 29.5:.0f} MB > 126 MB L2); "
-                             "~1.5 GB of activations stream through L2 per frame",
-                       "parallelism": f"replicas x{world} (independent clips, no data-path collective)",
-                       "precision": "outputs within 1e-3 of the fp64 oracle (measured ~1e-5, tests/test_gpu_net.py)"},
+            "config": config_for(args.arch),
+            "notes": {"l2": f"inputs cycle through a pool of {POOL} distinct frames ({POOL * 29.5:.0f} MB > 126 MB L2); "
+                            "~1.5 GB of activations stream through L2 per frame",
+                      "parallelism": f"replicas x{world} (independent clips, no data-path collective)",
+                      "precision": "outputs within 1e-3 of the fp64 oracle (measured ~1e-5, tests/test_gpu_net.py, "
+                                   "tests/test_gpu_parity_large.py)",
+                      "timing": f"{regions} timed regions of exactly {K} steps each (barrier + synchronize on both sides, CUDA "
+                                "events, max over ranks); value / e2e = the MEDIAN region"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * t_e2e / K, "host_enqueue_ms_per_step": 1e3 * t_enqueue / K,
                     "gpu_ms_last_frame": gpu_ms_last,
@@ -363,8 +429,19 @@ def run_ours(args):
                                "traffic_source": "profiles/r01_temporal_input_v6.ncu-rep (33.2 MB read = exactly the input planes; "
                                                  "the 25.8 MB written stay in the 126 MB L2)",
                                "bytes_per_launch": FRONT_BYTES_PER_PX * H * W, "ms": front_ms},
+            "roofline_warp": None if not warp else {
+                "bound": "hbm", "kernel": "warp_vec4_kernel<3> via fav_warp_image (nn.BilinearSamplerBDHW forward, 3x720x1280)",
+                "achieved": warp["real"]["gbs"], "peak": pk["hbm"], "unit": "GB/s", "frac": warp["real"]["gbs"] / pk["hbm"],
+                "bytes_per_launch": 32 * H * W, "traffic": None,
+                "vs_original_kernel": warp["real"]["vs_original_kernel"],
+                "real_flow": warp["real"], "stress_flow_u64px": warp["stress"],
+                "original_kernel": "stnbdhw/BilinearSamplerBDHW.cu:48-109 compiled for sm_100a from /root/reference "
+                                   "(oracle/Makefile refwarp), launch config of :119-120"},
+            "value_full_note": "value_full = device-resident frames/s with the occlusion test (flow pair) and the 7x7 min filter "
+                               "inside the timed region as well (the whole north-star path; `value` takes precomputed certainty)",
             "breakdown_ms_per_frame": {"conv": conv_ms, "in_stats": stats_ms, "in_apply": apply_ms, "pack_input": pack_ms,
-                                       "temporal_input": front_ms, "total_device": 1e3 * t_dev / K},
+                                       "temporal_input": front_ms, "total_device": 1e3 * t_dev / K,
+                                       "total_device_full_path": 1e3 * t_full / K},
             "layers": [{"name": p["name"], "kind": p["kind"], "ms": round(p["ms"], 4),
                         **({"tflops": round(p["work"] / (p["ms"] * 1e-3) / 1e12, 1)} if p["kind"] == "conv" else
                            {"gbs": round(p["work"] / (p["ms"] * 1e-3) / 1e9, 1)})} for p in prof],

@@ -10,6 +10,8 @@ constexpr int kMaxRfRows = 24;  // row-fold: R + KH - 1 patch rows per unit
 constexpr int kMaxRows = 10;
 constexpr int kMaxGroups = 12;
 constexpr int kTileM = 128;  // output pixels per MMA tile = TMEM lanes
+constexpr int kTraceWords = 64;   // u64 words per CTA in the optional timeline buffer
+constexpr int kTraceUnits = 6;    // units (tiles) per CTA recorded
 
 // One K=16 step of the implicit GEMM: two K8 "units" (a unit = 8 input channels of one filter tap).
 // a_off16: offset (16-byte units) of the first unit's pixel 0 inside the shared-memory patch stage;
@@ -81,6 +83,8 @@ struct ConvJob {
   const float4 *nl_raw; int nl_Cq, nl_Wp, nl_H, nl_W, nl_padT, nl_padL, nl_relu, nl_C;
   const double *nl_sums; const float *nl_gamma, *nl_beta; double nl_inv_count, nl_eps;
   TmaMap tm_hi, tm_lo;  // tma: 4-D tiled maps of the operand planes [Hs][Cb][slab][8 x fp16], box = [nrows][CbG][pslab16][8]
+  // per-CTA timeline (diagnostics, fav_debug_set_trace): kTraceWords u64 per CTA, null = off.  Layout in conv_tc.cu.
+  unsigned long long *trace;
   // timing ablations (env FAV_DBG, diagnostics only; results are wrong when non-zero): 1 = no epilogue stores/stats,
   // 2 = 16-byte weight copies, 4 = 16-byte patch copies, 8 = epilogue skips the TMEM loads too
   int dbg;
@@ -117,6 +121,8 @@ struct SimtJob {
 int launch_conv_tc(const ConvJob &job, int num_sms, cudaStream_t st);
 int launch_conv_simt(const SimtJob &job, cudaStream_t st);
 size_t conv_tc_smem_bytes(const ConvJob &job);
+void conv_tc_set_trace(unsigned long long *buf, size_t words);  // diagnostics (fav_debug_set_trace)
+size_t conv_tc_trace_used();
 void conv_tc_choose_slots(ConvJob &job);  // fills b_slots / b_resident from the shared-memory budget
 
 // elementwise / reduction kernels of the net (net_kernels.cu)

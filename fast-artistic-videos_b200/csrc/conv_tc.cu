@@ -186,6 +186,16 @@ __device__ __forceinline__ float tc_final_value(float v, int k, int mode, float 
   return t;
 }
 
+// ---- optional per-CTA timeline (job.trace != null; tools/trace_conv.py) ------------------------------------------------
+// word 0: globaltimer at entry (ns), 1: clock64 at entry, 2: clock64 after setup (barriers, TMEM), 3: clock64 at exit,
+// 4: units of this CTA; then per unit u < kTraceUnits at 8 + 8u: +0 MMA warp 6: accumulator stage free (unit start),
+// +1 first patch stage landed, +2 all MMAs issued, +3 cycles spent waiting for patch stages, +4 ... for weight chunks,
+// +5 epilogue warp 0: accumulator complete, +6 epilogue of the unit done.  clock64 values are per-SM cycle counters.
+__device__ __forceinline__ void trace_put(const ConvJob &job, int word, long long v) {
+  if (job.trace) job.trace[(size_t)blockIdx.x * kTraceWords + word] = (unsigned long long)v;
+}
+__device__ __forceinline__ long long trace_clock(const ConvJob &job) { return job.trace ? clock64() : 0; }
+
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvJob job) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t a_stage_bytes = (uint32_t)job.stage16 * 16u;  // one of hi / lo
@@ -197,6 +207,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   TcShared *sh = reinterpret_cast<TcShared *>(b_base + nslots * chunk_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (job.trace && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    trace_put(job, 0, (long long)gt);
+    trace_put(job, 1, clock64());
+  }
 
   // Two-row units (mt = 2) are issued by TWO warps, one accumulator row each: a single warp sustains only ~1 UTCHMMA per
   // 80-100 cycles on this loop (tools/mma_bench3.cu), two warps reach the 64-cycle tensor-pipe floor.
@@ -233,6 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
+  if (threadIdx.x == 0) trace_put(job, 2, trace_clock(job));
 
   const int ngroups = job.ngroups, nchunks = job.nchunks, spc = job.spc, Npad = job.Npad;
 
@@ -451,6 +468,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t as = tl & 1, tph = (tl >> 1) & 1;
       mbar_wait(&sh->t_empty[as], tph ^ 1);
       tc_fence_after();
+      const bool tr = job.trace && warp == 6 && lane == 0 && tl < (uint32_t)kTraceUnits;
+      long long tr_a = 0, tr_b = 0;
+      if (tr) trace_put(job, 8 + 8 * (int)tl, clock64());
       const uint32_t d0 = tmem_base + as * 256u + drow * 128u, d1 = d0 + 128u;
       if (job.rf_R) {
         // ===== row-fold issue loop (conv.cuh): patch row iy feeds output rows r_min..r_max in ONE MMA per K step =====
@@ -548,15 +568,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       uint32_t accumulate = 0, sc = 0;  // sc: K-step counter of the unit (K-split parity)
       const bool dbg_nowait = job.dbg & 16, dbg_one = job.dbg & 32;
       for (int g = 0; g < ngroups; ++g) {
+        long long tw = tr ? clock64() : 0;
         if (!dbg_nowait) mbar_wait(&sh->a_full[sa], aph);
         tc_fence_after();
+        if (tr) { const long long now = clock64(); tr_a += now - tw; if (g == 0) trace_put(job, 8 + 8 * (int)tl + 1, now); }
         const uint32_t a_hi16 = (smem_u32(a_base + sa * 2 * a_stage_bytes) >> 4) + (dual_rows ? drow * a_tile16 : 0u), a_lo16 = a_hi16 + a_stage16;
         int sidx = 0;
         for (int c = 0; c < nchunks; ++c) {
           // ring: slot sb, phase bph.  resident: slot = chunk index, filled once (parity 0 stays satisfied afterwards)
           if ((!job.b_resident || tl == 0) && !dbg_nowait) {  // resident weights are complete after the first tile
+            const long long tw2 = tr ? clock64() : 0;
             mbar_wait(&sh->b_full[sb], job.b_resident ? 0u : bph);
             tc_fence_after();
+            if (tr) tr_b += clock64() - tw2;
           }
           const uint32_t bh = (smem_u32(b_base + sb * chunk_bytes) >> 4) | ((uint32_t)Npad << 16);  // LBO = Npad * 16 B
           if (Npad >= 128) {
@@ -619,6 +643,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (++sa == nstages) { sa = 0; aph ^= 1; }
       }
       if (leader) tc_commit(&sh->t_full[as]);  // accumulator complete -> epilogue
+      if (tr) { trace_put(job, 8 + 8 * (int)tl + 2, clock64()); trace_put(job, 8 + 8 * (int)tl + 3, tr_a); trace_put(job, 8 + 8 * (int)tl + 4, tr_b); }
     }
     __syncwarp();
   } else if (warp < 4 || (warp >= 8 && warp < 12 && job.nl != 1)) {
@@ -639,6 +664,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t as = tl & 1, tph = (tl >> 1) & 1;
       mbar_wait(&sh->t_full[as], tph);
       tc_fence_after();
+      const bool etr = job.trace && threadIdx.x == 0 && tl < (uint32_t)kTraceUnits;
+      if (etr) trace_put(job, 8 + 8 * (int)tl + 5, clock64());
       if (job.dbg & 8) { tc_fence_before(); mbar_arrive(&sh->t_empty[as]); continue; }
       if (job.pf) {
         // 4 phase blocks of pf_cout columns: block k -> output pixel (2y + a, 2x + b), (a,b) = (0,0),(0,1),(1,1),(1,0).
@@ -787,6 +814,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         tc_fence_before();
         mbar_arrive(&sh->t_empty[as]);
       }
+      if (etr) trace_put(job, 8 + 8 * (int)tl + 6, clock64());
     }
     if (job.stats) {
       // 4 warps -> shared memory in per-warp slots, summed in a FIXED order (deterministic per CTA: the tile ->
@@ -814,6 +842,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    trace_put(job, 3, trace_clock(job));
+    int nu = 0;
+    for (int tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) ++nu;
+    trace_put(job, 4, nu);
+  }
   if (warp == 6) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
@@ -852,17 +886,33 @@ void conv_tc_choose_slots(ConvJob &job) {
   }
 }
 
-int launch_conv_tc(const ConvJob &job, int num_sms, cudaStream_t st) {
+// diagnostics: device buffer receiving the timeline of the next launches (kTraceWords u64 per CTA, launches appended)
+static unsigned long long *g_trace_buf = nullptr;
+static size_t g_trace_cap = 0, g_trace_used = 0;
+void conv_tc_set_trace(unsigned long long *buf, size_t words) { g_trace_buf = buf; g_trace_cap = words; g_trace_used = 0; }
+size_t conv_tc_trace_used() { return g_trace_used; }
+
+int launch_conv_tc(const ConvJob &job_in, int num_sms, cudaStream_t st) {
+  ConvJob job = job_in;
+  job.trace = nullptr;
+  {
+    const size_t need = (size_t)(job.ntiles < num_sms ? job.ntiles : num_sms) * kTraceWords;
+    if (g_trace_buf && g_trace_used + need <= g_trace_cap) { job.trace = g_trace_buf + g_trace_used; g_trace_used += need; }
+  }
   size_t smem = conv_tc_smem_bytes(job);
   if (smem > 227 * 1024) {
     set_error("conv_tc: shared memory %zu exceeds 227 KB", smem);
     return FAV_ERR_UNSUPPORTED;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in to > 48 KB of dynamic shared memory is a PER-DEVICE function attribute
+  static std::atomic<uint64_t> attr_set{0};
+  int dev = 0;
+  FAV_TRY(check_cuda(cudaGetDevice(&dev), "cudaGetDevice"));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(attr_set.load(std::memory_order_acquire) & bit)) {
     FAV_TRY(check_cuda(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
                        "cudaFuncSetAttribute(conv_tc)"));
-    attr_set = true;
+    attr_set.fetch_or(bit, std::memory_order_release);
   }
   int grid = job.ntiles < num_sms ? job.ntiles : num_sms;
   conv_tc_kernel<<<grid, kThreads, smem, st>>>(job);
@@ -870,3 +920,13 @@ int launch_conv_tc(const ConvJob &job, int num_sms, cudaStream_t st) {
 }
 
 }  // namespace fav
+
+extern "C" {
+// diagnostics: timeline of the following conv_tc launches into a caller-owned device buffer (bytes / 8 u64 words);
+// NULL switches it off.  Used by tools/trace_conv.py through fav_net_forward (graph launches keep the pointer they captured).
+int fav_debug_set_trace(void *dev_buf, size_t bytes) {
+  fav::conv_tc_set_trace(reinterpret_cast<unsigned long long *>(dev_buf), dev_buf ? bytes / 8 : 0);
+  return FAV_OK;
+}
+size_t fav_debug_trace_words(void) { return fav::conv_tc_trace_used(); }
+}

@@ -177,6 +177,11 @@ FAV_API int fav_net_profile(fav_net_t *net, const float *in7, int H, int W, floa
 FAV_API int fav_net_layer_output(fav_net_t *net, int index, float *out, int *C, int *Hl, int *Wl,
                                  void *stream);
 
+/* diagnostics (tools/trace_conv.py): per-CTA timeline of the following tcgen05 convolution launches (clock64 marks of
+ * the MMA / epilogue warps, 64 u64 words per CTA, launches appended) into a caller-owned DEVICE buffer; NULL = off. */
+FAV_API int fav_debug_set_trace(void *dev_buf, size_t bytes);
+FAV_API size_t fav_debug_trace_words(void);
+
 /* a-9  run_image (frame 1, model_img == nil)    fast_artistic_video_core.lua:121-158
  * content [3,H,W] RGB [0,1] -> out_rgb [3,H,W] = deprocess(model_vid(...))[1].
  * fav_run_image / fav_run_next_image enqueue the fused input kernel plus ONE CUDA-graph launch of the network (captured on
