@@ -23,8 +23,6 @@ struct KStep {
 };
 
 // tcgen05 implicit-GEMM job (one convolution, or one sub-pixel phase of a transposed convolution)
-struct alignas(64) TmaMap { unsigned char bytes[128]; };  // a CUtensorMap (driver API), kept opaque here
-
 struct ConvJob {
   // input operand (hi/lo fp16 planes), addressed in 16-byte units
   const uint4 *a_hi, *a_lo;
@@ -76,13 +74,9 @@ struct ConvJob {
       rf_off_new[kMaxRfRows];
   // norm-on-load: the input is the RAW output of the previous convolution; InstanceNorm (+ReLU) and the fp16 hi/lo split
   // happen in the producer warps while the patch is staged (replaces a separate in_apply pass + operand round trip)
-  int ucopy;           // experimental (FAV_UCOPY=1): one elected lane issues the patch copies with warp-uniform operands
-  int tma;             // experimental (FAV_TMA=1): ONE cp.async.bulk.tensor per plane and stage instead of a bulk copy per (row, block)
-  int aprod;           // experimental (FAV_APROD=4): warps 4, 12, 13, 14 share the patch copies of a stage (0/1: warp 4 alone)
   int nl;
   const float4 *nl_raw; int nl_Cq, nl_Wp, nl_H, nl_W, nl_padT, nl_padL, nl_relu, nl_C;
   const double *nl_sums; const float *nl_gamma, *nl_beta; double nl_inv_count, nl_eps;
-  TmaMap tm_hi, tm_lo;  // tma: 4-D tiled maps of the operand planes [Hs][Cb][slab][8 x fp16], box = [nrows][CbG][pslab16][8]
   // per-CTA timeline (diagnostics, fav_debug_set_trace): kTraceWords u64 per CTA, null = off.  Layout in conv_tc.cu.
   unsigned long long *trace;
   // timing ablations (env FAV_DBG, diagnostics only; results are wrong when non-zero): 1 = no epilogue stores/stats,

@@ -470,8 +470,6 @@ static inline int fill_conv_job(const ConvDef &c, const ConvPhase &ph, const Ope
     j.chunk16 = j.pf_len16[0];  // slot size = largest chunk (tap (0,0): all four phases)
     j.oy_mul = j.ox_mul = 2; j.oy_off = j.ox_off = 0;
   }
-  j.ucopy = getenv("FAV_UCOPY") ? 1 : 0;  // experimental patch-copy issue loop (conv_tc.cu), off by default
-  j.aprod = getenv("FAV_APROD") ? 4 : 1;  // experimental: four warps share the patch copies (conv_tc.cu), off by default
   // K-split between the two issuing warps (conv_tc.cu): one-row units whose accumulator needs <= 128 columns
   {
     const int cols = ph.rf_R ? ph.rf_R * ph.Npad : ph.Npad;

@@ -87,14 +87,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// 4-D tiled tensor copy (TMA): coordinates innermost first = (channel-in-block, pixel, channel block, row)
-__device__ __forceinline__ void tma_load4(void *dst, const TmaMap *map, int c0, int c1, int c2, int c3, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
-      : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -222,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const bool dual = dual_rows || ksplit;
   const uint32_t nissue = dual ? 2u : 1u;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], job.nl == 1 ? kNlWarps : (job.nl == 2 ? 4 : (job.aprod == 4 ? 4 : 1))); mbar_init(&sh->a_empty[i], nissue); }
+    for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], job.nl == 1 ? kNlWarps : (job.nl == 2 ? 4 : 1)); mbar_init(&sh->a_empty[i], nissue); }
     for (int i = 0; i < kMaxB; ++i) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], nissue); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], nissue); mbar_init(&sh->t_empty[i], job.nl == 1 ? 128 : 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -326,15 +318,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (++s == nstages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 4 || (job.aprod == 4 && !job.nl && warp >= 12 && warp <= 14)) {
-    // ===== A producer: the input patch of each (tile, channel group) =====
-    // (experimental FAV_APROD=4: warps 4, 12, 13, 14 each issue a quarter of the copies of a stage -- the bulk-copy
-    // instruction itself costs ~88 issue cycles)
-    const int npw = job.aprod == 4 ? 4 : 1, pw = warp == 4 ? 0 : warp - 11;
+  } else if (warp == 4) {
+    // ===== A producer: the input patch of each (tile, channel group): one bulk copy per (patch row, channel block, hi/lo),
+    // spread over the 32 lanes.  (Measured alternatives, all slower on B200 and removed: four producer warps sharing the
+    // copies, a single elected lane with warp-uniform operands, one 4-D cp.async.bulk.tensor per plane -- DESIGN.md 9.3.) =====
     const int per_row = job.CbG * job.nseg * 2;  // copies per patch row (x2: hi, lo)
     const int ncopies = job.nrows * per_row;
-    uint32_t ucopy_leader;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ucopy_leader));
     uint32_t stage_tx = 0;
     for (int s = 0; s < job.nseg; ++s) stage_tx += (job.dbg & 4) ? 16u : (uint32_t)job.seg_len16[s] * 16u;
     stage_tx *= (uint32_t)(job.nrows * job.CbG * 2);
@@ -344,55 +333,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int y = yu * job.mt;
       for (int g = 0; g < ngroups; ++g) {
         mbar_wait(&sh->a_empty[s], ph ^ 1);
-        if (npw == 1) {
-          if (lane == 0) mbar_arrive_expect_tx(&sh->a_full[s], stage_tx);
-        } else {  // this warp's share of the stage's bytes: copies pw*32 + lane + 128*k
-          uint32_t my = 0;
-          for (int c = pw * 32 + lane; c < ncopies; c += 32 * npw) {
-            const int r = c % per_row, seg = (r % (job.nseg * 2)) >> 1;
-            my += (job.dbg & 4) ? 16u : (uint32_t)job.seg_len16[seg] * 16u;
-          }
-          my = __reduce_add_sync(0xffffffffu, my);
-          if (lane == 0) mbar_arrive_expect_tx(&sh->a_full[s], my);
-        }
+        if (lane == 0) mbar_arrive_expect_tx(&sh->a_full[s], stage_tx);
         __syncwarp();
         uint8_t *stage = a_base + s * 2 * a_stage_bytes;
-        if (job.tma && npw == 1) {
-          // Experimental: the whole stage = one 4-D box per plane; out-of-range parts of the
-          // box are zero-filled by the TMA unit and still count towards the transaction bytes.
-          if (lane == 0) {
-            const int row = job.row_mul * y + job.grp_row[g][0], px = job.seg_src16[0] + x0;
-            tma_load4(stage, &job.tm_hi, 0, px, job.grp_cb0[g], row, &sh->a_full[s]);
-            tma_load4(stage + a_stage_bytes, &job.tm_lo, 0, px, job.grp_cb0[g], row, &sh->a_full[s]);
-          }
-          __syncwarp();
-          if (++s == nstages) { s = 0; ph ^= 1; }
-          continue;
-        }
-        if (job.ucopy && npw == 1) {
-          // Experimental: with per-lane copy parameters ptxas serialises the 32 lanes through
-          // an ELECT/R2UR/BRA.U.ANY waterfall (~88 cycles per copy, measured).  Here ONE elected lane walks the copies of
-          // the stage; every operand is warp-uniform, so the UBLKCPs issue from uniform registers without a waterfall.
-          if (ucopy_leader) {
-            for (int ri = 0; ri < job.nrows; ++ri)
-              for (int cbi = 0; cbi < job.CbG; ++cbi) {
-                const int64_t row16 = ((int64_t)(job.row_mul * y + job.grp_row[g][ri]) * job.a_Cb + job.grp_cb0[g] + cbi) *
-                                          job.a_slab16 + x0;
-                uint8_t *drow = stage + (uint32_t)((ri * job.CbG + cbi) * job.pslab16) * 16u;
-                for (int seg = 0; seg < job.nseg; ++seg) {
-                  const uint32_t bytes = (job.dbg & 4) ? 16u : (uint32_t)job.seg_len16[seg] * 16u;
-                  const int64_t s16 = row16 + job.seg_src16[seg];
-                  uint8_t *d = drow + (uint32_t)job.seg_dst16[seg] * 16u;
-                  bulk_g2s(d, job.a_hi + s16, bytes, &sh->a_full[s]);
-                  bulk_g2s(d + a_stage_bytes, job.a_lo + s16, bytes, &sh->a_full[s]);
-                }
-              }
-          }
-          __syncwarp();
-          if (++s == nstages) { s = 0; ph ^= 1; }
-          continue;
-        }
-        for (int c = pw * 32 + lane; c < ncopies; c += 32 * npw) {
+        for (int c = lane; c < ncopies; c += 32) {
           int ri = c / per_row, r = c - ri * per_row;
           int cbi = r / (job.nseg * 2);
           r -= cbi * job.nseg * 2;

@@ -12,7 +12,6 @@
 #include <cmath>
 #include <cstring>
 
-#include <cuda.h>  // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link dependency)
 #include "conv_plan.hpp"
 
 namespace fav {
@@ -204,42 +203,6 @@ static int make_operand(Plan &pl, int C, int H, int W, const ConvDef *consumer, 
   return FAV_OK;
 }
 
-// Experimental (FAV_TMA=1): tensor maps of the operand planes for the tcgen05 kernel's patch producer.  Falls back to the
-// bulk-copy producer (j.tma stays 0) whenever the stage is not one dense, 128-byte aligned 4-D box.
-static void try_make_tma(ConvJob &j, const Operand &in) {
-  static_assert(sizeof(CUtensorMap) == sizeof(TmaMap), "CUtensorMap size");
-  j.tma = 0;
-  if (!getenv("FAV_TMA") || j.nl || j.nseg != 1 || j.seg_dst16[0] != 0 || j.seg_len16[0] != j.pslab16 || in.parity) return;
-  if ((j.stage16 % 8) != 0 || j.pslab16 > 256 || j.CbG > 256 || j.nrows > 256) return;
-  for (int g = 0; g < j.ngroups; ++g)
-    for (int ri = 1; ri < j.nrows; ++ri)
-      if (j.grp_row[g][ri] != j.grp_row[g][0] + ri) return;  // the rows of a stage must be consecutive
-  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
-  if (!encode) {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) { cudaGetLastError(); return; }
-    encode = reinterpret_cast<EncodeFn>(fn);
-  }
-  const cuuint64_t slab = (cuuint64_t)in.slab16();
-  const cuuint64_t gdim[4] = {8, slab, (cuuint64_t)in.Cb, (cuuint64_t)in.Hs};
-  const cuuint64_t gstr[3] = {16, slab * 16, slab * 16 * (cuuint64_t)in.Cb};  // bytes, dims 1..3
-  const cuuint32_t box[4] = {8, (cuuint32_t)j.pslab16, (cuuint32_t)j.CbG, (cuuint32_t)j.nrows};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUtensorMap hi, lo;
-  if (encode(&hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, in.hi, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
-      encode(&lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, in.lo, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return;
-  memcpy(&j.tm_hi, &hi, sizeof(hi));
-  memcpy(&j.tm_lo, &lo, sizeof(lo));
-  j.tma = 1;
-}
-
 static int build_conv_jobs(fav_net *net, Plan &pl, PlanStep &st, const ConvDef &c, bool last, float *out3) {
   const Operand &in = pl.ops[st.src];
   bool fold_done = false;
@@ -254,7 +217,6 @@ static int build_conv_jobs(fav_net *net, Plan &pl, PlanStep &st, const ConvDef &
         j.raw = st.raw.p; j.raw_Cq = st.raw.Cq; j.raw_Wp = st.raw.Wp;
         j.final_mode = 0; j.out3 = out3; j.tanh_c = net->tanh_c;
         conv_tc_choose_slots(j);
-        try_make_tma(j, in);
         if (const char *e = getenv("FAV_DBG")) j.dbg = atoi(e);
         if (conv_tc_smem_bytes(j) > 227 * 1024) { set_error("conv %s: shared memory budget exceeded (fold)", c.name.c_str()); return FAV_ERR_UNSUPPORTED; }
         st.tc.push_back(j);
@@ -266,7 +228,6 @@ static int build_conv_jobs(fav_net *net, Plan &pl, PlanStep &st, const ConvDef &
     j.raw = st.raw.p; j.raw_Cq = st.raw.Cq; j.raw_Wp = st.raw.Wp;
     j.final_mode = last ? 1 : 0; j.out3 = out3; j.tanh_c = net->tanh_c;
     conv_tc_choose_slots(j);
-    try_make_tma(j, in);
     if (const char *e = getenv("FAV_DBG")) j.dbg = atoi(e);
     if (conv_tc_smem_bytes(j) > 227 * 1024) {
       set_error("conv %s: shared memory budget exceeded", c.name.c_str());
@@ -376,7 +337,7 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
           ok = !j.rf_R && !j.pf && !j.xfold_kw && j.nseg == 1 && j.seg_dst16[0] == 0 && j.seg_len16[0] == j.pslab16 && j.row_mul == 1;
           if (ok) {
             ConvJob t = j;
-            t.nl = 1; t.tma = 0;
+            t.nl = 1;
             if (const char *e = getenv("FAV_NL_MODE")) t.nl = atoi(e) == 2 ? 2 : 1;
             t.nl_raw = reinterpret_cast<const float4 *>(ap.raw.p); t.nl_Cq = ap.raw.Cq; t.nl_Wp = ap.raw.Wp;
             t.nl_H = ap.raw.H; t.nl_W = ap.raw.W; t.nl_padT = in.padT; t.nl_padL = in.padL; t.nl_relu = ap.relu; t.nl_C = n.C;

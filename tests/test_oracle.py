@@ -52,6 +52,18 @@ def test_consistency_oracle_equals_reference_binary_live(tmp_path):
     assert np.array_equal(pyoracle.consistency(bw, fw, img), synth.read_pgm(d + "/r4.pgm"))
 
 
+def test_warp_oracle_reproduces_reference_kernel_vectors():
+    """tests/golden/warp_ref.npz = outputs of the REFERENCE's own CUDA kernel (stnbdhw/BilinearSamplerBDHW.cu:48-109 compiled
+    for sm_100a, oracle/ref_warp) on a B200, written by tests/golden/make_warp_golden.py: the C restatement (including the
+    FMA contraction of :103-106) must reproduce them bit for bit -- this pins orc_warp_bdhw with the reference itself."""
+    import make_warp_golden
+
+    gold = np.load(os.path.join(GOLD, "warp_ref.npz"))
+    for case in make_warp_golden.WARP_CASES:
+        img, flow = make_warp_golden.warp_inputs(case)
+        assert np.array_equal(pyoracle.warp_bdhw(img, flow), gold[case[0]]), case[0]
+
+
 def _grid_sample_warp(img, flow):
     C, H, W = img.shape
     y, x = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
