@@ -1,5 +1,6 @@
 // common.cu -- error state, launch counter, device probing.
 #include "fav_common.cuh"
+#include <stdlib.h>
 
 namespace fav {
 static thread_local char g_err[512] = "";
@@ -10,6 +11,11 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("FAV_NO_PDL") == nullptr;
+  return on;
 }
 
 int require_device() {

@@ -106,6 +106,7 @@ struct SimtJob {
   int Ho, Wo;
   float *raw;
   int raw_Cq, raw_Wp;
+  int raw_planar, raw_Hp;  // planar raw output [C][Hp][Wp] (steps whose tcgen05 path is conv_res.cu)
   int oy_mul, oy_off, ox_mul, ox_off;
   int final_mode;
   float *out3;
@@ -116,6 +117,7 @@ int launch_conv_tc(const ConvJob &job, int num_sms, cudaStream_t st);
 int launch_conv_simt(const SimtJob &job, cudaStream_t st);
 size_t conv_tc_smem_bytes(const ConvJob &job);
 void conv_tc_set_trace(unsigned long long *buf, size_t words);  // diagnostics (fav_debug_set_trace)
+unsigned long long *conv_trace_claim(size_t words);             // next `words` u64 of the timeline buffer, or null
 size_t conv_tc_trace_used();
 void conv_tc_choose_slots(ConvJob &job);  // fills b_slots / b_resident from the shared-memory budget
 

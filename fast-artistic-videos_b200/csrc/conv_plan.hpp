@@ -106,6 +106,8 @@ static inline int build_phase_tables(const ConvDef &c, ConvPhase &ph) {
       return FAV_ERR_UNSUPPORTED;
     }
     ph.kind = 0; ph.CbG = (c.Cb % 4 == 0) ? 4 : 2;
+    // 3x3 stride-1 layers with 128 output channels run on conv_res.cu, whose stages hold two channel blocks
+    if (c.k == 3 && c.stride == 1 && c.cout == 128 && !c.transposed) ph.CbG = 2;
     if (const char *e = getenv("FAV_CBG")) { int v = atoi(e); if (v == 2 || v == 4) ph.CbG = v; }  // tuning knob
     ph.nchg = c.Cb / ph.CbG;
     ph.nseg = 1; ph.pslab16 = kTileM + (ph.dxmax - ph.dxmin); ph.seg_len16[0] = ph.pslab16; ph.seg_dst16[0] = 0;

@@ -30,6 +30,7 @@
 // Pipelines: A stages and weight slots (ring, or resident for small layers) with full/empty mbarriers; TMEM accumulator
 // double-buffered so the epilogue of unit i overlaps the MMAs of unit i+1.
 #include "conv.cuh"
+#include "tc_common.cuh"
 
 namespace fav {
 
@@ -50,86 +51,6 @@ struct __align__(16) TcShared {
   uint32_t pad_;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t done = 0;
-  const uint32_t addr = smem_u32(bar);
-  long long t0 = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (!done && (spin & 255u) == 255u) {
-      long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) __trap();  // ~2 s at 2 GHz
-    }
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major, no swizzle: canonical layout ((8,m),(8 elems,2)) : ((16 B, SBO), (2 B, LBO))   [cute/atom/mma_traits_sm100.hpp]
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo16, uint32_t sbo16) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16) |
-         ((uint64_t)(sbo16 & 0x3FFF) << 32) | (1ull << 46) /* descriptor version: Blackwell */;
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// two 16-column loads in flight, one wait (single asm statement: no use of the registers can be scheduled before the wait)
-__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, uint32_t (&r)[16], uint32_t (&q)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(q[0]), "=r"(q[1]),
-        "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]), "=r"(q[9]), "=r"(q[10]),
-        "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
-      : "r"(ta), "r"(tb)
-      : "memory");
-}
 // accumulator columns [taddr, taddr+16) as floats; K-split jobs add the second issuing warp's partial sums (+128 columns)
 __device__ __forceinline__ void tmem_ld16_acc(uint32_t taddr, bool ksplit, float (&v)[16]) {
   uint32_t r[16];
@@ -199,6 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   TcShared *sh = reinterpret_cast<TcShared *>(b_base + nslots * chunk_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();  // PDL (fav_common.cuh): the next kernel's prologue may overlap this kernel's tail
   if (job.trace && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -229,6 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   // as in_apply_kernel: biased variance, eps inside the sqrt, InstanceNormalization.lua:39-50)
   float *nl_tab = reinterpret_cast<float *>(sh + 1) + (256 + 8 * 2 * 128);
   if (job.nl && (int)threadIdx.x < job.nl_C) {
+    pdl_wait();  // the statistics are the previous kernel's output
     const int c = threadIdx.x;
     const double mean = job.nl_sums[c] * job.nl_inv_count;
     double var = job.nl_sums[job.nl_C + c] * job.nl_inv_count - mean * mean;
@@ -250,6 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // A warp owns whole (patch row, channel block) slabs: lanes run along x (coalesced 512-byte loads), up to
     // kNlPx float4 pairs in flight per lane, no per-pixel index arithmetic.
     // nl == 1: 8 producer warps (4, 8..14; one epilogue group); nl == 2: 4 producer warps (4, 12..14; two epilogue groups)
+    pdl_wait();  // the raw input is the previous kernel's output
     const int nlw = job.nl == 1 ? kNlWarps : 4;
     const int pw = warp == 4 ? 0 : (job.nl == 1 ? warp - 7 : warp - 11);
     const int pslab = job.pslab16, nslabs = job.nrows * job.CbG;
@@ -322,6 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ===== A producer: the input patch of each (tile, channel group): one bulk copy per (patch row, channel block, hi/lo),
     // spread over the 32 lanes.  (Measured alternatives, all slower on B200 and removed: four producer warps sharing the
     // copies, a single elected lane with warp-uniform operands, one 4-D cp.async.bulk.tensor per plane -- DESIGN.md 9.3.) =====
+    pdl_wait();  // the operand is the previous kernel's output (weights, TMEM, barriers did not have to wait)
     const int per_row = job.CbG * job.nseg * 2;  // copies per patch row (x2: hi, lo)
     const int ncopies = job.nrows * per_row;
     uint32_t stage_tx = 0;
@@ -835,14 +760,16 @@ static unsigned long long *g_trace_buf = nullptr;
 static size_t g_trace_cap = 0, g_trace_used = 0;
 void conv_tc_set_trace(unsigned long long *buf, size_t words) { g_trace_buf = buf; g_trace_cap = words; g_trace_used = 0; }
 size_t conv_tc_trace_used() { return g_trace_used; }
+unsigned long long *conv_trace_claim(size_t words) {
+  if (!g_trace_buf || g_trace_used + words > g_trace_cap) return nullptr;
+  unsigned long long *p = g_trace_buf + g_trace_used;
+  g_trace_used += words;
+  return p;
+}
 
 int launch_conv_tc(const ConvJob &job_in, int num_sms, cudaStream_t st) {
   ConvJob job = job_in;
-  job.trace = nullptr;
-  {
-    const size_t need = (size_t)(job.ntiles < num_sms ? job.ntiles : num_sms) * kTraceWords;
-    if (g_trace_buf && g_trace_used + need <= g_trace_cap) { job.trace = g_trace_buf + g_trace_used; g_trace_used += need; }
-  }
+  job.trace = conv_trace_claim((size_t)(job.ntiles < num_sms ? job.ntiles : num_sms) * kTraceWords);
   size_t smem = conv_tc_smem_bytes(job);
   if (smem > 227 * 1024) {
     set_error("conv_tc: shared memory %zu exceeds 227 KB", smem);
@@ -859,7 +786,7 @@ int launch_conv_tc(const ConvJob &job_in, int num_sms, cudaStream_t st) {
     attr_set.fetch_or(bit, std::memory_order_release);
   }
   int grid = job.ntiles < num_sms ? job.ntiles : num_sms;
-  conv_tc_kernel<<<grid, kThreads, smem, st>>>(job);
+  FAV_TRY(check_cuda(launch_pdl(conv_tc_kernel, dim3(grid), dim3(kThreads), smem, st, true, job), "launch(conv_tc)"));
   return post_launch("conv_tc");
 }
 

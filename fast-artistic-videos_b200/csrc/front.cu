@@ -16,6 +16,7 @@
 // warp is bit-identical to the reference's own CUDA kernel compiled for sm_100a (oracle/ref_warp) and to the CPU oracle.
 #include "fav_common.cuh"
 #include "net_layout.cuh"
+#include "occlusion.cuh"
 
 namespace fav {
 
@@ -80,6 +81,18 @@ __device__ __forceinline__ float sample_plane(const Sample &s, const float *__re
     v = __fadd_rn(v, __fmul_rn(__fmul_rn(s.wy, s.wx), vbr));
     return v;
   }
+}
+
+// same blend on taps already in registers (the fused kernels request every tap of a thread before using any)
+__device__ __forceinline__ float blend_taps(const Sample &s, float vtl, float vtr, float vbl, float vbr, int border_mode) {
+  const float omx = __fsub_rn(1.0f, s.wx), omy = __fsub_rn(1.0f, s.wy);
+  if (border_mode == FAV_BORDER_PER_TAP) return bilinear_ref_blend(s.wx, s.wy, omx, omy, vtl, vtr, vbl, vbr);
+  if (s.off) return 0.0f;
+  float v = __fmul_rn(__fmul_rn(omy, omx), vtl);
+  v = __fadd_rn(v, __fmul_rn(__fmul_rn(omy, s.wx), vtr));
+  v = __fadd_rn(v, __fmul_rn(__fmul_rn(s.wy, omx), vbl));
+  v = __fadd_rn(v, __fmul_rn(__fmul_rn(s.wy, s.wx), vbr));
+  return v;
 }
 
 // ---- a-1: standalone warp ------------------------------------------------------------------------
@@ -168,14 +181,13 @@ static int launch_warp(const float *img, const int64_t isz[4], const int64_t ist
 // out7: [7,H,W] fp32.  VEC pixels per thread.
 // PACK: instead of the 7 fp32 planes, write the network's first operand directly (fp16 hi/lo, 8th channel zero) including
 // the nn.SpatialReflectionPadding(R) copies (train_video.lua:319-324) -- what pack_input_kernel would produce from out7.
-template <int VEC, bool FIRST, bool PACK = false>
-__global__ void __launch_bounds__(256) temporal_input_kernel(
+// Per-thread body: VEC consecutive pixels of row y starting at x0, certainty c[] already in registers (read from the cert
+// plane by temporal_input_kernel, computed in shared memory by temporal_stage_kernel).
+template <int VEC, bool FIRST, bool PACK>
+__device__ __forceinline__ void temporal_pixels(
     const float *__restrict__ content, const float *__restrict__ prev, const float *__restrict__ flow,
-    const float *__restrict__ cert, const float *__restrict__ fill, const float *__restrict__ flow_mask,
-    float *__restrict__ out7, int H, int W, int border_mode, Operand dst = Operand(), int R = 0) {
-  int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-  int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x0 >= W || y >= H) return;
+    const float (&c)[VEC], const float *__restrict__ fill, const float *__restrict__ flow_mask,
+    float *__restrict__ out7, int H, int W, int x0, int y, int border_mode, const Operand &dst, int R) {
   const int64_t HW = (int64_t)H * W;
   const int64_t o = (int64_t)y * W + x0;
   const float mean[3] = {FAV_MEAN_B, FAV_MEAN_G, FAV_MEAN_R};
@@ -190,23 +202,44 @@ __global__ void __launch_bounds__(256) temporal_input_kernel(
       cont[j][0] = __ldcs(content + j * HW + o);
     }
   }
-  float dy[VEC], dx[VEC], c[VEC], fm[VEC];
+  float dy[VEC], dx[VEC], fm[VEC];
   if (!FIRST) {
     if (VEC == 4) {
-      float4 t = __ldcs(reinterpret_cast<const float4 *>(flow + o));
+      float4 t = __ldg(reinterpret_cast<const float4 *>(flow + o));
       dy[0] = t.x; dy[1] = t.y; dy[2] = t.z; dy[3] = t.w;
-      t = __ldcs(reinterpret_cast<const float4 *>(flow + HW + o));
+      t = __ldg(reinterpret_cast<const float4 *>(flow + HW + o));
       dx[0] = t.x; dx[1] = t.y; dx[2] = t.z; dx[3] = t.w;
-      t = __ldcs(reinterpret_cast<const float4 *>(cert + o));
-      c[0] = t.x; c[1] = t.y; c[2] = t.z; c[3] = t.w;
       if (flow_mask) {
         t = __ldcs(reinterpret_cast<const float4 *>(flow_mask + o));
         fm[0] = t.x; fm[1] = t.y; fm[2] = t.z; fm[3] = t.w;
       }
     } else {
-      dy[0] = flow[o]; dx[0] = flow[HW + o]; c[0] = cert[o];
+      dy[0] = flow[o]; dx[0] = flow[HW + o];
       if (flow_mask) fm[0] = flow_mask[o];
     }
+  }
+  // all bilinear taps of the thread's pixels are requested before any of them is used (VEC x 3 planes x 4 corners
+  // independent gathers in flight: the kernel is latency bound, not traffic bound)
+  float wv[VEC][3];
+  if (!FIRST) {
+    Sample sm[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) sm[i] = make_sample(dy[i], dx[i], y, x0 + i, H, W, border_mode);
+    float tap[VEC][3][4];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float *p = prev + k * HW;
+        tap[i][k][0] = sm[i].tl ? __ldg(p + (int64_t)sm[i].y0 * W + sm[i].x0) : 0.f;
+        tap[i][k][1] = sm[i].tr ? __ldg(p + (int64_t)sm[i].y0 * W + sm[i].x1) : 0.f;
+        tap[i][k][2] = sm[i].bl ? __ldg(p + (int64_t)sm[i].y1 * W + sm[i].x0) : 0.f;
+        tap[i][k][3] = sm[i].br ? __ldg(p + (int64_t)sm[i].y1 * W + sm[i].x1) : 0.f;
+      }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) wv[i][k] = blend_taps(sm[i], tap[i][k][0], tap[i][k][1], tap[i][k][2], tap[i][k][3], border_mode);
   }
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -218,15 +251,10 @@ __global__ void __launch_bounds__(256) temporal_input_kernel(
       for (int k = 0; k < 3; ++k) res[3 + k][i] = 0.0f;
       res[6][i] = 0.0f;  // core.lua:135-136: everything "uncertain"
     } else {
-      Sample s = make_sample(dy[i], dx[i], y, x0 + i, H, W, border_mode);
-      float wr = sample_plane(s, prev, W, 1, border_mode);
-      float wg = sample_plane(s, prev + HW, W, 1, border_mode);
-      float wb = sample_plane(s, prev + 2 * HW, W, 1, border_mode);
-      float wrgb[3] = {wr, wg, wb};
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        float pre = __fsub_rn(__fmul_rn(wrgb[2 - k], 255.0f), mean[k]);  // core.lua:166
-        res[3 + k][i] = __fmul_rn(pre, c[i]);                              // :167
+        float pre = __fsub_rn(__fmul_rn(wv[i][2 - k], 255.0f), mean[k]);  // core.lua:166
+        res[3 + k][i] = __fmul_rn(pre, c[i]);                               // :167
       }
       res[6][i] = flow_mask ? fminf(c[i], fm[i]) : c[i];  // :169 cmin
     }
@@ -276,6 +304,97 @@ __global__ void __launch_bounds__(256) temporal_input_kernel(
   }
 }
 
+template <int VEC, bool FIRST, bool PACK = false>
+__global__ void __launch_bounds__(256) temporal_input_kernel(
+    const float *__restrict__ content, const float *__restrict__ prev, const float *__restrict__ flow,
+    const float *__restrict__ cert, const float *__restrict__ fill, const float *__restrict__ flow_mask,
+    float *__restrict__ out7, int H, int W, int border_mode, Operand dst = Operand(), int R = 0) {
+  int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x0 >= W || y >= H) return;
+  const int64_t o = (int64_t)y * W + x0;
+  float c[VEC];
+  if (!FIRST) {
+    if (VEC == 4) {
+      const float4 t = __ldcs(reinterpret_cast<const float4 *>(cert + o));
+      c[0] = t.x; c[1] = t.y; c[2] = t.z; c[3] = t.w;
+    } else {
+      c[0] = cert[o];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) c[i] = 0.f;
+  }
+  temporal_pixels<VEC, FIRST, PACK>(content, prev, flow, c, fill, flow_mask, out7, H, W, x0, y, border_mode, dst, R);
+}
+
+// ---- the WHOLE temporal-consistency stage in one kernel ---------------------------------------------------------------
+// north star: "BilinearSamplerBDHW warp of the previous stylized frame by the supplied optical flow, consistencyChecker's
+// forward/backward-flow occlusion test, and the channel concat ... become one fused sm_100a kernel ... that writes the
+// 7-channel tensor the net consumes directly".  Per 64 x 16 pixel tile:
+//   1. certainty of the tile + a (r/2)-pixel halo into shared memory: MODE 0 = the occlusion test itself
+//      (consistencyChecker.cpp:99-125, 3-argument mode; flow1 = the backward flow that also drives the warp, flow2 = forward
+//      flow) -- halo pixels are recomputed instead of exchanged; MODE 1 = a given certainty plane (func_load_cert output);
+//   2. utils.min_filter (utils.lua:161-169) as a separable r x r minimum in shared memory (pad cells = +inf);
+//   3. warp + preprocess + mask + concat of the thread's 4 pixels (temporal_pixels above).
+// Bit-identical to consistency_kernel -> min_filter_kernel -> temporal_input_kernel (tests/test_gpu_front.py).
+constexpr int TS_TX = 64, TS_TY = 16, TS_MAXP = 7;
+template <bool PACK, int MODE>
+__global__ void __launch_bounds__(256) temporal_stage_kernel(
+    const float *__restrict__ content, const float *__restrict__ prev, const float *__restrict__ flow,
+    const float *__restrict__ fw_u, const float *__restrict__ fw_v, const float *__restrict__ cert_raw,
+    const float *__restrict__ fill, const float *__restrict__ flow_mask, float *__restrict__ out7,
+    float *__restrict__ cert_out, int H, int W, int r, int border_mode, Operand dst, int R) {
+  __shared__ float cs[TS_TY + 2 * TS_MAXP][TS_TX + 2 * TS_MAXP + 1];
+  __shared__ float rm[TS_TY + 2 * TS_MAXP][TS_TX + 1];
+  const int p = r / 2, bx = blockIdx.x * TS_TX, by = blockIdx.y * TS_TY;
+  const int tw = TS_TX + 2 * p, th = TS_TY + 2 * p;
+  const int64_t HW = (int64_t)H * W;
+  for (int i = threadIdx.x; i < tw * th; i += 256) {
+    const int ty = i / tw, tx = i - ty * tw;
+    const int gy = by + ty - p, gx = bx + tx - p;
+    float v = INFINITY;  // outside the image: ignored by the max-pooling of utils.min_filter (-inf padding)
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      const int64_t o = (int64_t)gy * W + gx;
+      if (MODE == 0) {
+        // flow = (dy, dx) = (v, u) of the backward flow = flow1 of the checker
+        v = check_pixel(fw_u, fw_v, __ldg(flow + HW + o), __ldg(flow + o), gx, gy, W, H, nullptr, 0.f) ? 1.f : 0.f;
+      } else {
+        v = __ldg(cert_raw + o);
+      }
+    }
+    cs[ty][tx] = v;
+  }
+  __syncthreads();
+  if (p > 0) {
+    for (int i = threadIdx.x; i < th * TS_TX; i += 256) {
+      const int ty = i / TS_TX, tx = i % TS_TX;
+      float m = INFINITY;
+      for (int d = 0; d < r; ++d) m = fminf(m, cs[ty][tx + d]);
+      rm[ty][tx] = m;
+    }
+    __syncthreads();
+  }
+  const int tx4 = (threadIdx.x & 15) * 4, ty = threadIdx.x >> 4;
+  const int x0 = bx + tx4, y = by + ty;
+  if (x0 >= W || y >= H) return;
+  float c[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (p > 0) {
+      float m = INFINITY;
+      for (int d = 0; d < r; ++d) m = fminf(m, rm[ty + d][tx4 + i]);
+      // MulConstant(-1), AddConstant(1), pool, MulConstant(-1), AddConstant(1)  (utils.lua:162-167)
+      const float t = __fadd_rn(__fmul_rn(m, -1.0f), 1.0f);
+      c[i] = __fadd_rn(__fmul_rn(t, -1.0f), 1.0f);
+    } else {
+      c[i] = cs[ty][tx4 + i];
+    }
+  }
+  if (cert_out) *reinterpret_cast<float4 *>(cert_out + (int64_t)y * W + x0) = make_float4(c[0], c[1], c[2], c[3]);
+  temporal_pixels<4, false, PACK>(content, prev, flow, c, fill, flow_mask, out7, H, W, x0, y, border_mode, dst, R);
+}
+
 // run_[next_]image: the fused input written straight into the first operand of the network (no out7 round trip)
 int launch_temporal_input_packed(const float *content, const float *prev, const float *flow, const float *cert,
                                  const float *fill, const float *flow_mask, const Operand &dst, int R, int H, int W,
@@ -297,6 +416,28 @@ int launch_temporal_input_packed(const float *content, const float *prev, const 
       temporal_input_kernel<1, false, true><<<grid, block, 0, st>>>(content, prev, flow, cert, fill, flow_mask, nullptr, H, W, border_mode, dst, R);
   }
   return post_launch(first ? "first_frame_input" : "temporal_input");
+}
+
+// the whole stage in one launch.  Exactly one of (fw_uv, cert_raw) is non-null.  dst != null: write the network's first
+// operand (PACK), else the 7 fp32 planes out7.  Returns FAV_ERR_UNSUPPORTED when the 16-byte vector path does not apply
+// (callers then fall back to the three separate kernels).
+int launch_temporal_stage(const float *content, const float *prev, const float *flow, const float *fw_uv, const float *cert_raw,
+                          const float *fill, const float *flow_mask, float *out7, float *cert_out, const Operand *dst, int R,
+                          int H, int W, int r, int border_mode, cudaStream_t st) {
+  const bool vec = (W % 4 == 0) && aligned16(content) && aligned16(flow) && (!flow_mask || aligned16(flow_mask)) &&
+                   (!fill || aligned16(fill)) && (!out7 || aligned16(out7)) && (!cert_out || aligned16(cert_out));
+  if (!vec || r < 0 || r / 2 > TS_MAXP || (r > 1 && !(r & 1))) return FAV_ERR_UNSUPPORTED;
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid(ceil_div(W, TS_TX), ceil_div(H, TS_TY));
+  const Operand d = dst ? *dst : Operand();
+  if (fw_uv) {
+    if (dst) temporal_stage_kernel<true, 0><<<grid, 256, 0, st>>>(content, prev, flow, fw_uv, fw_uv + HW, nullptr, fill, flow_mask, nullptr, cert_out, H, W, r, border_mode, d, R);
+    else temporal_stage_kernel<false, 0><<<grid, 256, 0, st>>>(content, prev, flow, fw_uv, fw_uv + HW, nullptr, fill, flow_mask, out7, cert_out, H, W, r, border_mode, d, R);
+  } else {
+    if (dst) temporal_stage_kernel<true, 1><<<grid, 256, 0, st>>>(content, prev, flow, nullptr, nullptr, cert_raw, fill, flow_mask, nullptr, cert_out, H, W, r, border_mode, d, R);
+    else temporal_stage_kernel<false, 1><<<grid, 256, 0, st>>>(content, prev, flow, nullptr, nullptr, cert_raw, fill, flow_mask, out7, cert_out, H, W, r, border_mode, d, R);
+  }
+  return post_launch("temporal_stage");
 }
 
 int launch_temporal_input(const float *content, const float *prev, const float *flow, const float *cert,
@@ -451,6 +592,22 @@ int fav_temporal_input(const float *content, const float *prev, const float *flo
   FAV_TRY(require_device());
   return launch_temporal_input(content, prev, flow, cert, fill, flow_mask, out7, H, W, border_mode, false,
                                (cudaStream_t)stream);
+}
+
+int fav_temporal_stage(const float *content, const float *prev, const float *flow_bw, const float *flow_fw_uv,
+                       const float *cert_raw, const float *fill, const float *flow_mask, float *out7, float *cert_out,
+                       int H, int W, int min_filter_r, int border_mode, void *stream) {
+  FAV_REQUIRE(content && prev && flow_bw && out7, "temporal_stage: null tensor");
+  FAV_REQUIRE((flow_fw_uv != nullptr) != (cert_raw != nullptr), "temporal_stage: give either the forward flow or a certainty plane");
+  FAV_REQUIRE(H > 0 && W > 0, "temporal_stage: empty frame");
+  FAV_REQUIRE(min_filter_r >= 0 && (min_filter_r <= 1 || (min_filter_r & 1)) && min_filter_r / 2 <= TS_MAXP,
+              "temporal_stage: occlusions_min_filter must be odd and <= %d", 2 * TS_MAXP + 1);
+  FAV_REQUIRE(border_mode == FAV_BORDER_PER_TAP || border_mode == FAV_BORDER_PAD_PIXEL, "bad border_mode");
+  FAV_TRY(require_device());
+  int rc = launch_temporal_stage(content, prev, flow_bw, flow_fw_uv, cert_raw, fill, flow_mask, out7, cert_out, nullptr, 0, H, W,
+                                 min_filter_r, border_mode, (cudaStream_t)stream);
+  if (rc == FAV_ERR_UNSUPPORTED) set_error("temporal_stage: needs W %% 4 == 0 and 16-byte aligned planes");
+  return rc;
 }
 
 int fav_first_frame_input(const float *content, const float *fill, float *out7, int H, int W, void *stream) {

@@ -13,12 +13,19 @@
 #include <cstring>
 
 #include "conv_plan.hpp"
+#include "conv_res_plan.hpp"
 
 namespace fav {
 
 int launch_temporal_input(const float *content, const float *prev, const float *flow, const float *cert,
                           const float *fill, const float *flow_mask, float *out7, int H, int W, int border_mode,
                           bool first, cudaStream_t st);
+int launch_temporal_stage(const float *content, const float *prev, const float *flow, const float *fw_uv, const float *cert_raw,
+                          const float *fill, const float *flow_mask, float *out7, float *cert_out, const Operand *dst, int R,
+                          int H, int W, int r, int border_mode, cudaStream_t st);
+int launch_min_filter(const float *in, float *out, int n, int H, int W, int r, cudaStream_t st);
+int launch_consistency(const float *f1u, const float *f1v, const float *f2u, const float *f2v, const float *structure,
+                       const float *avg_dev, float avg_host, uint8_t *rel, float *cert, int W, int H, cudaStream_t st);
 int launch_temporal_input_packed(const float *content, const float *prev, const float *flow, const float *cert,
                                  const float *fill, const float *flow_mask, const Operand &dst, int R, int H, int W,
                                  int border_mode, bool first, cudaStream_t st);
@@ -56,6 +63,7 @@ struct PlanStep {
   int relu = 0;
   RawTensor raw;
   std::vector<ConvJob> tc;
+  std::vector<ResJob> res;   // non-empty: the tcgen05 path of this step is conv_res.cu (raw output planar)
   std::vector<SimtJob> simt;
   int stats_off = 0;
   int layer_index = -1;  // arch token index whose output this step completes (for fav_net_layer_output)
@@ -71,6 +79,7 @@ struct Plan {
   size_t stats_bytes = 0;
   float *msb = nullptr;
   float *in7 = nullptr, *out3 = nullptr;  // scratch for run_image / run_next_image
+  float *cert_a = nullptr, *cert_b = nullptr;  // scratch of the unfused fallback of fav_run_next_image_flows
   std::vector<PlanStep> steps;
   std::map<int, int> layer_operand;  // arch token index -> operand holding its output
   // CUDA graphs of the whole per-frame kernel sequence (run_[next_]image), one per destination buffer: a frame is ~40
@@ -242,9 +251,27 @@ static int build_conv_jobs(fav_net *net, Plan &pl, PlanStep &st, const ConvDef &
     for (int t = 0; t < s.ntaps; ++t) { s.tdy[t] = (int8_t)ph.taps[t].dy; s.tdx[t] = (int8_t)ph.taps[t].dx; }
     s.w = ph.d_w_simt; s.Cin_pad = c.cin_pad; s.Cout = c.cout; s.Cout_pad8 = c.cout_pad8; s.bias = c.d_bias;
     s.Ho = c.transposed ? in.H : st.raw.H; s.Wo = c.transposed ? in.W : st.raw.W; s.raw = st.raw.p; s.raw_Cq = st.raw.Cq; s.raw_Wp = st.raw.Wp;
+    s.raw_planar = st.raw.planar; s.raw_Hp = st.raw.Hp;
     s.oy_mul = s.ox_mul = c.out_mul; s.oy_off = ph.oy_off; s.ox_off = ph.ox_off;
     s.final_mode = last ? 1 : 0; s.out3 = out3; s.tanh_c = net->tanh_c;
     st.simt.push_back(s);
+  }
+  if (st.raw.planar) {  // residual-block kernel (conv_res.cu): cost-balanced tile table, same packed weights as conv_tc
+    const ConvPhase &ph = c.phases[0];
+    ResJob r;
+    FAV_TRY(fill_res_job(c, ph, in, r));
+    ResPlan rp = plan_res_tiles(r.Ho, r.Wo, net->num_sms);
+    void *d_tiles = nullptr, *d_first = nullptr;
+    FAV_TRY(check_cuda(cudaMalloc(&d_tiles, rp.tiles.size() * sizeof(ResTile)), "cudaMalloc(res tiles)"));
+    pl.allocs.push_back(d_tiles);
+    FAV_TRY(check_cuda(cudaMalloc(&d_first, rp.cta_first.size() * sizeof(int)), "cudaMalloc(res tiles)"));
+    pl.allocs.push_back(d_first);
+    FAV_TRY(check_cuda(cudaMemcpy(d_tiles, rp.tiles.data(), rp.tiles.size() * sizeof(ResTile), cudaMemcpyHostToDevice), "cudaMemcpy(res tiles)"));
+    FAV_TRY(check_cuda(cudaMemcpy(d_first, rp.cta_first.data(), rp.cta_first.size() * sizeof(int), cudaMemcpyHostToDevice), "cudaMemcpy(res tiles)"));
+    r.tiles = (const ResTile *)d_tiles; r.cta_first = (const int *)d_first; r.grid = rp.grid;
+    r.b = ph.d_b_tc; r.bias = c.d_bias;
+    r.raw = st.raw.p; r.raw_Hp = st.raw.Hp; r.raw_Wp = st.raw.Wp;
+    st.res.push_back(r);
   }
   return FAV_OK;
 }
@@ -325,6 +352,10 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
       cs.raw.p = (pos & 1) ? pl->raw_buf2 : pl->raw_buf; cs.raw.C = c.cout; cs.raw.Cq = round_up(c.cout, 4) / 4; cs.raw.H = ho; cs.raw.W = wo;
       cs.raw.Hp = ho + 2; cs.raw.Wp = round_up(wo, kTileM);
       const bool last = op.last && i == n - 1;
+      if (!last && !getenv("FAV_NO_RES")) {  // residual-block convolutions: swapped-role kernel, planar raw output
+        ConvDef &cm = net->convs[op.conv[i]];
+        if (cm.phases.size() == 1 && conv_res_eligible(cm, cm.phases[0])) { cs.raw.planar = 1; cs.raw.Wp = round_up(wo, 16); }
+      }
       FAV_TRY(build_conv_jobs(net, *pl, cs, c, last, nullptr));
       // second conv of a residual block: fold the preceding InstanceNorm + ReLU pass into its patch producers
       if (op.kind == 1 && i == 1 && !pl->steps.empty() && pl->steps.back().kind == 1 && !getenv("FAV_NO_NL")) {
@@ -332,6 +363,20 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
         const InDef &n = net->inorms[ap.inorm];
         const Operand &in = pl->ops[cs.src];
         bool ok = ap.skip < 0 && n.C <= 256 && cs.tc.size() == 1;
+        if (ok && !cs.res.empty()) {  // conv_res.cu reads the PLANAR raw output of the block's first conv
+          ok = ap.raw.planar && n.C == pl->ops[cs.src].C;
+          if (ok) {
+            ResJob &r = cs.res[0];
+            const Operand &in = pl->ops[cs.src];
+            r.nl = 1; r.nl_pad = c.pad; r.nl_raw = ap.raw.p; r.nl_Hp = ap.raw.Hp; r.nl_Wp = ap.raw.Wp; r.nl_H = ap.raw.H; r.nl_W = ap.raw.W;
+            r.nl_relu = ap.relu; r.nl_C = n.C; r.nl_sums = pl->stats + ap.stats_off; r.nl_gamma = n.d_gamma; r.nl_beta = n.d_beta;
+            r.nl_inv_count = 1.0 / ((double)ap.raw.H * ap.raw.W); r.nl_eps = 1e-5;
+            (void)in;
+            ap.fused_nl = true;
+          }
+        } else if (ok && ap.raw.planar) {
+          ok = false;  // conv_tc's norm-on-load reads the quad layout only
+        } else
         if (ok) {
           ConvJob &j = cs.tc[0];
           ok = !j.rf_R && !j.pf && !j.xfold_kw && j.nseg == 1 && j.seg_dst16[0] == 0 && j.seg_len16[0] == j.pslab16 && j.row_mul == 1;
@@ -360,6 +405,7 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
       PlanStep ns;
       ns.kind = 1; ns.inorm = op.inorm[i]; ns.raw = raw; ns.stats_off = stats_off;
       for (ConvJob &j : pl->steps.back().tc) j.stats = pl->stats + stats_off;  // statistics fused into the epilogue
+      for (ResJob &j : pl->steps.back().res) j.stats = pl->stats + stats_off;
       stats_off += 2 * c.cout;
       const ConvDef *consumer = pos + 1 < order.size() ? &net->convs[order[pos + 1]] : nullptr;
       FAV_TRY(make_operand(*pl, c.cout, ho, wo, consumer, &ns.dst));
@@ -420,7 +466,9 @@ static int run_plan(fav_net *net, Plan &pl, const float *in7, float *out3, int f
         double px = c.transposed ? (double)in.H * in.W : (double)s.raw.H * s.raw.W;
         FAV_TRY(begin(1, 2.0 * c.cin * c.cout * c.k * c.k * px, c.name));
       }
-      if (net->conv_impl == 0) {
+      if (net->conv_impl == 0 && !s.res.empty()) {
+        for (ResJob &j : s.res) FAV_TRY(launch_conv_res(j, st));
+      } else if (net->conv_impl == 0) {
         for (ConvJob &j : s.tc) {
           if (j.final_mode) { j.final_mode = final_mode; j.out3 = out3; }
           FAV_TRY(launch_conv_tc(j, net->num_sms, st));
@@ -732,5 +780,43 @@ int fav_run_next_image(fav_net_t *net, const float *content, const float *prev_r
   }
   FAV_TRY(launch_temporal_input(content, prev_rgb, flow, cert, fill, flow_mask, pl->in7, H, W, border_mode, false, st));
   return run_plan_frame(net, *pl, pl->in7, out_rgb, st);  // core.lua:172-173
+}
+
+// a-8 with the certainty computed inside: the whole temporal stage (occlusion test or given certainty -> min filter -> warp
+// -> preprocess -> mask -> concat) is ONE kernel that writes the network's first operand, followed by one graph launch.
+int fav_run_next_image_flows(fav_net_t *net, const float *content, const float *prev_rgb, const float *flow_bw,
+                             const float *flow_fw_uv, const float *cert_raw, const float *fill, const float *flow_mask,
+                             int H, int W, int min_filter_r, int border_mode, float *out_rgb, void *stream) {
+  FAV_REQUIRE(net && content && prev_rgb && flow_bw && out_rgb, "fav_run_next_image_flows: null argument");
+  FAV_REQUIRE((flow_fw_uv != nullptr) != (cert_raw != nullptr), "fav_run_next_image_flows: give either the forward flow or a certainty plane");
+  FAV_REQUIRE(net->finalized, "fav_run_next_image_flows: call fav_net_finalize first");
+  FAV_REQUIRE(net->in_dim == 7, "fav_run_next_image_flows: video model (7 input channels) required");
+  FAV_REQUIRE(border_mode == FAV_BORDER_PER_TAP || border_mode == FAV_BORDER_PAD_PIXEL, "bad border_mode");
+  FAV_REQUIRE(min_filter_r >= 0 && (min_filter_r <= 1 || (min_filter_r & 1)) && min_filter_r <= 15, "occlusions_min_filter must be odd <= 15");
+  Plan *pl;
+  FAV_TRY(build_plan(net, H, W, &pl));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_temporal_stage(content, prev_rgb, flow_bw, flow_fw_uv, cert_raw, fill, flow_mask, nullptr, nullptr, &pl->ops[0],
+                                 net->reflect_pad, H, W, min_filter_r, border_mode, st);
+  if (rc == FAV_ERR_UNSUPPORTED) {  // unaligned planes / W % 4 != 0: the three separate kernels
+    const int64_t HW = (int64_t)H * W;
+    if (!pl->cert_a) {
+      FAV_TRY(alloc_zero(*pl, (void **)&pl->cert_a, HW * sizeof(float)));
+      FAV_TRY(alloc_zero(*pl, (void **)&pl->cert_b, HW * sizeof(float)));
+    }
+    const float *cert = cert_raw;
+    if (flow_fw_uv) {
+      FAV_TRY(launch_consistency(flow_bw + HW, flow_bw, flow_fw_uv, flow_fw_uv + HW, nullptr, nullptr, 0.f, nullptr, pl->cert_a, W, H, st));
+      cert = pl->cert_a;
+    }
+    if (min_filter_r > 1) {
+      FAV_TRY(launch_min_filter(cert, pl->cert_b, 1, H, W, min_filter_r, st));
+      cert = pl->cert_b;
+    }
+    rc = launch_temporal_input_packed(content, prev_rgb, flow_bw, cert, fill, flow_mask, pl->ops[0], net->reflect_pad, H, W,
+                                      border_mode, false, st);
+  }
+  FAV_TRY(rc);
+  return run_plan_frame(net, *pl, nullptr, out_rgb, st);
 }
 }

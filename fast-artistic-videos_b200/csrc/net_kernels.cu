@@ -60,7 +60,14 @@ __global__ void __launch_bounds__(256) in_stats_kernel(RawTensor raw, double *__
   for (int y = y0; y < min(y0 + kStatRows, raw.H); ++y) {
     const float4 *row = reinterpret_cast<const float4 *>(raw.p) + raw.off4(y, cq, 0);
     for (int x = threadIdx.x; x < raw.W; x += 256) {
-      float4 v = __ldg(row + x);
+      float4 v;
+      if (raw.planar) {
+        v.x = cq * 4 + 0 < raw.C ? __ldg(raw.p + raw.offp(cq * 4 + 0, y, x)) : 0.f;
+        v.y = cq * 4 + 1 < raw.C ? __ldg(raw.p + raw.offp(cq * 4 + 1, y, x)) : 0.f;
+        v.z = cq * 4 + 2 < raw.C ? __ldg(raw.p + raw.offp(cq * 4 + 2, y, x)) : 0.f;
+        v.w = cq * 4 + 3 < raw.C ? __ldg(raw.p + raw.offp(cq * 4 + 3, y, x)) : 0.f;
+      } else
+      v = __ldg(row + x);
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
       q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
     }
@@ -102,7 +109,33 @@ __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const doub
                                                        int shave, Operand dst) {
   __shared__ float s_mean[8], s_scale[8], s_beta[8];
   const int xbase = blockIdx.x * (128 * kApplyIter) + threadIdx.x;
-  int y = blockIdx.y, cb = blockIdx.z;
+  const int y = blockIdx.y, cb = blockIdx.z;
+  pdl_launch_dependents();  // PDL (fav_common.cuh)
+  pdl_wait();               // raw tensor and statistics are the previous kernel's output
+  // 1. every streaming load of the thread is requested first (they do not depend on the statistics): the per-block
+  //    finalisation below (dependent global loads + double sqrt / divide on 8 threads) then runs in their shadow
+  float v[kApplyIter][8];
+  uint4 skh[kApplyIter], skl[kApplyIter];
+  const float4 *rp = reinterpret_cast<const float4 *>(raw.p);
+#pragma unroll
+  for (int it = 0; it < kApplyIter; ++it) {
+    const int x = xbase + it * 128;
+    if (x < raw.W) {
+      if (raw.planar) {  // output of conv_res.cu: one plane per channel, lanes run along x (128-byte coalesced per plane)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[it][i] = __ldg(raw.p + raw.offp(cb * 8 + i, y, x));
+      } else {
+        const float4 a = __ldg(rp + raw.off4(y, 2 * cb, x)), b = __ldg(rp + raw.off4(y, 2 * cb + 1, x));
+        v[it][0] = a.x; v[it][1] = a.y; v[it][2] = a.z; v[it][3] = a.w; v[it][4] = b.x; v[it][5] = b.y; v[it][6] = b.z; v[it][7] = b.w;
+      }
+      if (has_skip) {  // ConcatTable{conv_block, ShaveImage(2)} -> CAddTable (models_video.lua:41-53)
+        const int64_t so = skip.off16(skip.padT + y + shave, cb, skip.padL + x + shave);
+        skh[it] = __ldg(reinterpret_cast<const uint4 *>(skip.hi) + so);
+        skl[it] = __ldg(reinterpret_cast<const uint4 *>(skip.lo) + so);
+      }
+    }
+  }
+  // 2. mean / gamma * rstd / beta of the block's 8 channels
   if (threadIdx.x < 8) {
     int c = cb * 8 + threadIdx.x;
     double mean = sums[c] * inv_count;
@@ -113,27 +146,28 @@ __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const doub
     s_beta[threadIdx.x] = beta[c];
   }
   __syncthreads();
-  const float4 *rp = reinterpret_cast<const float4 *>(raw.p);
+  // 3. normalise (+ReLU) (+skip), split into fp16 hi / lo, store the next operand
 #pragma unroll
   for (int it = 0; it < kApplyIter; ++it) {
-  const int x = xbase + it * 128;
-  if (x >= raw.W) return;
-  float4 a = __ldg(rp + raw.off4(y, 2 * cb, x)), b = __ldg(rp + raw.off4(y, 2 * cb + 1, x));
-  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const int x = xbase + it * 128;
+    if (x >= raw.W) break;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float t = (v[i] - s_mean[i]) * s_scale[i] + s_beta[i];
-    v[i] = relu ? fmaxf(t, 0.f) : t;
-  }
-  if (has_skip) {  // ConcatTable{conv_block, ShaveImage(2)} -> CAddTable (models_video.lua:41-53)
-    float sk[8];
-    int64_t so = skip.off16(skip.padT + y + shave, cb, skip.padL + x + shave);
-    load_join8(reinterpret_cast<const uint4 *>(skip.hi) + so, reinterpret_cast<const uint4 *>(skip.lo) + so, sk);
+    for (int i = 0; i < 8; ++i) {
+      float t = (v[it][i] - s_mean[i]) * s_scale[i] + s_beta[i];
+      v[it][i] = relu ? fmaxf(t, 0.f) : t;
+    }
+    if (has_skip) {
+      const uint32_t hw[4] = {skh[it].x, skh[it].y, skh[it].z, skh[it].w}, lw[4] = {skl[it].x, skl[it].y, skl[it].z, skl[it].w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += sk[i];
-  }
-  int64_t o = dst.off16(dst.padT + y, cb, dst.padL + x);
-  split_store8(v, reinterpret_cast<uint4 *>(dst.hi) + o, reinterpret_cast<uint4 *>(dst.lo) + o);
+      for (int i = 0; i < 4; ++i) {  // same arithmetic as load_join8
+        v[it][2 * i] += __half2float(__ushort_as_half((unsigned short)(hw[i] & 0xffff))) +
+                        __half2float(__ushort_as_half((unsigned short)(lw[i] & 0xffff)));
+        v[it][2 * i + 1] += __half2float(__ushort_as_half((unsigned short)(hw[i] >> 16))) +
+                            __half2float(__ushort_as_half((unsigned short)(lw[i] >> 16)));
+      }
+    }
+    const int64_t o = dst.off16(dst.padT + y, cb, dst.padL + x);
+    split_store8(v[it], reinterpret_cast<uint4 *>(dst.hi) + o, reinterpret_cast<uint4 *>(dst.lo) + o);
   }
 }
 
@@ -141,8 +175,8 @@ int launch_in_apply(const RawTensor &raw, const double *sums, const float *gamma
                     const Operand *skip, int shave, const Operand &dst, cudaStream_t st) {
   dim3 grid(ceil_div(raw.W, 128 * kApplyIter), raw.H, raw.C / 8);
   Operand sk = skip ? *skip : Operand();
-  in_apply_kernel<<<grid, 128, 0, st>>>(raw, sums, gamma, beta, 1.0 / ((double)raw.H * raw.W), (double)eps, relu, sk,
-                                        skip ? 1 : 0, shave, dst);
+  FAV_TRY(check_cuda(launch_pdl(in_apply_kernel, grid, dim3(128), 0, st, true, raw, sums, gamma, beta, 1.0 / ((double)raw.H * raw.W),
+                                (double)eps, relu, sk, skip ? 1 : 0, shave, dst), "launch(in_apply)"));
   return post_launch("in_apply");
 }
 
@@ -286,7 +320,11 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ 
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] += (co0 + i < j.Cout) ? __ldg(j.bias + co0 + i) : 0.f;
   const int yo = y * j.oy_mul + j.oy_off, xo = x * j.ox_mul + j.ox_off;
-  if (j.final_mode == 0) {
+  if (j.final_mode == 0 && j.raw_planar) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (co0 + i < j.Cout) j.raw[((int64_t)(co0 + i) * j.raw_Hp + yo) * j.raw_Wp + xo] = acc[i];
+  } else if (j.final_mode == 0) {
     float4 *rp = reinterpret_cast<float4 *>(j.raw);
     int64_t o0 = (((int64_t)yo * j.raw_Cq + (co0 >> 2)) * j.raw_Wp + xo);
     rp[o0] = make_float4(acc[0], acc[1], acc[2], acc[3]);

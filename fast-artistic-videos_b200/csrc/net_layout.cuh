@@ -14,7 +14,8 @@
 //           (even x plane, then odd x plane) so that stride-2 taps stay contiguous.
 //  Raw      fp32 convolution output before InstanceNorm: [Ho][Cq][Wp][4 channels] -- 16 bytes per
 //           (pixel, channel-quad); the epilogue thread that owns TMEM lane = pixel writes float4s that are
-//           coalesced across the 32 lanes of a warp.
+//           coalesced across the 32 lanes of a warp.  The residual-block kernel (conv_res.cu: TMEM lane = output
+//           channel) writes PLANAR fp32 [C][Hp][Wp] instead (RawTensor::planar).
 #pragma once
 #include "fav_common.cuh"
 #include <cuda_fp16.h>
@@ -59,8 +60,10 @@ struct RawTensor {
   float *p = nullptr;
   int C = 0, Cq = 0;  // channels, channel quads
   int H = 0, W = 0;   // logical size
-  int Hp = 0, Wp = 0; // allocated rows / row pitch in pixels (multiple of 128)
+  int Hp = 0, Wp = 0; // allocated rows / row pitch in pixels (multiple of 128; planar: multiple of 16)
+  int planar = 0;     // 1: fp32 [C][Hp][Wp] (output of conv_res.cu, one channel per TMEM lane); 0: [Ho][Cq][Wp][4]
   __host__ __device__ int64_t off4(int y, int cq, int x) const { return (((int64_t)y * Cq + cq) * Wp + x); }
+  __host__ __device__ int64_t offp(int c, int y, int x) const { return (((int64_t)c * Hp + y) * Wp + x); }
 };
 
 // one filter tap of a (phase of a) convolution: input pixel = (sy*y + dy, sx*x + dx)

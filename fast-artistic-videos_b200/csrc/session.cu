@@ -4,17 +4,17 @@
 // The recurrent state last_frame_stylized stays on the device as unclamped fp32 (fast_artistic_video.lua:169).
 // Three streams: H2D (frame i+1 inputs), compute (frame i), D2H (frame i-1 result); inputs and outputs are
 // double buffered and ordered with events, so copies overlap compute whenever the caller's host buffers are
-// pinned.  Nothing in the loop synchronises the host except fav_session_sync().
+// pinned.  Nothing in the loop synchronises the host except fav_session_sync(); host buffers handed to a call must stay
+// untouched until then (the copies are asynchronous).  Per frame the compute stream runs TWO launches: the fused
+// temporal-stage kernel (fav_run_next_image_flows) and the CUDA graph of the network.
+// The flows variant evaluates checkConsistency in its 3-argument mode (video_dataset/make_occlusions.sh:31-36); the
+// 4-argument structure term of makeOptFlow_deepflow.sh:59-60 is available through fav_compute_corners +
+// fav_consistency_check + the cert-given variant.
 #include <memory>
 #include <vector>
 
 #include "fav_common.cuh"
 
-namespace fav {
-int launch_min_filter(const float *in, float *out, int n, int H, int W, int r, cudaStream_t st);
-int launch_consistency(const float *f1u, const float *f1v, const float *f2u, const float *f2v, const float *structure,
-                       const float *avg_dev, float avg_host, uint8_t *rel, float *cert, int W, int H, cudaStream_t st);
-}
 
 using namespace fav;
 
@@ -66,7 +66,9 @@ void fav_session_destroy(fav_session_t *s) {
 
 int fav_session_create(fav_net_t *net, int H, int W, fav_session_t **out) {
   FAV_REQUIRE(net && out, "fav_session_create: null argument");
-  FAV_REQUIRE(H > 0 && W > 0, "fav_session_create: empty frame");
+  FAV_REQUIRE(H >= 16 && W >= 16 && H % 4 == 0 && W % 4 == 0,
+              "fav_session_create: frame size %dx%d: H and W must be multiples of 4 and >= 16 (reflect-start nets restore the "
+              "input size only then)", W, H);
   FAV_TRY(require_device());
   std::unique_ptr<fav_session, void (*)(fav_session *)> s(new fav_session(), fav_session_destroy);
   s->net = net; s->H = H; s->W = W;
@@ -114,20 +116,6 @@ static int session_step(fav_session *s, int mode, const float *content_host, con
     FAV_TRY(check_cuda(cudaMemcpyAsync(in.flow, flow_a + HW, HW * 4, cudaMemcpyHostToDevice, s->s_h2d), "H2D flow v"));
     FAV_TRY(check_cuda(cudaMemcpyAsync(in.flow_fw, flow_b, 2 * HW * 4, cudaMemcpyHostToDevice, s->s_h2d), "H2D flow fw"));
   }
-  // The occlusion mask and its min filter depend on this frame's uploads only, not on the previous stylized frame: they
-  // run on the upload stream and overlap the network of the previous frame.
-  const float *cert_dev = in.cert_raw;
-  if (mode != 0) {
-    if (mode == 2) {
-      // flow1 = backward flow (u at flow+HW, v at flow), flow2 = forward flow; 3-argument mode
-      FAV_TRY(launch_consistency(in.flow + HW, in.flow, in.flow_fw, in.flow_fw + HW, nullptr, nullptr, 0.f, nullptr,
-                                 in.cert_raw, W, H, s->s_h2d));
-    }
-    if (min_filter_r > 1) {  // utils.min_filter(cert, opt.occlusions_min_filter)  core.lua:207
-      FAV_TRY(launch_min_filter(in.cert_raw, in.cert, 1, H, W, min_filter_r, s->s_h2d));
-      cert_dev = in.cert;
-    }
-  }
   FAV_TRY(check_cuda(cudaEventRecord(in.uploaded, s->s_h2d), "cudaEventRecord"));
   // ---- compute
   FAV_TRY(check_cuda(cudaStreamWaitEvent(s->s_comp, in.uploaded, 0), "cudaStreamWaitEvent"));
@@ -137,8 +125,11 @@ static int session_step(fav_session *s, int mode, const float *content_host, con
   if (mode == 0) {
     FAV_TRY(fav_run_image(s->net, in.content, nullptr, H, W, s->out[so], s->s_comp));
   } else {
-    FAV_TRY(fav_run_next_image(s->net, in.content, s->out[so ^ 1], in.flow, cert_dev, nullptr, nullptr, H, W, border_mode,
-                               s->out[so], s->s_comp));
+    // ONE temporal-stage kernel per frame: occlusion test (mode 2) or given certainty (mode 1) -> min filter -> warp ->
+    // preprocess -> mask -> concat -> first operand of the net; then one graph launch
+    FAV_TRY(fav_run_next_image_flows(s->net, in.content, s->out[so ^ 1], in.flow, mode == 2 ? in.flow_fw : nullptr,
+                                     mode == 1 ? in.cert_raw : nullptr, nullptr, nullptr, H, W, min_filter_r, border_mode,
+                                     s->out[so], s->s_comp));
   }
   FAV_TRY(check_cuda(cudaEventRecord(s->t1, s->s_comp), "cudaEventRecord"));
   FAV_TRY(check_cuda(cudaEventRecord(in.consumed, s->s_comp), "cudaEventRecord"));

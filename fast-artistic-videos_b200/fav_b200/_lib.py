@@ -55,6 +55,7 @@ SIGNATURES = {
     "fav_vgg_preprocess": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     "fav_vgg_deprocess": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     "fav_temporal_input": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    "fav_temporal_stage": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     "fav_first_frame_input": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, _fp]),
     "fav_consistency_check": (C.c_int, [_fp, _fp, _fp, C.c_float, _fp, _fp, C.c_int, C.c_int, _fp]),
     "fav_compute_corners_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
@@ -79,6 +80,7 @@ SIGNATURES = {
     "fav_debug_trace_words": (C.c_size_t, []),
     "fav_run_image": (C.c_int, [C.c_void_p, _fp, _fp, C.c_int, C.c_int, _fp, _fp]),
     "fav_run_next_image": (C.c_int, [C.c_void_p, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp]),
+    "fav_run_next_image_flows": (C.c_int, [C.c_void_p, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp]),
     "fav_session_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "fav_session_destroy": (None, [C.c_void_p]),
     "fav_session_run_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

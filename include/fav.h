@@ -95,6 +95,16 @@ FAV_API int fav_vgg_deprocess(const float *in, float *out, int N, int H, int W, 
 FAV_API int fav_temporal_input(const float *content, const float *prev, const float *flow,
                                const float *cert, const float *fill, const float *flow_mask,
                                float *out7, int H, int W, int border_mode, void *stream);
+/* The WHOLE temporal-consistency stage in one kernel (north star): certainty from the forward/backward flow pair
+ * (checkConsistency, consistencyChecker.cpp:99-125, 3-argument mode) or from a given plane, utils.min_filter
+ * (utils.lua:161-169), then the fused warp + preprocess + mask + concat above.  Bit-identical to fav_consistency_check ->
+ * fav_min_filter -> fav_temporal_input.  flow_bw [2,H,W] (dy,dx) = (v,u) of the backward flow (drives the warp AND is
+ * flow1 of the checker); exactly one of flow_fw_uv [2,H,W] (u,v) / cert_raw [H,W] is non-NULL; min_filter_r =
+ * opt.occlusions_min_filter (odd, <= 15; 0/1 = none); cert_out [H,W] or NULL receives the filtered certainty.
+ * Needs W % 4 == 0 and 16-byte aligned planes (FAV_ERR_UNSUPPORTED otherwise). */
+FAV_API int fav_temporal_stage(const float *content, const float *prev, const float *flow_bw, const float *flow_fw_uv,
+                               const float *cert_raw, const float *fill, const float *flow_mask, float *out7,
+                               float *cert_out, int H, int W, int min_filter_r, int border_mode, void *stream);
 /* a-9 (front half)  run_image with model_img == nil: cat(pre(img), fill(cert=0), zeros)  :133-137 */
 FAV_API int fav_first_frame_input(const float *content, const float *fill, float *out7, int H, int W,
                                   void *stream);
@@ -195,6 +205,14 @@ FAV_API int fav_run_next_image(fav_net_t *net, const float *content, const float
                                const float *flow, const float *cert, const float *fill,
                                const float *flow_mask, int H, int W, int border_mode, float *out_rgb,
                                void *stream);
+
+/* a-8 including func_load_cert + utils.min_filter (core.lua:206-208): ONE temporal-stage kernel (fav_temporal_stage, writing
+ * the network's first operand directly) + one graph launch.  Arguments as fav_temporal_stage; falls back to the three
+ * separate kernels when the vector path does not apply. */
+FAV_API int fav_run_next_image_flows(fav_net_t *net, const float *content, const float *prev_rgb, const float *flow_bw,
+                                     const float *flow_fw_uv, const float *cert_raw, const float *fill,
+                                     const float *flow_mask, int H, int W, int min_filter_r, int border_mode,
+                                     float *out_rgb, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a-10  frame loop with HOST buffers (the reference-facing call bench.py's e2e times)

@@ -16,8 +16,9 @@ EMU = os.path.join(ROOT, "tests", "emu")
 def emu():
     so = os.path.join(EMU, "libfav_emu.so")
     src = os.path.join(EMU, "conv_emu.cu")
-    hdr = os.path.join(ROOT, "fast-artistic-videos_b200", "csrc", "conv_plan.hpp")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    csrc = os.path.join(ROOT, "fast-artistic-videos_b200", "csrc")
+    hdrs = [os.path.join(csrc, h) for h in ("conv_plan.hpp", "conv_res_plan.hpp", "conv_res.cuh", "conv.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs):
         subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
                                "-Wno-deprecated-gpu-targets", "-o", so, src])
     lib = C.CDLL(so)
@@ -78,3 +79,41 @@ def test_planner_decisions_for_the_720p_layers(emu):
     for case in ((32, 64, 3, 2, 1, 0, 0, 800, 1360), (64, 128, 3, 2, 1, 0, 0, 400, 680)):
         d = plan(emu, *case)
         assert d["mt"] == 1 and d["ksplit"]
+
+
+# ---- conv_res.cu: swapped-role residual kernel, cost-balanced tile table ---------------------------------------------------
+RES_CASES = [  # cin, pad, H, W, nctas
+    (128, 0, 6, 134, 148),    # fewer granules than CTAs
+    (128, 0, 7, 320, 148),    # odd output row count (second row of the last pair missing), 318-px rows
+    (128, 0, 14, 340, 12),    # several tiles per CTA, cuts inside rows, 338-px rows (last granule 2 px wide)
+    (128, 0, 11, 100, 5),
+    (128, 1, 5, 130, 7),      # zero-padded variant (c3s1-128)
+    (64, 0, 6, 70, 3),        # two channel groups
+    (128, 0, 3, 3, 148),      # 1x1 output
+]
+
+
+@pytest.mark.parametrize("case", RES_CASES)
+def test_emulated_residual_kernel_matches_direct_conv(emu, case):
+    me, mr = C.c_double(), C.c_double()
+    info = (C.c_int * 4)()
+    rc = emu.emu_res_check(*case, 3, C.byref(me), C.byref(mr), info)
+    assert rc == 0, emu.emu_last_error().decode()
+    assert me.value <= 2e-6 * max(mr.value, 1.0), (me.value, mr.value)
+
+
+@pytest.mark.parametrize("shape", [(198, 338), (196, 336), (180, 320), (288, 498), (270, 480), (560 - 2, 980 - 2), (532 - 2, 532 - 2)])
+def test_residual_tile_table_is_balanced(emu, shape):
+    """Every granule exactly once; the most expensive CTA within 6 % of the mean (the first design gave 2 or 3 fixed 128-px
+    units per SM: up to 50 % imbalance at 297 units on 148 SMs).  198x338 is the one awkward 720p layer: 99 row pairs x 22
+    granules need 148.5 CTAs for a sliver-free 3-CTAs-per-2-row-pairs pattern, so ONE kind of CTA gets three tiles (6,6,1
+    granules, cost 163 vs 134); the rest must stay tight."""
+    info = (C.c_int * 6)()
+    assert emu.emu_res_plan(shape[0], shape[1], 148, info) == 0, emu.emu_last_error().decode()
+    grid, tiles, mx, sm, narrow, wide = list(info)
+    assert grid == 148 and wide <= 128
+    if shape == (198, 338):
+        assert mx <= 163 and sm / grid <= 136, (mx, sm / grid)
+    else:
+        assert mx <= 1.16 * sm / grid, (mx, sm / grid)  # row pairs of 20-22 granules vs 12-15 per CTA: a few whole-granule patterns only
+        assert narrow >= 48, narrow

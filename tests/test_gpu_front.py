@@ -129,6 +129,59 @@ def test_fused_temporal_input_bit_exact(fav, shape, border):
     assert np.array_equal(out.cpu().numpy(), pyoracle.first_frame_input(c))
 
 
+@pytest.mark.parametrize("shape", [(64, 96), (100, 76), (33, 132), (256, 256), (360, 640)])
+@pytest.mark.parametrize("border", [0, 1])
+def test_whole_temporal_stage_in_one_kernel_bit_exact(fav, shape, border):
+    """fav_temporal_stage (occlusion test / given certainty -> min filter -> warp -> preprocess -> mask -> concat in ONE launch)
+    == fav_consistency_check -> fav_min_filter -> fav_temporal_input, and == the oracle composition, bit for bit."""
+    from fav_b200 import _lib
+    from oracle import pyoracle
+
+    H, W = shape
+    c, p = synth.make_frame(H, W, 2), synth.make_frame(H, W, 1) * 1.2 - 0.1
+    bw, fw = synth.make_backward_flow(H, W, 2), synth.make_forward_flow(H, W, 2)
+    flow = synth.checker_to_lua(bw)
+    rng = np.random.default_rng(11)
+    fill = rng.normal(0, 40, size=(3, H, W)).astype(np.float32)
+    fmask = rng.uniform(size=(H, W)).astype(np.float32)
+    cert_given = (rng.uniform(size=(H, W)) > 0.15).astype(np.float32)
+    tc, tp, tflow, tfw = T(c), T(p), T(flow), T(fw)
+    for (given, r, f, m) in ((None, 7, None, None), (None, 3, fill, fmask), (None, 0, None, None), (cert_given, 7, None, None),
+                             (cert_given, 1, fill, None)):
+        tfill, tm = (T(f) if f is not None else None), (T(m) if m is not None else None)
+        tgiven = T(given) if given is not None else None
+        out = torch.empty((7, H, W), device="cuda")
+        cert_out = torch.empty((H, W), device="cuda")
+        _lib.check(_lib.lib.fav_temporal_stage(_lib.dptr(tc), _lib.dptr(tp), _lib.dptr(tflow), None if given is not None else _lib.dptr(tfw),
+                                               _lib.dptr(tgiven), _lib.dptr(tfill), _lib.dptr(tm), _lib.dptr(out), _lib.dptr(cert_out),
+                                               H, W, r, border, _lib.stream_ptr()))
+        # the three separate kernels
+        cert = tgiven if given is not None else fav.consistencyChecker.check(T(bw), tfw, want_cert=True)[1]
+        if r > 1:
+            cert = fav.utils.min_filter(cert, r)
+        sep = torch.empty((7, H, W), device="cuda")
+        _lib.check(_lib.lib.fav_temporal_input(_lib.dptr(tc), _lib.dptr(tp), _lib.dptr(tflow), _lib.dptr(cert), _lib.dptr(tfill),
+                                               _lib.dptr(tm), _lib.dptr(sep), H, W, border, _lib.stream_ptr()))
+        assert torch.equal(cert_out, cert), (given is None, r)
+        assert torch.equal(out, sep), (given is None, r)
+        # the oracle composition
+        ocert = given if given is not None else pyoracle.consistency(bw, fw).astype(np.float32) / 255.0
+        if r > 1:
+            ocert = pyoracle.min_filter(ocert, r)
+        assert np.array_equal(out.cpu().numpy(), pyoracle.temporal_input(c, p, flow, ocert, f, m, warp_mode=border)), (given is None, r)
+
+
+def test_temporal_stage_rejects_unaligned(fav):
+    from fav_b200 import _lib
+
+    H, W = 32, 50  # W % 4 != 0
+    z = torch.zeros((7, H, W), device="cuda")
+    with pytest.raises(_lib.FavError) as e:
+        _lib.check(_lib.lib.fav_temporal_stage(_lib.dptr(z[:3]), _lib.dptr(z[:3]), _lib.dptr(z[:2]), _lib.dptr(z[:2]), None, None, None,
+                                               _lib.dptr(z), None, H, W, 7, 0, _lib.stream_ptr()))
+    assert e.value.status == _lib.FAV_ERR_UNSUPPORTED
+
+
 @pytest.mark.parametrize("case", make_golden.CONSISTENCY_CASES)
 def test_consistency_check_equals_reference_binary(fav, case):
     H, W, idx, sigma, seed = case
