@@ -749,7 +749,10 @@ int fav_run_image(fav_net_t *net, const float *content, const float *fill, int H
                   void *stream) {
   FAV_REQUIRE(net && content && out_rgb, "fav_run_image: null argument");
   FAV_REQUIRE(net->finalized, "fav_run_image: call fav_net_finalize first");
-  FAV_REQUIRE(net->in_dim == 7, "fav_run_image: video model (7 input channels) required");
+  // model_img == nil: the video model on cat(pre(img), fill, zeros) (core.lua:133-138); a separate 3-channel image model
+  // (-model_img, core.lua:61-68,146) gets pre(img) only -- the same fused input kernel, whose channels 3..7 are then zero
+  FAV_REQUIRE(net->in_dim == 7 || net->in_dim == 3, "fav_run_image: video model (7 input channels) or image model (3) required");
+  if (net->in_dim == 3) fill = nullptr;
   Plan *pl;
   FAV_TRY(build_plan(net, H, W, &pl));
   cudaStream_t st = (cudaStream_t)stream;

@@ -20,6 +20,7 @@ using namespace fav;
 
 struct fav_session {
   fav_net_t *net = nullptr;
+  fav_net_t *net_img = nullptr;  // optional separate image model for single images (-model_img, core.lua:61-68,146)
   int H = 0, W = 0;
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
   struct InSet {
@@ -123,7 +124,7 @@ static int session_step(fav_session *s, int mode, const float *content_host, con
     FAV_TRY(check_cuda(cudaStreamWaitEvent(s->s_comp, s->downloaded[so], 0), "cudaStreamWaitEvent"));
   FAV_TRY(check_cuda(cudaEventRecord(s->t0, s->s_comp), "cudaEventRecord"));
   if (mode == 0) {
-    FAV_TRY(fav_run_image(s->net, in.content, nullptr, H, W, s->out[so], s->s_comp));
+    FAV_TRY(fav_run_image(s->net_img ? s->net_img : s->net, in.content, nullptr, H, W, s->out[so], s->s_comp));
   } else {
     // ONE temporal-stage kernel per frame: occlusion test (mode 2) or given certainty (mode 1) -> min filter -> warp ->
     // preprocess -> mask -> concat -> first operand of the net; then one graph launch
@@ -142,6 +143,12 @@ static int session_step(fav_session *s, int mode, const float *content_host, con
   s->out_used[so] = true;
   s->have_prev = true;
   s->frame++;
+  return FAV_OK;
+}
+
+int fav_session_set_image_model(fav_session_t *s, fav_net_t *net_img) {
+  FAV_REQUIRE(s, "fav_session_set_image_model: null session");
+  s->net_img = net_img;
   return FAV_OK;
 }
 

@@ -66,3 +66,96 @@ def gather_clips(local: Dict[int, torch.Tensor], shapes: List[tuple], dst: int =
     for r in reqs:
         r.wait()
     return out if rank == dst else None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Streaming data plane (BASELINE.json config 3: 8 independent 1080p clips across 8 GPUs, "NCCL over NVLink only to scatter
+# frames and gather outputs").  Rank `src` owns every clip's inputs (decoded into pinned host memory); per chunk of
+# `chunk` frames it uploads the chunk and sends it to the owning rank, owners run the recurrent frame loop on their clips
+# and send the stylized chunk back.  One batch_isend_irecv per chunk step (NCCL group: no ordering deadlocks); the transfers
+# of chunk k+1 (inputs) and k-1 (outputs) fly while chunk k is processed.
+# ---------------------------------------------------------------------------------------------------------------------
+def stream_clips(num_clips, n_frames, chunk, in_shapes, out_shape, load_chunk, process_chunk, store_chunk, src=0, device=None,
+                 dtype=torch.float32):
+    """in_shapes: per-frame shapes of the input tensors of a clip, e.g. [(3,H,W), (2,H,W), (2,H,W)]; out_shape e.g. (3,H,W).
+    load_chunk(clip, f0, f1) -> list of tensors [f1-f0, *shape] (rank src only; host or device; moved to `device`),
+    process_chunk(clip, f0, inputs) -> tensor [f1-f0, *out_shape] on `device` (owner ranks, called in frame order),
+    store_chunk(clip, f0, out) (rank src only).  Returns dict(comm_wait_s, steps, bytes_in, bytes_out) of this rank."""
+    import time
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    nsteps = (n_frames + chunk - 1) // chunk
+    mine = [c for c in range(num_clips) if owner(c, world) == rank]
+    span = lambda k: (k * chunk, min(n_frames, (k + 1) * chunk))
+    inbuf = {}   # (clip, k) -> list of device tensors
+    outbuf = {}  # (clip, k) -> device tensor
+    stats = dict(comm_wait_s=0.0, steps=nsteps, bytes_in=0, bytes_out=0)
+
+    def to_dev(t):
+        return t.to(device, non_blocking=True) if device is not None else t
+
+    def exchange(k):
+        """post the transfers of step k: inputs of chunk k (src -> owners) and outputs of chunk k-2 (owners -> src)"""
+        ops = []
+        if 0 <= k < nsteps:
+            f0, f1 = span(k)
+            for c in range(num_clips):
+                o = owner(c, world)
+                if rank == src:
+                    ts = [to_dev(t) for t in load_chunk(c, f0, f1)]
+                    if o == src:
+                        inbuf[(c, k)] = ts
+                    else:
+                        for t in ts:
+                            ops.append(dist.P2POp(dist.isend, t.contiguous(), o))
+                            stats["bytes_in"] += t.numel() * t.element_size()
+                        inbuf[(c, k)] = ts  # keep alive until the send completes
+                elif rank == o:
+                    ts = [torch.empty((f1 - f0,) + tuple(s), dtype=dtype, device=device) for s in in_shapes]
+                    for t in ts:
+                        ops.append(dist.P2POp(dist.irecv, t, src))
+                    inbuf[(c, k)] = ts
+        kk = k - 2
+        if 0 <= kk < nsteps:
+            f0, f1 = span(kk)
+            for c in range(num_clips):
+                o = owner(c, world)
+                if o == src:
+                    continue
+                if rank == o:
+                    ops.append(dist.P2POp(dist.isend, outbuf[(c, kk)].contiguous(), src))
+                    stats["bytes_out"] += outbuf[(c, kk)].numel() * outbuf[(c, kk)].element_size()
+                elif rank == src:
+                    t = torch.empty((f1 - f0,) + tuple(out_shape), dtype=dtype, device=device)
+                    ops.append(dist.P2POp(dist.irecv, t, o))
+                    outbuf[(c, kk)] = t
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def finish(works, k):
+        t0 = time.perf_counter()
+        for w in works:
+            w.wait()
+        stats["comm_wait_s"] += time.perf_counter() - t0
+        kk = k - 2
+        if 0 <= kk < nsteps:
+            f0, _ = span(kk)
+            for c in range(num_clips):
+                if rank == src:
+                    store_chunk(c, f0, outbuf.pop((c, kk)))
+                elif owner(c, world) == rank:
+                    outbuf.pop((c, kk), None)
+        if rank == src and 0 <= k < nsteps:  # remote clips' staging buffers of step k are on the wire no longer
+            for c in range(num_clips):
+                if owner(c, world) != src:
+                    inbuf.pop((c, k), None)
+
+    pending = exchange(0)
+    finish(pending, 0)
+    for k in range(nsteps + 2):
+        pending = exchange(k + 1)          # in flight while chunk k is processed
+        if k < nsteps:
+            f0, _ = span(k)
+            for c in mine:
+                outbuf[(c, k)] = process_chunk(c, f0, inbuf.pop((c, k)))
+        finish(pending, k + 1)
+    return stats

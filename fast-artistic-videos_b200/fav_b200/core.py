@@ -34,7 +34,7 @@ def _opt(opt, k, d=None):
     return opt.get(k, d) if isinstance(opt, dict) else getattr(opt, k, d)
 
 
-def load_model(path_or_style: str, arch: str = synth.DEFAULT_ARCH) -> models_video.StyleNet:
+def load_model(path_or_style: str, arch: str = synth.DEFAULT_ARCH, in_dim: int = 7) -> models_video.StyleNet:
     """get_model (core.lua:38-57): a Torch7 `.t7` checkpoint (fav_b200/t7.py; the arch is recovered from the module
     tree), a `.npz` state dict, or `synthetic:<style>` = seeded random-init weights (no network here to fetch the
     released checkpoints)."""
@@ -42,28 +42,31 @@ def load_model(path_or_style: str, arch: str = synth.DEFAULT_ARCH) -> models_vid
         import numpy as np
 
         w = dict(np.load(path_or_style))
-        return models_video.StyleNet(arch).load_state(w)
+        return models_video.StyleNet(arch, in_dim=in_dim).load_state(w)
     if path_or_style.endswith(".t7"):  # torch.load(path).model (core.lua:39-47)
         from . import t7
 
         t7_arch, state, tanh_c, _pad = t7.load_checkpoint(path_or_style)
-        return models_video.StyleNet(t7_arch, tanh_constant=tanh_c).load_state(state)
+        cin = int(next(v for k, v in state.items() if k == "l0.weight").shape[1])
+        return models_video.StyleNet(t7_arch, tanh_constant=tanh_c, in_dim=cin).load_state(state)
     style = path_or_style.split(":", 1)[-1]
-    return models_video.synthetic_model(style, arch)
+    return models_video.synthetic_model(style, arch, in_dim)
 
 
 def run_fast_neural_video(opt, func_load_image, func_load_cert, func_eval, func_make_last_frame_warped,
-                          func_is_single_image, func_save_image, model_vid=None):
+                          func_is_single_image, func_save_image, model_vid=None, model_img=None):
     dtype = "torch.CudaTensor"  # utils.setup_gpu (utils.lua:43-66): this implementation is GPU-only
     dev = torch.device("cuda", int(_opt(opt, "gpu", 0)) if int(_opt(opt, "gpu", 0)) >= 0 else 0)
     torch.cuda.set_device(dev)
     if _opt(opt, "evaluate", False):
         raise _lib.FavError(_lib.FAV_ERR_UNSUPPORTED, "-evaluate needs the VGG-16 loss network (out of scope)")
-    if _opt(opt, "model_img", "self") != "self":
-        raise _lib.FavError(_lib.FAV_ERR_UNSUPPORTED, "separate image model for frame 1: use -model_img self")
     if float(_opt(opt, "scale_factor", 1)) != 1:
         raise _lib.FavError(_lib.FAV_ERR_UNSUPPORTED, "-scale_factor != 1 (bicubic image.scale) is not on the GPU path")
     model = model_vid if model_vid is not None else load_model(_opt(opt, "model_vid"), _opt(opt, "arch", synth.DEFAULT_ARCH))
+    # get_model (core.lua:59-69): 'self' -> model_img = nil, the video model also stylizes single images
+    model_img = model_img if model_img is not None else (
+        None if _opt(opt, "model_img", "self") in ("self", "", None)
+        else load_model(_opt(opt, "model_img"), _opt(opt, "arch_img", _opt(opt, "arch", synth.DEFAULT_ARCH)), in_dim=3))
     fill_mode = _opt(opt, "fill_occlusions", "vgg-mean")
     assert fill_mode in ("vgg-mean", "uniform-random")
 
@@ -78,7 +81,10 @@ def run_fast_neural_video(opt, func_load_image, func_load_cert, func_eval, func_
     def run_image(img):  # core.lua:121-158
         t1 = time.perf_counter()
         H, W = img.shape[-2:]
-        out = model.run_image(img.to(dev), generate_fill(H, W, torch.zeros((1, H, W), device=dev)))
+        if model_img is not None:  # core.lua:146: model_img:forward(img_pre)
+            out = model_img.run_image(img.to(dev))
+        else:
+            out = model.run_image(img.to(dev), generate_fill(H, W, torch.zeros((1, H, W), device=dev)))
         print("Elapsed time for stylizing frame independently:%f" % (time.perf_counter() - t1))
         return out
 

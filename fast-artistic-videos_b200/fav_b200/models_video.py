@@ -115,6 +115,21 @@ class StyleNet:
         return out
 
 
+    def run_next_image_flows(self, img, prev_rgb, flow_bw, flow_fw_uv=None, cert_raw=None, min_filter_r=7, fill=None,
+                             flow_mask=None, border_mode=_lib.BORDER_PER_TAP) -> torch.Tensor:
+        """run_next_image with func_load_cert + utils.min_filter inside (fav_run_next_image_flows): the whole temporal stage is
+        ONE kernel.  flow_bw [2,H,W] (dy,dx); flow_fw_uv [2,H,W] (u,v) -> occlusion test on the GPU, or cert_raw [H,W]."""
+        x, p, f = img.contiguous(), prev_rgb.contiguous(), flow_bw.contiguous()
+        fw = None if flow_fw_uv is None else flow_fw_uv.contiguous()
+        cr = None if cert_raw is None else cert_raw.contiguous()
+        H, W = x.shape[-2:]
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib.fav_run_next_image_flows(self._h, _lib.dptr(x), _lib.dptr(p), _lib.dptr(f), _lib.dptr(fw), _lib.dptr(cr),
+                                                     _lib.dptr(fill), _lib.dptr(flow_mask), H, W, int(min_filter_r), border_mode,
+                                                     _lib.dptr(out), _lib.stream_ptr()))
+        return out
+
+
 def build_model(opt) -> StyleNet:
     """M.build_model(opt) (models_video.lua:55): opt.arch, opt.padding_type, opt.tanh_constant, opt.use_instance_norm."""
     get = (lambda k, d: opt.get(k, d)) if isinstance(opt, dict) else (lambda k, d: getattr(opt, k, d))
@@ -124,6 +139,7 @@ def build_model(opt) -> StyleNet:
                     float(get("tanh_constant", 150.0)))
 
 
-def synthetic_model(style: str = "candy", arch: str = synth.DEFAULT_ARCH) -> StyleNet:
-    """Seeded random-init weights for a named style (no network => no released checkpoints)."""
-    return StyleNet(arch).load_state(synth.make_weights(arch, style))
+def synthetic_model(style: str = "candy", arch: str = synth.DEFAULT_ARCH, in_dim: int = 7) -> StyleNet:
+    """Seeded random-init weights for a named style (no network => no released checkpoints).
+    in_dim = 3: an image model (-model_img) of the same architecture."""
+    return StyleNet(arch, in_dim=in_dim).load_state(synth.make_weights(arch, style, in_dim))

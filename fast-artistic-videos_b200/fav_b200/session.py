@@ -30,6 +30,11 @@ class Session:
             _lib.lib.fav_session_destroy(h)
             self._h = None
 
+    def set_image_model(self, net_img: StyleNet = None):
+        """-model_img: single images go through a separate 3-channel image model (None = 'self')."""
+        _lib.check(_lib.lib.fav_session_set_image_model(self._h, net_img._h if net_img is not None else None))
+        self.net_img = net_img  # keep it alive
+
     def run_image(self, content_host, out_host):
         _lib.check(_lib.lib.fav_session_run_image(self._h, _hp(content_host), _hp(out_host)))
 

@@ -192,8 +192,10 @@ FAV_API int fav_net_layer_output(fav_net_t *net, int index, float *out, int *C, 
 FAV_API int fav_debug_set_trace(void *dev_buf, size_t bytes);
 FAV_API size_t fav_debug_trace_words(void);
 
-/* a-9  run_image (frame 1, model_img == nil)    fast_artistic_video_core.lua:121-158
- * content [3,H,W] RGB [0,1] -> out_rgb [3,H,W] = deprocess(model_vid(...))[1].
+/* a-9  run_image                               fast_artistic_video_core.lua:121-158
+ * content [3,H,W] RGB [0,1] -> out_rgb [3,H,W] = deprocess(model(...))[1].  A net created with in_dim = 7 is the video model
+ * fed cat(pre(img), fill, zeros) (model_img == nil, :133-138); in_dim = 3 is a separate image model fed pre(img) (:146, fill
+ * is ignored).  -scale_factor != 1 (bicubic image.scale of the un-vendored `image` rock, :127-129,150-152) is not built.
  * fav_run_image / fav_run_next_image enqueue the fused input kernel plus ONE CUDA-graph launch of the network (captured on
  * the second call for each distinct out_rgb pointer, 8 graphs cached per frame size): ping-pong a few output buffers.
  * One stream at a time per net (it owns the activation buffers), like model:forward in the reference. */
@@ -224,6 +226,9 @@ FAV_API int fav_run_next_image_flows(fav_net_t *net, const float *content, const
 typedef struct fav_session fav_session_t;
 FAV_API int fav_session_create(fav_net_t *net, int H, int W, fav_session_t **out);
 FAV_API void fav_session_destroy(fav_session_t *s);
+/* -model_img (fast_artistic_video.lua:24, core.lua:61-68,146): single images go through this 3-channel image model instead
+ * of the video model with an empty prior; NULL = "self".  The session does not own it. */
+FAV_API int fav_session_set_image_model(fav_session_t *s, fav_net_t *net_img);
 /* frame 1 (func_is_single_image): host content [3,H,W] fp32 -> host out [3,H,W] fp32 */
 FAV_API int fav_session_run_image(fav_session_t *s, const float *content_host, float *out_host);
 /* frames >= 2: host content, host flow [2,H,W] (dy,dx), host cert [H,W] fp32 in [0,1] BEFORE the

@@ -42,10 +42,11 @@ def _inorm(x, w, name):
 
 class NetOracle:
     def __init__(self, arch=synth.DEFAULT_ARCH, style="candy", dtype=torch.float64, weights=None,
-                 tanh_constant=150.0, operand_round=None):
-        self.specs = synth.parse_arch(arch)
+                 tanh_constant=150.0, operand_round=None, in_dim=7):
+        self.specs = synth.parse_arch(arch, in_dim)
         self.pad = synth.reflect_start_pad(self.specs)
-        wnp = weights if weights is not None else synth.make_weights(arch, style)
+        self.in_dim = in_dim
+        wnp = weights if weights is not None else synth.make_weights(arch, style, in_dim)
         self.w = {k: torch.from_numpy(v).to(dtype) for k, v in wnp.items()}
         self.dtype = dtype
         self.tanh_constant = tanh_constant
@@ -98,8 +99,11 @@ class NetOracle:
         return ((y + mean) / 255.0)[:, [2, 1, 0]]
 
     def run_image(self, content01: np.ndarray) -> np.ndarray:
-        """fast_artistic_video_core.lua:121-158 with model_img == nil, fill 'vgg-mean', scale_factor 1."""
+        """fast_artistic_video_core.lua:121-158, fill 'vgg-mean', scale_factor 1: model_img == nil (in_dim 7, :133-138) or a
+        separate image model on pre(img) alone (in_dim 3, :146)."""
         x7 = torch.from_numpy(pyoracle.first_frame_input(content01))[None]
+        if self.in_dim == 3:
+            x7 = x7[:, :3]
         return self.deprocess(self.forward(x7))[0].to(torch.float64).numpy()
 
     def run_next_image(self, content01, prev_rgb, flow_lua, cert, warp_mode=0) -> np.ndarray:

@@ -60,6 +60,71 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _stream_worker(rank, world, port, q):
+    import sys
+
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from fav_b200 import clips
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_clips, n_frames, chunk, H, W = 3, 7, 3, 4, 6
+        g = torch.Generator().manual_seed(5)
+        frames = torch.rand((n_clips, n_frames, 3, H, W), generator=g)
+        flows = torch.rand((n_clips, n_frames, 2, H, W), generator=g)
+        state, got = {}, {}
+
+        def load_chunk(c, f0, f1):
+            return [frames[c, f0:f1].clone(), flows[c, f0:f1].clone()]
+
+        def process_chunk(c, f0, inputs):  # recurrent stand-in for the GPU frame loop: needs frame order and its own state
+            fr, fl = inputs
+            outs = []
+            for i in range(fr.shape[0]):
+                prev = state.get(c, torch.zeros((3, H, W)))
+                prev = 0.5 * prev + fr[i] + fl[i].sum(0, keepdim=True)
+                state[c] = prev
+                outs.append(prev)
+            return torch.stack(outs)
+
+        def store_chunk(c, f0, out):
+            got[(c, f0)] = out.clone()
+
+        st = clips.stream_clips(n_clips, n_frames, chunk, [(3, H, W), (2, H, W)], (3, H, W), load_chunk, process_chunk, store_chunk)
+        if rank == 0:
+            ok = True
+            for c in range(n_clips):
+                prev = torch.zeros((3, H, W))
+                for i in range(n_frames):
+                    prev = 0.5 * prev + frames[c, i] + flows[c, i].sum(0, keepdim=True)
+                    f0 = (i // chunk) * chunk
+                    ok &= bool(torch.equal(got[(c, f0)][i - f0], prev))
+            ok &= st["bytes_in"] > 0 and len(got) == n_clips * 3
+            q.put(ok)
+        else:
+            assert not got and st["bytes_out"] > 0
+    finally:
+        dist.destroy_process_group()
+
+
+def test_streaming_data_plane_world2_gloo():
+    """BASELINE.json config 3's data plane (rank 0 feeds chunks of frames to the owning ranks, outputs come back) on CPU."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stream_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
 def test_assign_clips_partitions():
     from fav_b200 import clips
 

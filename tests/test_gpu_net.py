@@ -194,6 +194,45 @@ def test_full_size_720p_properties(net):
     assert torch.equal(o1, o2) and torch.equal(o1, a)
 
 
+def test_separate_image_model_for_single_images(tmp_path):
+    """-model_img (fast_artistic_video.lua:24 default is an image model; core.lua:61-68,146): frame 1 = model_img(pre(img)),
+    a 3-channel-input net; later frames = the video model.  C ABI, host-buffer session and the Lua-driver mirror vs the fp64
+    oracle."""
+    from fav_b200 import core, models_video, session
+    from oracle import net_oracle
+
+    H, W = 64, 96
+    img_net = models_video.synthetic_model("mosaic", synth.DEFAULT_ARCH, in_dim=3)
+    vid_net = models_video.synthetic_model("candy")
+    o_img = net_oracle.NetOracle(style="mosaic", dtype=torch.float64, in_dim=3)
+    o_vid = net_oracle.NetOracle(style="candy", dtype=torch.float64)
+    f1, f2 = synth.make_frame(H, W, 1), synth.make_frame(H, W, 2)
+    ref1 = o_img.run_image(f1)
+    out1 = img_net.run_image(T(f1))
+    assert np.abs(out1.cpu().numpy() - ref1).max() < TOL / 10
+    assert np.abs(out1.cpu().numpy() - o_vid.run_image(f1)).max() > 1e-2  # really a different model
+    # session: frame 1 through the image model, frame 2 through the video model with frame 1 as the prior
+    s = session.Session(vid_net, H, W)
+    s.set_image_model(img_net)
+    o1, o2 = torch.empty((3, H, W)).pin_memory(), torch.empty((3, H, W)).pin_memory()
+    bw, fw = synth.make_backward_flow(H, W, 2), synth.make_forward_flow(H, W, 2)
+    s.run_image(torch.from_numpy(f1).pin_memory(), o1)
+    s.run_next_image_flows(torch.from_numpy(f2).pin_memory(), torch.from_numpy(bw).pin_memory(), torch.from_numpy(fw).pin_memory(), o2, 7)
+    s.sync()
+    assert torch.equal(o1, out1.cpu())
+    ref2 = o_vid.run_next_image(f2, o1.numpy(), synth.checker_to_lua(bw), net_oracle.make_cert(H, W, 2))
+    assert np.abs(o2.numpy() - ref2).max() < TOL / 10
+    # the driver mirror (run_fast_neural_video with opt.model_img)
+    saved = {}
+    opt = dict(model_vid="synthetic:candy", model_img="synthetic:mosaic", num_frames=2, gpu=0)
+    core.run_fast_neural_video(
+        opt, lambda o, i, d: T(synth.make_frame(H, W, i)) if i <= 2 else None,
+        lambda o, i, d: torch.from_numpy(net_oracle.make_cert(H, W, i)).cuda(), None,
+        lambda o, i, d, c: core.FusedWarp(saved[i - 1], T(synth.checker_to_lua(synth.make_backward_flow(H, W, i)))),
+        lambda i, o: i == 1, lambda o, i, img, d=None: saved.__setitem__(i, img.clone()))
+    assert torch.equal(saved[1].cpu(), o1)
+
+
 def test_error_behaviour(net):
     from fav_b200 import _lib
 
