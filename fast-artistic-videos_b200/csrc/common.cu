@@ -1,6 +1,5 @@
 // common.cu -- error state, launch counter, device probing.
 #include "fav_common.cuh"
-#include <stdlib.h>
 
 namespace fav {
 static thread_local char g_err[512] = "";
@@ -11,11 +10,6 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
-}
-
-bool pdl_enabled() {
-  static const bool on = getenv("FAV_NO_PDL") == nullptr;
-  return on;
 }
 
 int require_device() {

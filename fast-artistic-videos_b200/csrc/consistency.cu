@@ -65,9 +65,9 @@ int launch_consistency(const float *f1u, const float *f1v, const float *f2u, con
 //   2. Deriche-style IIR along X (one thread per row) then along Y (one thread per column, coalesced)
 //      for dxx, dyy, dxy -- the recurrences are sequential per line, as in the reference
 //   3. smallest eigenvalue (parallel)
-//   4. normalize(0,1) with the reference's `else if` min/max scan and the sequential fp32 avg: both are
-//      order-dependent in the reference, so they are evaluated in reference order by one thread
-//      (exactness over speed: this is a per-flow-pair preprocessing step, not the frame loop).
+//   4. normalize(0,1): the reference's `else if` min/max scan is evaluated EXACTLY by a parallel prefix-maximum scan
+//      (norm_*_kernel); the fp32 avg is order-dependent by rounding and stays one sequential FADD chain fed through
+//      shared memory by the rest of the block (avg_scan_kernel).
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float deriv3(float m1, float c0, float p1) {
   // sum over i=-1,0,1 of f[i]*v starting from 0 (CFilter.h:1510-1514): ((0 + -0.5*m1) + 0*c0) + 0.5*p1
@@ -163,19 +163,92 @@ __global__ void __launch_bounds__(256) eigen_kernel(const float *__restrict__ dx
   corners[i] = (temp2 < 0.0f) ? 0.0f : (float)__dsub_rn((double)temp, __dsqrt_rn((double)temp2));
 }
 
-// reference-order scans (single thread): CMatrix.h:721-736 then CMatrix.h:1245-1251
-__global__ void normalize_scan_kernel(const float *__restrict__ m, int64_t n, float *__restrict__ minmax) {
-  float cmin = 30000.f, cmax = -30000.f;
-  for (int64_t i = 0; i < n; ++i) {
-    float v = m[i];
-    if (v > cmax) cmax = v;
-    else if (v < cmin) cmin = v;
+// CMatrix::normalize's scan (CMatrix.h:721-736):  if (v > max) max = v; else if (v < min) min = v;
+// max is the plain maximum (floor -30000).  An element that raises the running maximum is NOT offered to the minimum, so
+//   min = min(30000, { v_i : v_i <= max(-30000, v_0..v_{i-1}) }):
+// the minimum over the elements that are not strict prefix maxima.  Prefix maximum is an associative scan, so the quirk
+// parallelises exactly: per-block maxima -> exclusive prefix maximum over the blocks -> per-block rescan with the carry.
+constexpr int kNormBlock = 1024;
+__global__ void __launch_bounds__(kNormBlock) norm_block_max_kernel(const float *__restrict__ m, int64_t n, float *__restrict__ bmax) {
+  const int64_t i = (int64_t)blockIdx.x * kNormBlock + threadIdx.x;
+  float v = i < n ? m[i] : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) bmax[blockIdx.x] = v;
   }
-  float t = __fsub_rn(cmax, cmin);
-  if (t == 0.f) t = 1.f;
-  else t = __fdiv_rn(1.0f, t);
-  minmax[0] = cmin;
-  minmax[1] = t;
+}
+// one block: carry[b] = max(-30000, maxima of blocks < b) (exclusive), carry[nb] = the total
+__global__ void __launch_bounds__(1024) norm_carry_kernel(const float *__restrict__ bmax, int nb, float *__restrict__ carry) {
+  __shared__ float part[1024];
+  const int per = (nb + 1023) / 1024, b0 = threadIdx.x * per;
+  float loc = -INFINITY;
+  for (int b = b0; b < min(nb, b0 + per); ++b) loc = fmaxf(loc, bmax[b]);
+  part[threadIdx.x] = loc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float run = -30000.f;  // CMatrix.h:722 initial maximum
+    for (int t = 0; t < 1024; ++t) { const float v = part[t]; part[t] = run; run = fmaxf(run, v); }
+    carry[nb] = run;
+  }
+  __syncthreads();
+  float run = part[threadIdx.x];
+  for (int b = b0; b < min(nb, b0 + per); ++b) { carry[b] = run; run = fmaxf(run, bmax[b]); }
+}
+__global__ void __launch_bounds__(kNormBlock) norm_block_min_kernel(const float *__restrict__ m, int64_t n, const float *__restrict__ carry,
+                                                                    float *__restrict__ bmin) {
+  const int64_t i = (int64_t)blockIdx.x * kNormBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float v = i < n ? m[i] : -INFINITY;
+  // exclusive prefix maximum inside the block: warp scan, then the warps' totals
+  float inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = fmaxf(inc, t); }
+  float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) exc = -INFINITY;
+  __shared__ float wtot[32], red[32];
+  if (lane == 31) wtot[w] = inc;
+  __syncthreads();
+  float before = carry[blockIdx.x];
+  for (int k = 0; k < w; ++k) before = fmaxf(before, wtot[k]);
+  const float pmax = fmaxf(before, exc);              // max(-30000, v_0 .. v_{i-1})
+  float cand = (i < n && !(v > pmax)) ? v : INFINITY;  // the `else if (v < min)` branch sees v only when it did not raise max
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cand = fminf(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+  if (lane == 0) red[w] = cand;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    cand = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cand = fminf(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+    if (threadIdx.x == 0) bmin[blockIdx.x] = cand;
+  }
+}
+__global__ void __launch_bounds__(1024) norm_final_kernel(const float *__restrict__ bmin, int nb, const float *__restrict__ carry,
+                                                          float *__restrict__ minmax) {
+  float v = INFINITY;
+  for (int b = threadIdx.x; b < nb; b += 1024) v = fminf(v, bmin[b]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float cmin = 30000.f;  // CMatrix.h:722 initial minimum
+    for (int k = 0; k < 32; ++k) cmin = fminf(cmin, red[k]);
+    const float cmax = carry[nb];
+    float t = __fsub_rn(cmax, cmin);  // :729-731
+    if (t == 0.f) t = 1.f;
+    else t = __fdiv_rn(1.0f, t);
+    minmax[0] = cmin;
+    minmax[1] = t;
+  }
 }
 __global__ void __launch_bounds__(256) normalize_apply_kernel(float *__restrict__ m, int64_t n,
                                                               const float *__restrict__ minmax) {
@@ -185,10 +258,38 @@ __global__ void __launch_bounds__(256) normalize_apply_kernel(float *__restrict_
   v = __fmul_rn(v, minmax[1]);
   m[i] = __fadd_rn(v, 0.0f);
 }
-__global__ void avg_scan_kernel(const float *__restrict__ m, int64_t n, float *__restrict__ avg) {
+// CMatrix::avg (CMatrix.h:1245-1251) adds the elements IN ORDER in fp32: every partial sum is rounded, so the result depends on
+// the order and no reassociated (parallel) sum reproduces it bit for bit.  It stays a sequential chain of dependent FADDs
+// (4 cycles each: ~2 ms per 720p frame, the floor of a single chain); what parallelises is everything around it: the block
+// streams the data through shared memory (double buffered, coalesced) so that the summing thread never waits for DRAM.
+constexpr int kAvgChunk = 4096;
+__global__ void __launch_bounds__(256) avg_scan_kernel(const float *__restrict__ m, int64_t n, float *__restrict__ avg) {
+  __shared__ float buf[2][kAvgChunk];
+  const int64_t nchunks = (n + kAvgChunk - 1) / kAvgChunk;
+  auto load = [&](int64_t c, int s) {
+    for (int i = threadIdx.x; i < kAvgChunk; i += 256) {
+      const int64_t g = c * kAvgChunk + i;
+      buf[s][i] = g < n ? m[g] : 0.f;
+    }
+  };
+  load(0, 0);
+  __syncthreads();
   float a = 0.f;
-  for (int64_t i = 0; i < n; ++i) a = __fadd_rn(a, m[i]);
-  *avg = __fdiv_rn(a, (float)(int)n);
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int s = (int)(c & 1);
+    if (threadIdx.x == 0) {
+      const int cnt = (int)min((int64_t)kAvgChunk, n - c * kAvgChunk);
+#pragma unroll 8
+      for (int i = 0; i < cnt; ++i) a = __fadd_rn(a, buf[s][i]);
+    } else if (c + 1 < nchunks) {
+      for (int i = threadIdx.x - 1; i < kAvgChunk; i += 255) {
+        const int64_t g = (c + 1) * kAvgChunk + i;
+        buf[s ^ 1][i] = g < n ? m[g] : 0.f;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *avg = __fdiv_rn(a, (float)(int)n);
 }
 
 }  // namespace fav
@@ -210,8 +311,9 @@ int fav_consistency_check(const float *flow1, const float *flow2, const float *s
 
 size_t fav_compute_corners_workspace(int Z, int W, int H) {
   (void)Z;
-  // dxx,dyy,dxy + 3 scratch planes + minmax
-  return (size_t)6 * W * H * sizeof(float) + 256;
+  // dxx,dyy,dxy + 3 scratch planes + minmax + the per-block maxima / carries / minima of the normalize scan
+  const size_t nb = ((size_t)W * H + 1023) / 1024;
+  return (size_t)6 * W * H * sizeof(float) + (8 + 3 * nb + 8) * sizeof(float) + 256;
 }
 
 int fav_compute_corners(const float *image, int Z, int W, int H, float rho, float *corners, float *avg_out,
@@ -241,12 +343,22 @@ int fav_compute_corners(const float *image, int Z, int W, int H, float rho, floa
   FAV_TRY(post_launch("computeCorners.iirY"));
   eigen_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(dxx, dxy, dyy, corners, n);
   FAV_TRY(post_launch("computeCorners.eigen"));
-  normalize_scan_kernel<<<1, 1, 0, st>>>(corners, n, minmax);
-  FAV_TRY(post_launch("normalize.scan"));
+  {  // normalize(0,1): min / max with the reference's `else if` scan, evaluated as an exact parallel prefix-maximum scan
+    const int nb = (int)ceil_div64(n, kNormBlock);
+    float *bmax = minmax + 8, *carry = bmax + nb, *bmin = carry + nb + 1;
+    norm_block_max_kernel<<<nb, kNormBlock, 0, st>>>(corners, n, bmax);
+    FAV_TRY(post_launch("normalize.blockmax"));
+    norm_carry_kernel<<<1, 1024, 0, st>>>(bmax, nb, carry);
+    FAV_TRY(post_launch("normalize.carry"));
+    norm_block_min_kernel<<<nb, kNormBlock, 0, st>>>(corners, n, carry, bmin);
+    FAV_TRY(post_launch("normalize.blockmin"));
+    norm_final_kernel<<<1, 1024, 0, st>>>(bmin, nb, carry, minmax);
+    FAV_TRY(post_launch("normalize.final"));
+  }
   normalize_apply_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(corners, n, minmax);
   FAV_TRY(post_launch("normalize.apply"));
   if (avg_out) {
-    avg_scan_kernel<<<1, 1, 0, st>>>(corners, n, avg_out);
+    avg_scan_kernel<<<1, 256, 0, st>>>(corners, n, avg_out);
     FAV_TRY(post_launch("avg.scan"));
   }
   return FAV_OK;

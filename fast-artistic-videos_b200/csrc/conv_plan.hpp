@@ -47,6 +47,7 @@ struct ConvDef {
   bool transposed = false;
   int cin_pad = 0, Cb = 0, Npad = 0, cout_pad8 = 0;
   int in_stride = 1;  // stride of the input sampling grid (2 for 'd' layers)
+  int tpad = 0;       // transposed: zero border the input operand needs (= -min tap offset over the sub-pixel phases)
   int out_mul = 1;    // 2 for transposed stride-2 (sub-pixel phases)
   std::vector<ConvPhase> phases;
   ConvPhase fold;    // transposed conv: all 4 phases in one tcgen05 job (phase-fold); phases[] stay for the comparator
@@ -300,18 +301,24 @@ static inline void build_phases(ConvDef &c) {
       for (int kx = 0; kx < c.k; ++kx) ph.taps.push_back(ConvTap{ky - c.pad, kx - c.pad, ky, kx});
     c.phases.push_back(std::move(ph));
   } else {
-    // out[2y+a, 2x+b]:  oy = 2*iy - pad + ky  =>  2*iy = 2*y + (a + pad - ky)
-    for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 2; ++b) {
+    // out[s*y+a, s*x+b]:  oy = s*iy - pad + ky  =>  s*iy = s*y + (a + pad - ky): one sub-pixel phase per (a, b), its taps are
+    // the filter taps with (a + pad - ky) divisible by the stride (stride 1, the fXs1 token: a plain convolution with the
+    // flipped filter)
+    const int sdiv = c.stride;
+    auto fdiv = [](int n, int d) { return n >= 0 ? n / d : -((-n + d - 1) / d); };
+    c.tpad = 0;
+    for (int a = 0; a < sdiv; ++a)
+      for (int b = 0; b < sdiv; ++b) {
         ConvPhase ph;
         ph.oy_off = a; ph.ox_off = b;
         for (int ky = 0; ky < c.k; ++ky) {
           int ny = a + c.pad - ky;
-          if (ny % 2) continue;
+          if (((ny % sdiv) + sdiv) % sdiv) continue;
           for (int kx = 0; kx < c.k; ++kx) {
             int nx = b + c.pad - kx;
-            if (nx % 2) continue;
-            ph.taps.push_back(ConvTap{ny / 2, nx / 2, ky, kx});
+            if (((nx % sdiv) + sdiv) % sdiv) continue;
+            ph.taps.push_back(ConvTap{fdiv(ny, sdiv), fdiv(nx, sdiv), ky, kx});
+            c.tpad = std::max(c.tpad, std::max(-fdiv(ny, sdiv), -fdiv(nx, sdiv)));
           }
         }
         c.phases.push_back(std::move(ph));
@@ -328,7 +335,7 @@ static inline void init_conv_def(ConvDef &c, const std::string &name, int cin, i
   c.Npad = std::max(16, round_up(cout, 16));
   c.cout_pad8 = round_up(cout, 8);
   c.in_stride = (!tr && stride == 2) ? 2 : 1;
-  c.out_mul = (tr && stride == 2) ? 2 : 1;
+  c.out_mul = tr ? stride : 1;
 }
 
 // packed tcgen05 weights of one phase: [group][chunk][hi|lo][step][k8 half][Npad][8] fp16 (as uint16 bit patterns)
@@ -391,7 +398,7 @@ static inline Operand operand_geometry(int C, int H, int W, const ConvDef *consu
   Operand o;
   o.C = C; o.Cb = round_up(C, 8) / 8; o.H = H; o.W = W;
   int pad = consumer ? consumer->pad : 0;
-  if (consumer && consumer->transposed) pad = 0;
+  if (consumer && consumer->transposed) pad = consumer->tpad;
   o.padT = o.padL = pad;
   o.Hs = H + 2 * pad + 2 + 4;  // +2: transposed-conv / mt=2 overrun, +4: row-fold units of 4 output rows
   o.parity = (consumer && consumer->in_stride == 2) ? 1 : 0;

@@ -61,7 +61,6 @@ __global__ void __launch_bounds__(kResThreads, 1) conv_res_kernel(const __grid_c
   ResShared *sh = reinterpret_cast<ResShared *>(b_base + kResSlots * kResChunkBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool nl = job.nl != 0;
-  pdl_launch_dependents();  // the next kernel of the frame may start its prologue as SMs drain
   if (job.trace && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -89,11 +88,9 @@ __global__ void __launch_bounds__(kResThreads, 1) conv_res_kernel(const __grid_c
 
   if (nl && warp >= 4 && warp < 12) {
     // ===== norm-on-load patch producers =====
-    // The input (raw tensor + statistics) is the previous kernel's output: wait for it here -- the weight producer, the TMEM
-    // allocation and the barrier set-up above did not have to.  The 8 producer warps then finalise mean / gamma * rstd / beta
-    // of the input channels (same arithmetic as in_apply_kernel: biased variance, eps inside the sqrt,
-    // InstanceNormalization.lua:39-50) and meet at a named barrier of their own.
-    pdl_wait();
+    // The 8 producer warps first finalise mean / gamma * rstd / beta of the input channels from the producer conv's fused
+    // statistics (same arithmetic as in_apply_kernel: biased variance, eps inside the sqrt, InstanceNormalization.lua:39-50)
+    // and meet at a named barrier of their own; weight producer and MMA warps are already running.
     {
       const int c = (int)threadIdx.x - 128;
       if (c < job.nl_C) {
@@ -165,7 +162,6 @@ __global__ void __launch_bounds__(kResThreads, 1) conv_res_kernel(const __grid_c
     }
   } else if (!nl && warp == 12) {
     // ===== patch producer (operand input): lane = (patch row, channel block, hi/lo) =====
-    pdl_wait();  // the operand is the previous kernel's output
     constexpr int kCopies = 4 * kResCbG * 2;  // per stage: 4 patch rows x 2 channel blocks x (hi, lo) = 16 <= 32 lanes
     const int ri = lane / (2 * kResCbG), cbi = (lane >> 1) % kResCbG, part = lane & 1;
     const uint4 *plane = part ? job.a_lo : job.a_hi;
@@ -340,7 +336,7 @@ int launch_conv_res(const ResJob &job_in, cudaStream_t st) {
                        "cudaFuncSetAttribute(conv_res)"));
     attr_set.fetch_or(bit, std::memory_order_release);
   }
-  FAV_TRY(check_cuda(launch_pdl(conv_res_kernel, dim3(job.grid), dim3(kResThreads), smem, st, true, job), "launch(conv_res)"));
+  conv_res_kernel<<<job.grid, kResThreads, smem, st>>>(job);
   return post_launch("conv_res");
 }
 

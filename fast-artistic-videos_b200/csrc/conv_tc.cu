@@ -120,7 +120,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   TcShared *sh = reinterpret_cast<TcShared *>(b_base + nslots * chunk_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  pdl_launch_dependents();  // PDL (fav_common.cuh): the next kernel's prologue may overlap this kernel's tail
   if (job.trace && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -151,7 +150,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   // as in_apply_kernel: biased variance, eps inside the sqrt, InstanceNormalization.lua:39-50)
   float *nl_tab = reinterpret_cast<float *>(sh + 1) + (256 + 8 * 2 * 128);
   if (job.nl && (int)threadIdx.x < job.nl_C) {
-    pdl_wait();  // the statistics are the previous kernel's output
     const int c = threadIdx.x;
     const double mean = job.nl_sums[c] * job.nl_inv_count;
     double var = job.nl_sums[job.nl_C + c] * job.nl_inv_count - mean * mean;
@@ -173,7 +171,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // A warp owns whole (patch row, channel block) slabs: lanes run along x (coalesced 512-byte loads), up to
     // kNlPx float4 pairs in flight per lane, no per-pixel index arithmetic.
     // nl == 1: 8 producer warps (4, 8..14; one epilogue group); nl == 2: 4 producer warps (4, 12..14; two epilogue groups)
-    pdl_wait();  // the raw input is the previous kernel's output
     const int nlw = job.nl == 1 ? kNlWarps : 4;
     const int pw = warp == 4 ? 0 : (job.nl == 1 ? warp - 7 : warp - 11);
     const int pslab = job.pslab16, nslabs = job.nrows * job.CbG;
@@ -246,7 +243,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ===== A producer: the input patch of each (tile, channel group): one bulk copy per (patch row, channel block, hi/lo),
     // spread over the 32 lanes.  (Measured alternatives, all slower on B200 and removed: four producer warps sharing the
     // copies, a single elected lane with warp-uniform operands, one 4-D cp.async.bulk.tensor per plane -- DESIGN.md 9.3.) =====
-    pdl_wait();  // the operand is the previous kernel's output (weights, TMEM, barriers did not have to wait)
     const int per_row = job.CbG * job.nseg * 2;  // copies per patch row (x2: hi, lo)
     const int ncopies = job.nrows * per_row;
     uint32_t stage_tx = 0;
@@ -786,7 +782,7 @@ int launch_conv_tc(const ConvJob &job_in, int num_sms, cudaStream_t st) {
     attr_set.fetch_or(bit, std::memory_order_release);
   }
   int grid = job.ntiles < num_sms ? job.ntiles : num_sms;
-  FAV_TRY(check_cuda(launch_pdl(conv_tc_kernel, dim3(grid), dim3(kThreads), smem, st, true, job), "launch(conv_tc)"));
+  conv_tc_kernel<<<grid, kThreads, smem, st>>>(job);
   return post_launch("conv_tc");
 }
 

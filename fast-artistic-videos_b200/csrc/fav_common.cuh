@@ -7,7 +7,6 @@
 #include <stdarg.h>
 #include <atomic>
 #include <string>
-#include <utility>
 
 #include "../../include/fav.h"
 
@@ -45,28 +44,6 @@ int require_device();  // FAV_ERR_NO_DEVICE when no GPU: there is no CPU fallbac
       return FAV_ERR_INVALID;         \
     }                                 \
   } while (0)
-
-// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
-// Inside a frame the ~27 kernels of the net run back to back on one stream / in one graph.  With PDL a kernel's CTAs may be
-// scheduled while the previous kernel is still draining: its prologue (barrier init, TMEM allocation, constant loads, weight
-// prefetch) overlaps the predecessor's tail, and everything that reads the predecessor's output sits behind pdl_wait().
-// Rule: a kernel launched through launch_pdl(..., pdl = true) MUST execute pdl_wait() before its first dependent access.
-bool pdl_enabled();  // FAV_NO_PDL=1 switches it off (common.cu)
-#ifdef __CUDACC__
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args &&...args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
-}
-#endif
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

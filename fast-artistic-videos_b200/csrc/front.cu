@@ -14,6 +14,8 @@
 // All arithmetic uses explicit round-to-nearest intrinsics in the reference's evaluation order.  The bilinear
 // blend reproduces the FMA contraction nvcc applies to the reference kernel (bilinear_ref_blend, fav_common.cuh), so the
 // warp is bit-identical to the reference's own CUDA kernel compiled for sm_100a (oracle/ref_warp) and to the CPU oracle.
+#include <algorithm>
+
 #include "fav_common.cuh"
 #include "net_layout.cuh"
 #include "occlusion.cuh"
@@ -305,7 +307,7 @@ __device__ __forceinline__ void temporal_pixels(
 }
 
 template <int VEC, bool FIRST, bool PACK = false>
-__global__ void __launch_bounds__(256) temporal_input_kernel(
+__global__ void __launch_bounds__(256, 2) temporal_input_kernel(
     const float *__restrict__ content, const float *__restrict__ prev, const float *__restrict__ flow,
     const float *__restrict__ cert, const float *__restrict__ fill, const float *__restrict__ flow_mask,
     float *__restrict__ out7, int H, int W, int border_mode, Operand dst = Operand(), int R = 0) {
@@ -331,16 +333,16 @@ __global__ void __launch_bounds__(256) temporal_input_kernel(
 // ---- the WHOLE temporal-consistency stage in one kernel ---------------------------------------------------------------
 // north star: "BilinearSamplerBDHW warp of the previous stylized frame by the supplied optical flow, consistencyChecker's
 // forward/backward-flow occlusion test, and the channel concat ... become one fused sm_100a kernel ... that writes the
-// 7-channel tensor the net consumes directly".  Per 64 x 16 pixel tile:
+// 7-channel tensor the net consumes directly".  Per 64 x 32 pixel tile (256 threads, 2 x 4 pixels each):
 //   1. certainty of the tile + a (r/2)-pixel halo into shared memory: MODE 0 = the occlusion test itself
 //      (consistencyChecker.cpp:99-125, 3-argument mode; flow1 = the backward flow that also drives the warp, flow2 = forward
 //      flow) -- halo pixels are recomputed instead of exchanged; MODE 1 = a given certainty plane (func_load_cert output);
 //   2. utils.min_filter (utils.lua:161-169) as a separable r x r minimum in shared memory (pad cells = +inf);
 //   3. warp + preprocess + mask + concat of the thread's 4 pixels (temporal_pixels above).
 // Bit-identical to consistency_kernel -> min_filter_kernel -> temporal_input_kernel (tests/test_gpu_front.py).
-constexpr int TS_TX = 64, TS_TY = 16, TS_MAXP = 7;
+constexpr int TS_TX = 64, TS_TY = 32, TS_MAXP = 7;  // 64 x 32 tile: the 3-pixel halo costs 1.30x certainty evaluations (1.50x at 64 x 16)
 template <bool PACK, int MODE>
-__global__ void __launch_bounds__(256) temporal_stage_kernel(
+__global__ void __launch_bounds__(256, 2) temporal_stage_kernel(
     const float *__restrict__ content, const float *__restrict__ prev, const float *__restrict__ flow,
     const float *__restrict__ fw_u, const float *__restrict__ fw_v, const float *__restrict__ cert_raw,
     const float *__restrict__ fill, const float *__restrict__ flow_mask, float *__restrict__ out7,
@@ -375,24 +377,28 @@ __global__ void __launch_bounds__(256) temporal_stage_kernel(
     }
     __syncthreads();
   }
-  const int tx4 = (threadIdx.x & 15) * 4, ty = threadIdx.x >> 4;
-  const int x0 = bx + tx4, y = by + ty;
-  if (x0 >= W || y >= H) return;
-  float c[4];
+  const int tx4 = (threadIdx.x & 15) * 4, x0 = bx + tx4;
+  if (x0 >= W) return;
+#pragma unroll 1
+  for (int ty = threadIdx.x >> 4; ty < TS_TY; ty += 16) {
+    const int y = by + ty;
+    if (y >= H) return;
+    float c[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (p > 0) {
-      float m = INFINITY;
-      for (int d = 0; d < r; ++d) m = fminf(m, rm[ty + d][tx4 + i]);
-      // MulConstant(-1), AddConstant(1), pool, MulConstant(-1), AddConstant(1)  (utils.lua:162-167)
-      const float t = __fadd_rn(__fmul_rn(m, -1.0f), 1.0f);
-      c[i] = __fadd_rn(__fmul_rn(t, -1.0f), 1.0f);
-    } else {
-      c[i] = cs[ty][tx4 + i];
+    for (int i = 0; i < 4; ++i) {
+      if (p > 0) {
+        float m = INFINITY;
+        for (int d = 0; d < r; ++d) m = fminf(m, rm[ty + d][tx4 + i]);
+        // MulConstant(-1), AddConstant(1), pool, MulConstant(-1), AddConstant(1)  (utils.lua:162-167)
+        const float t = __fadd_rn(__fmul_rn(m, -1.0f), 1.0f);
+        c[i] = __fadd_rn(__fmul_rn(t, -1.0f), 1.0f);
+      } else {
+        c[i] = cs[ty][tx4 + i];
+      }
     }
+    if (cert_out) *reinterpret_cast<float4 *>(cert_out + (int64_t)y * W + x0) = make_float4(c[0], c[1], c[2], c[3]);
+    temporal_pixels<4, false, PACK>(content, prev, flow, c, fill, flow_mask, out7, H, W, x0, y, border_mode, dst, R);
   }
-  if (cert_out) *reinterpret_cast<float4 *>(cert_out + (int64_t)y * W + x0) = make_float4(c[0], c[1], c[2], c[3]);
-  temporal_pixels<4, false, PACK>(content, prev, flow, c, fill, flow_mask, out7, H, W, x0, y, border_mode, dst, R);
 }
 
 // run_[next_]image: the fused input written straight into the first operand of the network (no out7 round trip)
@@ -527,11 +533,54 @@ __global__ void __launch_bounds__(256) vgg_kernel(const float *__restrict__ in, 
   }
 }
 
+// ---- f-4: temporal loss of -evaluate (fast_artistic_video.lua:128-151) -------------------------------------------------
+// nn.MSECriterion(cmul(warp(prev_stylized, flow_eval), cert), cmul(stylized, cert)): one fused pass (warp + mask + squared
+// difference + reduction) instead of a warp, two cmuls and the criterion; the sum of squares is accumulated in double.
+__global__ void __launch_bounds__(256) temporal_mse_kernel(const float *__restrict__ prev, const float *__restrict__ cur,
+                                                           const float *__restrict__ flow, const float *__restrict__ cert,
+                                                           int H, int W, int border_mode, double *__restrict__ sum) {
+  const int64_t HW = (int64_t)H * W;
+  double acc = 0.0;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < HW; o += (int64_t)gridDim.x * blockDim.x) {
+    const int y = (int)(o / W), x = (int)(o - (int64_t)y * W);
+    const Sample s = make_sample(__ldg(flow + o), __ldg(flow + HW + o), y, x, H, W, border_mode);
+    const float c = __ldg(cert + o);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float a = __fmul_rn(sample_plane(s, prev + k * HW, W, 1, border_mode), c), b = __fmul_rn(__ldg(cur + k * HW + o), c);
+      const float d = __fsub_rn(a, b);
+      acc += (double)d * (double)d;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(sum, t);
+  }
+}
+
 }  // namespace fav
 
 using namespace fav;
 
 extern "C" {
+
+int fav_temporal_mse(const float *prev, const float *cur, const float *flow, const float *cert, int H, int W, int border_mode,
+                     double *sum_dev, void *stream) {
+  FAV_REQUIRE(prev && cur && flow && cert && sum_dev, "temporal_mse: null tensor");
+  FAV_REQUIRE(H > 0 && W > 0, "temporal_mse: empty frame");
+  FAV_REQUIRE(border_mode == FAV_BORDER_PER_TAP || border_mode == FAV_BORDER_PAD_PIXEL, "bad border_mode");
+  FAV_TRY(require_device());
+  const int64_t HW = (int64_t)H * W;
+  const int blocks = (int)std::min<int64_t>(ceil_div64(HW, 256), 148 * 8);
+  temporal_mse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(prev, cur, flow, cert, H, W, border_mode, sum_dev);
+  return post_launch("temporal_mse");
+}
 
 int fav_bilinear_sampler_bdhw_update_output(const float *img, const int64_t img_size[4], const int64_t img_stride[4],
                                             const float *grid, const int64_t grid_size[4],

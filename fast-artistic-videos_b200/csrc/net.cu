@@ -48,7 +48,10 @@ struct InDef {
 
 // arch-level program
 struct SpecOp {
-  int kind;  // 0 conv(+in+relu), 1 res block, 2 nearest upsampling (+in+relu)
+  int kind;  // 0 conv(+in+relu), 1 conv block: two 3x3 convs + IN (RX: + ShaveImage / Identity skip; CX: no skip, ReLU after),
+             // 2 nearest upsampling (+in+relu)
+  bool skip = true;   // kind 1: residual (RX) or plain (CX) block
+  int shave = 2;      // kind 1: ShaveImage(2) ('reflect-start') or Identity ('zero') on the skip branch
   int scale = 1;
   int conv[2] = {-1, -1};
   int inorm[2] = {-1, -1};
@@ -61,6 +64,7 @@ struct PlanStep {
   int conv = -1, inorm = -1;
   int src = -1, dst = -1, skip = -1;
   int relu = 0;
+  int shave = 2;
   RawTensor raw;
   std::vector<ConvJob> tc;
   std::vector<ResJob> res;   // non-empty: the tcgen05 path of this step is conv_res.cu (raw output planar)
@@ -100,6 +104,7 @@ using namespace fav;
 
 struct fav_net {
   std::string arch;
+  std::string padding_type = "reflect-start";
   float tanh_c = 150.f;
   int in_dim = 7;
   int reflect_pad = 0;
@@ -410,8 +415,9 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
       const ConvDef *consumer = pos + 1 < order.size() ? &net->convs[order[pos + 1]] : nullptr;
       FAV_TRY(make_operand(*pl, c.cout, ho, wo, consumer, &ns.dst));
       if (op.kind == 1) {
-        ns.relu = i == 0 ? 1 : 0;
-        ns.skip = i == 1 ? block_in : -1;  // ShaveImage(2) of the block input (models_video.lua:47-48)
+        ns.relu = i == 0 ? 1 : (op.relu ? 1 : 0);               // CX: needs_relu after the block (models_video.lua:108)
+        ns.skip = (i == 1 && op.skip) ? block_in : -1;          // RX: ShaveImage(2) / Identity of the block input (:46-50)
+        ns.shave = op.shave;
       } else {
         ns.relu = op.relu ? 1 : 0;
       }
@@ -498,7 +504,7 @@ static int run_plan(fav_net *net, Plan &pl, const float *in7, float *out3, int f
       }
       // InstanceNormalization.lua:21,39: eps = 1e-5, statistics over H*W of each (n, c)
       FAV_TRY(begin(3, (s.skip >= 0 ? 12.0 : 8.0) * elems, n.name + ".apply"));
-      FAV_TRY(launch_in_apply(s.raw, sums, n.d_gamma, n.d_beta, 1e-5f, s.relu, s.skip >= 0 ? &pl.ops[s.skip] : nullptr, 2,
+      FAV_TRY(launch_in_apply(s.raw, sums, n.d_gamma, n.d_beta, 1e-5f, s.relu, s.skip >= 0 ? &pl.ops[s.skip] : nullptr, s.shave,
                               pl.ops[s.dst], st));
       FAV_TRY(end());
     }
@@ -564,13 +570,19 @@ extern "C" {
 int fav_net_create(const char *arch, const char *padding_type, float tanh_constant, int in_dim, fav_net_t **out) {
   FAV_REQUIRE(arch && out, "fav_net_create: null argument");
   FAV_REQUIRE(in_dim >= 1 && in_dim <= 8, "fav_net_create: in_dim must be in [1,8] (video nets use 7, image nets 3)");
-  if (padding_type && strcmp(padding_type, "reflect-start") != 0) {
-    set_error("padding_type '%s' is not supported: the released video models use 'reflect-start' "
-              "(train_video.lua:25)", padding_type);
+  // models_video.lua:13-19,27-31,46-50,71-79: 'reflect-start' (every released video model; train_video.lua:25) = unpadded
+  // residual convs + ShaveImage(2) + one lazily inserted reflection pad (train_video.lua:319-324); 'zero' = residual convs with
+  // zero padding 1 and an Identity skip.  'reflect' / 'replicate' put a padding module in front of EVERY convolution and 'none'
+  // returns a smaller frame than it was given: not built (no released model uses them).
+  const std::string ptype = padding_type ? padding_type : "reflect-start";
+  if (ptype != "reflect-start" && ptype != "zero") {
+    set_error("padding_type '%s' is not supported (supported: 'reflect-start', the released video models' setting "
+              "(train_video.lua:25), and 'zero')", ptype.c_str());
     return FAV_ERR_UNSUPPORTED;
   }
+  const bool zero_pad = ptype == "zero";
   std::unique_ptr<fav_net> net(new fav_net());
-  net->arch = arch; net->tanh_c = tanh_constant; net->in_dim = in_dim;
+  net->arch = arch; net->tanh_c = tanh_constant; net->in_dim = in_dim; net->padding_type = ptype;
   // tokenise (models_video.lua:56)
   std::vector<std::string> toks;
   {
@@ -616,18 +628,27 @@ int fav_net_create(const char *arch, const char *padding_type, float tanh_consta
       op.inorm[0] = add_in(net.get(), name + ".n", next);
       needs_bn = false;
       scale /= sc;
-    } else if (c0 == 'R') {  // RX  :109-114
+    } else if (c0 == 'f' && v.size() >= 6 && v[2] == 's' && v[4] == '-') {  // fXsY-Z  :81-89  SpatialFullConvolution(f,f,s,s,p,p,s-1,s-1)
+      int f = v[1] - '0', st = v[3] - '0';
+      next = atoi(v.c_str() + 5);
+      FAV_REQUIRE(f % 2 == 1 && (st == 1 || st == 2) && next > 0, "bad arch token '%s'", v.c_str());
+      op.conv[0] = add_conv(net.get(), name, prev, next, f, st, (f - 1) / 2, true, st - 1);
+      scale /= st;
+    } else if (c0 == 'R' || c0 == 'C') {  // RX :109-114 residual block; CX :103-108 the same conv block without the skip
       next = atoi(v.c_str() + 1);
-      FAV_REQUIRE(next == prev, "residual block R%d needs %d input channels (got %d)", next, next, prev);
+      FAV_REQUIRE(next == prev, "block %c%d needs %d input channels (got %d)", c0, next, next, prev);
+      const int bp = zero_pad ? 1 : 0;  // build_conv_block :12-20
       op.kind = 1;
-      op.conv[0] = add_conv(net.get(), name + ".c1", prev, next, 3, 1, 0, false, 0);
+      op.skip = c0 == 'R';
+      op.shave = zero_pad ? 0 : 2;      // ShaveImage(2) vs Identity :46-50
+      op.conv[0] = add_conv(net.get(), name + ".c1", prev, next, 3, 1, bp, false, 0);
       op.inorm[0] = add_in(net.get(), name + ".n1", next);
-      op.conv[1] = add_conv(net.get(), name + ".c2", next, next, 3, 1, 0, false, 0);
+      op.conv[1] = add_conv(net.get(), name + ".c2", next, next, 3, 1, bp, false, 0);
       op.inorm[1] = add_in(net.get(), name + ".n2", next);
-      needs_bn = false; op.relu = false;
-      shrink += 4 * scale;
+      needs_bn = false; op.relu = c0 == 'C';  // :107-108, :113-114
+      if (!zero_pad) shrink += 4 * scale;
     } else {
-      set_error("arch token '%s' is not supported by the sm_100a path (supported: cXsY-Z, dX, uX, UX, RX)", v.c_str());
+      set_error("arch token '%s' is not supported by the sm_100a path (supported: cXsY-Z, fXsY-Z, dX, uX, UX, CX, RX)", v.c_str());
       return FAV_ERR_UNSUPPORTED;
     }
     if (op.last) { needs_bn = false; op.relu = false; }  // :117-120
@@ -636,7 +657,8 @@ int fav_net_create(const char *arch, const char *padding_type, float tanh_consta
     prev = next;
   }
   FAV_REQUIRE(prev == 3, "the last layer must produce 3 channels (got %d)", prev);
-  FAV_REQUIRE(net->ops.back().kind == 0, "the last arch token must be a convolution");
+  FAV_REQUIRE(net->ops.back().kind == 0 && !net->convs[net->ops.back().conv[0]].transposed,
+              "the last arch token must be a (non-transposed) convolution");
   FAV_REQUIRE(shrink == std::floor(shrink) && ((int)shrink) % 2 == 0, "unsupported shrink %f", shrink);
   net->reflect_pad = (int)shrink / 2;  // train_video.lua:319-324
   *out = net.release();

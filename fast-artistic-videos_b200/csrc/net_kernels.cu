@@ -110,8 +110,6 @@ __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const doub
   __shared__ float s_mean[8], s_scale[8], s_beta[8];
   const int xbase = blockIdx.x * (128 * kApplyIter) + threadIdx.x;
   const int y = blockIdx.y, cb = blockIdx.z;
-  pdl_launch_dependents();  // PDL (fav_common.cuh)
-  pdl_wait();               // raw tensor and statistics are the previous kernel's output
   // 1. every streaming load of the thread is requested first (they do not depend on the statistics): the per-block
   //    finalisation below (dependent global loads + double sqrt / divide on 8 threads) then runs in their shadow
   float v[kApplyIter][8];
@@ -175,8 +173,8 @@ int launch_in_apply(const RawTensor &raw, const double *sums, const float *gamma
                     const Operand *skip, int shave, const Operand &dst, cudaStream_t st) {
   dim3 grid(ceil_div(raw.W, 128 * kApplyIter), raw.H, raw.C / 8);
   Operand sk = skip ? *skip : Operand();
-  FAV_TRY(check_cuda(launch_pdl(in_apply_kernel, grid, dim3(128), 0, st, true, raw, sums, gamma, beta, 1.0 / ((double)raw.H * raw.W),
-                                (double)eps, relu, sk, skip ? 1 : 0, shave, dst), "launch(in_apply)"));
+  in_apply_kernel<<<grid, 128, 0, st>>>(raw, sums, gamma, beta, 1.0 / ((double)raw.H * raw.W), (double)eps, relu, sk,
+                                        skip ? 1 : 0, shave, dst);
   return post_launch("in_apply");
 }
 

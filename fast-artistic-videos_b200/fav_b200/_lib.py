@@ -57,6 +57,7 @@ SIGNATURES = {
     "fav_temporal_input": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     "fav_temporal_stage": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     "fav_first_frame_input": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, _fp]),
+    "fav_temporal_mse": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp]),
     "fav_consistency_check": (C.c_int, [_fp, _fp, _fp, C.c_float, _fp, _fp, C.c_int, C.c_int, _fp]),
     "fav_compute_corners_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "fav_compute_corners": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp, _fp]),

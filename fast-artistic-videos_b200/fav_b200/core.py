@@ -10,7 +10,8 @@ Differences that are design, not semantics:
     (weights 1,0,0,0);
   * `generate_fill` (:108-117) draws torch.rand even when the result is discarded ('vgg-mean'); here nothing is drawn
     for 'vgg-mean' and 'uniform-random' draws on the GPU (the reference RNG stream is not reproducible anyway).
--evaluate (perceptual / temporal losses, :76-98,214-239) needs VGG-16 weights and is out of scope.
+-evaluate (:76-98,214-239): the temporal loss is computed (utils.temporal_loss, one fused kernel); the perceptual
+style / content terms need the VGG-16 loss network (models/vgg16.t7, no network here) and are reported as NaN.
 """
 from __future__ import annotations
 
@@ -58,8 +59,7 @@ def run_fast_neural_video(opt, func_load_image, func_load_cert, func_eval, func_
     dtype = "torch.CudaTensor"  # utils.setup_gpu (utils.lua:43-66): this implementation is GPU-only
     dev = torch.device("cuda", int(_opt(opt, "gpu", 0)) if int(_opt(opt, "gpu", 0)) >= 0 else 0)
     torch.cuda.set_device(dev)
-    if _opt(opt, "evaluate", False):
-        raise _lib.FavError(_lib.FAV_ERR_UNSUPPORTED, "-evaluate needs the VGG-16 loss network (out of scope)")
+    evaluate = bool(_opt(opt, "evaluate", False))  # :76-98,214-239 -- see the evaluation block at the end of the loop
     if float(_opt(opt, "scale_factor", 1)) != 1:
         raise _lib.FavError(_lib.FAV_ERR_UNSUPPORTED, "-scale_factor != 1 (bicubic image.scale) is not on the GPU path")
     model = model_vid if model_vid is not None else load_model(_opt(opt, "model_vid"), _opt(opt, "arch", synth.DEFAULT_ARCH))
@@ -104,6 +104,7 @@ def run_fast_neural_video(opt, func_load_image, func_load_cert, func_eval, func_
         print("Elapsed time for stylizing frame:%f" % (time.perf_counter() - t1))
         return out
 
+    eval_tabl, eval_sum = [], []
     backward = bool(_opt(opt, "backward", False))
     num_frames = int(_opt(opt, "num_frames", 9999))
     start_idx = num_frames - 1 if backward else int(_opt(opt, "continue_with", 1))  # :189-191
@@ -123,4 +124,20 @@ def run_fast_neural_video(opt, func_load_image, func_load_cert, func_eval, func_
             cert = utils.min_filter(cert.to(dev).reshape(1, H, W), r) if r > 1 else cert.to(dev)  # :207
             nxt = run_next_image(H, W, img, cert.reshape(1, 1, H, W), i)
         func_save_image(opt, i, nxt, dtype)
+        if evaluate:
+            # core.lua:214-226: func_eval -> { style_loss, content_loss, temporal_loss }.  The perceptual terms need the VGG-16
+            # loss network (models/vgg16.t7, not available offline): func_eval is called with evaluate_image = None and reports
+            # NaN for them; the temporal term is computed (fused warp + mask + MSE kernel).
+            numbers, n_num = func_eval(opt, i, None, dtype)
+            for j in range(n_num):
+                if j >= len(eval_tabl):
+                    eval_tabl.append([]); eval_sum.append(0.0)
+                eval_tabl[j].append(numbers[j]); eval_sum[j] += numbers[j]
         i += inc
+    if evaluate:  # :231-240: one ';'-joined line per quantity, then the per-frame averages (sum / opt.num_frames)
+        with open(_opt(opt, "evaluation_file", "evaluation.txt"), "a") as fh:
+            for row in eval_tabl:
+                fh.write(";".join(repr(float(v)) for v in row) + "\n")
+            for t in eval_sum:
+                fh.write(repr(float(t) / num_frames) + "\n")
+        print("File written")

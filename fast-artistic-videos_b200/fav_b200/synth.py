@@ -54,8 +54,12 @@ def parse_arch(arch: str, in_dim: int = 7):
             spec = dict(kind="fullconv", cin=prev, cout=nxt, k=3, stride=2, pad=1, adj=1)
         elif c0 == "R":  # :109-114
             nxt = int(v[1:])
-            spec = dict(kind="res", cin=prev, cout=nxt, k=3, stride=1, pad=0)
+            spec = dict(kind="res", cin=prev, cout=nxt, k=3, stride=1, pad=0, skip=True)
             needs_bn = needs_relu = False
+        elif c0 == "C":  # :103-108: the conv block of a residual block without the skip, ReLU after it
+            nxt = int(v[1:])
+            spec = dict(kind="res", cin=prev, cout=nxt, k=3, stride=1, pad=0, skip=False)
+            needs_bn = False
         else:
             raise ValueError(f"unsupported arch token {v!r}")
         if i == len(toks) - 1:  # :117-120
@@ -67,8 +71,10 @@ def parse_arch(arch: str, in_dim: int = 7):
     return specs
 
 
-def reflect_start_pad(specs) -> int:
-    """Padding that train_video.lua:319-324 lazily inserts as layer 1 (reflect-start)."""
+def reflect_start_pad(specs, padding_type: str = "reflect-start") -> int:
+    """Padding that train_video.lua:319-324 lazily inserts as layer 1 (reflect-start): half of what the unpadded blocks shave."""
+    if padding_type != "reflect-start":
+        return 0
     # track (scale numerator) shrink in input pixels: each res block loses 4 px at its resolution
     scale = 1.0
     shrink = 0.0

@@ -32,6 +32,19 @@ def min_filter(batch: torch.Tensor, r: int, dtype=None) -> torch.Tensor:
     return out
 
 
+def temporal_loss(prev_stylized: torch.Tensor, stylized: torch.Tensor, flow: torch.Tensor, cert: torch.Tensor,
+                  dtype: str = "torch.CudaTensor") -> float:
+    """The temporal term of -evaluate (fast_artistic_video.lua:128-151):
+    nn.MSECriterion(cmul(warp_image(prev_stylized, flow), cert), cmul(stylized, cert)) as ONE fused kernel."""
+    p, c, f, m = prev_stylized.contiguous(), stylized.contiguous(), flow.contiguous(), cert.contiguous().reshape(-1)
+    H, W = c.shape[-2:]
+    acc = torch.zeros((1,), dtype=torch.float64, device=c.device)
+    mode = _lib.BORDER_PER_TAP if dtype == "torch.CudaTensor" else _lib.BORDER_PAD_PIXEL
+    _lib.check(_lib.lib.fav_temporal_mse(_lib.dptr(p), _lib.dptr(c), _lib.dptr(f), _lib.dptr(m), H, W, mode, _lib.dptr(acc),
+                                         _lib.stream_ptr()))
+    return float(acc.item()) / (3.0 * H * W)
+
+
 def file_exists(name: str) -> bool:  # utils.lua:68-71
     return os.path.isfile(name)
 

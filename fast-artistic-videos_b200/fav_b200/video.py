@@ -31,6 +31,9 @@ def build_parser():
     a("-create_inconsistent", action="store_true")
     a("-gpu", type=int, default=0); a("-backend", default="cuda"); a("-use_cudnn", type=int, default=1)
     a("-cudnn_benchmark", type=int, default=0); a("-evaluate", action="store_true")
+    a("-evaluation_file", default="evaluation.txt"); a("-flow_pattern_eval", default=""); a("-occlusions_pattern_eval", default="")
+    a("-invert_occlusion_eval", action="store_true"); a("-fix_occlusions_eval", action="store_true"); a("-backward_eval", action="store_true")
+    a("-model_img_arch", default="")
     a("-arch", default=core.synth.DEFAULT_ARCH)
     return p
 
@@ -92,6 +95,26 @@ class Driver:
         flow = torch.from_numpy(flowFileLoader.load(flowFileName)).cuda()
         return core.FusedWarp(self.last_frame_stylized, flow), None
 
+    def func_load_flow_cert_eval(self, opt, i, dtype):  # :114-126
+        flow = torch.from_numpy(flowFileLoader.load(getFormatedFlowFileName(opt.flow_pattern_eval, i - 1, i))).cuda()
+        cert = load_image(getFormatedFlowFileName(opt.occlusions_pattern_eval, i - 1, i), 1).cuda()
+        if opt.invert_occlusion_eval:
+            cert = 1.0 - cert
+        if opt.fix_occlusions_eval:
+            self.fix_occlusions(flow, cert)
+        return flow, cert
+
+    def func_eval(self, opt, i, func_percept_loss, dtype):  # :128-151
+        nan = float("nan")  # style / content loss: the VGG-16 loss network is not available (core.py)
+        if i > 1:
+            flow_eval, cert_eval = self.func_load_flow_cert_eval(opt, i, dtype)
+            if opt.backward_eval:
+                t = utils.temporal_loss(self.last_frame_stylized, self.prev_last_frame_stylized, flow_eval, cert_eval)
+            else:
+                t = utils.temporal_loss(self.prev_last_frame_stylized, self.last_frame_stylized, flow_eval, cert_eval)
+            return [nan, nan, t], 3
+        return [nan, nan, 0.0], 3
+
     def func_save_image(self, opt, i, img, dtype=None):  # :160-170
         out_path = "%s-%05d.png" % (opt.output_prefix, i)
         print("Writing output image to " + out_path)
@@ -114,7 +137,7 @@ def main(argv=None):
     if not opt.create_inconsistent and (opt.flow_pattern == "" or opt.occlusions_pattern == ""):
         raise SystemExit("Must give -flow_pattern and -occlusions_pattern")  # :180-182
     d = Driver(opt)
-    core.run_fast_neural_video(opt, d.func_load_image, d.func_load_cert, None, d.func_make_last_frame_warped,
+    core.run_fast_neural_video(opt, d.func_load_image, d.func_load_cert, d.func_eval, d.func_make_last_frame_warped,
                                d.func_is_single_image, d.func_save_image)
     torch.cuda.synchronize()
 

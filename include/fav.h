@@ -109,6 +109,12 @@ FAV_API int fav_temporal_stage(const float *content, const float *prev, const fl
 FAV_API int fav_first_frame_input(const float *content, const float *fill, float *out7, int H, int W,
                                   void *stream);
 
+/* f-4  temporal loss of -evaluate               fast_artistic_video.lua:128-151 (func_eval)
+ * adds sum_{c,y,x} (warp(prev, flow)*cert - cur*cert)^2 to the DEVICE double *sum_dev (caller zeroes it);
+ * nn.MSECriterion's value is that sum / (3*H*W).  prev, cur [3,H,W]; flow [2,H,W] (dy,dx); cert [H,W]. */
+FAV_API int fav_temporal_mse(const float *prev, const float *cur, const float *flow, const float *cert, int H, int W,
+                             int border_mode, double *sum_dev, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a-11  checkConsistency                       consistencyChecker/consistencyChecker.cpp:80-134
  * flow1, flow2: [2,H,W] planar, plane 0 = u, plane 1 = v (readMiddlebury :16-36).

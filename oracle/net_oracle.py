@@ -42,9 +42,11 @@ def _inorm(x, w, name):
 
 class NetOracle:
     def __init__(self, arch=synth.DEFAULT_ARCH, style="candy", dtype=torch.float64, weights=None,
-                 tanh_constant=150.0, operand_round=None, in_dim=7):
+                 tanh_constant=150.0, operand_round=None, in_dim=7, padding_type="reflect-start"):
+        assert padding_type in ("reflect-start", "zero")  # models_video.lua:13-19,46-50
         self.specs = synth.parse_arch(arch, in_dim)
-        self.pad = synth.reflect_start_pad(self.specs)
+        self.pad = synth.reflect_start_pad(self.specs, padding_type)
+        self.block_pad = 1 if padding_type == "zero" else 0
         self.in_dim = in_dim
         wnp = weights if weights is not None else synth.make_weights(arch, style, in_dim)
         self.w = {k: torch.from_numpy(v).to(dtype) for k, v in wnp.items()}
@@ -79,12 +81,18 @@ class NetOracle:
                 x = self._fullconv(x, n, s)
             elif s["kind"] == "up":
                 x = F.interpolate(x, scale_factor=s["scale"], mode="nearest")
-            elif s["kind"] == "res":
-                y = self._conv(x, n + ".c1", 1, 0)
+            elif s["kind"] == "res":  # build_conv_block :10-39 (+ ConcatTable / CAddTable :41-53 for RX)
+                bp = self.block_pad
+                y = self._conv(x, n + ".c1", 1, bp)
                 y = torch.relu(_inorm(y, self.w, n + ".n1"))
-                y = self._conv(y, n + ".c2", 1, 0)
+                y = self._conv(y, n + ".c2", 1, bp)
                 y = _inorm(y, self.w, n + ".n2")
-                x = y + x[:, :, 2:-2, 2:-2]  # ShaveImage(2) + CAddTable
+                if not s.get("skip", True):
+                    x = y                                    # CX
+                elif bp:
+                    x = y + x                                # Identity skip ('zero')
+                else:
+                    x = y + x[:, :, 2:-2, 2:-2]              # ShaveImage(2) + CAddTable
             if s["in_norm"]:
                 x = _inorm(x, self.w, n + ".n")
             if s["relu"]:

@@ -44,6 +44,9 @@ CASES = [  # cin, cout, k, stride, pad, transposed, adj, H, W
     (128, 64, 3, 2, 1, 1, 1, 4, 140),    # u64 phase-fold (N = 256, single issuer), two tiles
     (64, 32, 3, 2, 1, 1, 1, 3, 129),     # u32 phase-fold + K-split, one-pixel second tile
     (64, 3, 9, 1, 4, 0, 0, 11, 140),     # paper-arch final conv (64 channels): x-fold without row-fold
+    (64, 32, 3, 1, 1, 1, 0, 6, 140),     # f3s1-32: stride-1 full convolution = convolution with the flipped filter
+    (32, 16, 5, 2, 2, 1, 1, 5, 70),      # f5s2-16: four sub-pixel phases with 9/6/6/4 taps, tap offsets -1..1
+    (64, 64, 3, 1, 1, 0, 0, 7, 150),     # residual conv of the 'zero' padding type (pad 1, 64 channels: conv_tc path)
 ]
 
 

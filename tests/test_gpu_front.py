@@ -171,6 +171,23 @@ def test_whole_temporal_stage_in_one_kernel_bit_exact(fav, shape, border):
         assert np.array_equal(out.cpu().numpy(), pyoracle.temporal_input(c, p, flow, ocert, f, m, warp_mode=border)), (given is None, r)
 
 
+@pytest.mark.parametrize("shape", [(64, 96), (97, 75), (360, 640)])
+def test_temporal_loss_of_evaluate(fav, shape):
+    """-evaluate's temporal term (fast_artistic_video.lua:128-151): MSE(cmul(warp(prev, flow), cert), cmul(cur, cert)) as one
+    fused kernel vs the composition in float64 from the bit-exact oracle warp."""
+    from oracle import net_oracle, pyoracle
+
+    H, W = shape
+    prev, cur = synth.make_frame(H, W, 1) * 1.2 - 0.1, synth.make_frame(H, W, 2)
+    flow = synth.checker_to_lua(synth.make_backward_flow(H, W, 2))
+    cert = (net_oracle.make_cert(H, W, 2) if W % 4 == 0 else (np.random.default_rng(0).uniform(size=(H, W)) > 0.2)).astype(np.float32)
+    got = fav.utils.temporal_loss(T(prev), T(cur), T(flow), T(cert))
+    a = (pyoracle.warp_bdhw(prev, flow) * cert[None]).astype(np.float32)
+    b = (cur * cert[None]).astype(np.float32)
+    ref = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    assert abs(got - ref) <= 1e-9 + 1e-7 * ref, (got, ref)
+
+
 def test_temporal_stage_rejects_unaligned(fav):
     from fav_b200 import _lib
 

@@ -85,6 +85,44 @@ def test_paper_arch_with_nearest_upsampling(shape):
     assert np.abs(net_u.run_image(T(f1)).cpu().numpy() - ora.run_image(f1)).max() < TOL / 10
 
 
+@pytest.mark.parametrize("arch,ptype", [
+    ("c9s1-32,d64,C64,R64,f3s2-32,f3s1-32,c9s1-3", "reflect-start"),   # CX block, fXsY-Z full convolutions (stride 2 and 1), 64-ch blocks
+    ("c9s1-32,d64,d128,R128,R128,f5s2-64,u32,c9s1-3", "reflect-start"),  # 5x5 full convolution: 4 sub-pixel phases with 9/6/6/4 taps
+    (synth.DEFAULT_ARCH, "zero"),                                       # padding_type zero: padded residual convs, Identity skip
+])
+def test_arch_tokens_and_padding_types(arch, ptype):
+    """models_video.build_model's remaining tokens (fXsY-Z :81-89, CX :103-108) and padding_type 'zero' (:13-19,46-50) vs the
+    fp64 oracle, every layer."""
+    from fav_b200 import models_video
+    from oracle import net_oracle
+
+    H, W = 64, 96
+    w = synth.make_weights(arch, "scream")
+    net_x = models_video.StyleNet(arch, padding_type=ptype).load_state(w)
+    ora = net_oracle.NetOracle(arch=arch, style="scream", dtype=torch.float64, padding_type=ptype)
+    x7 = rand_input(H, W, 9)
+    taps = {}
+    ref = ora.forward(torch.from_numpy(x7)[None], taps)[0].numpy()
+    out = net_x.forward(T(x7)[None]).cpu().numpy()[0]
+    assert out.shape == ref.shape == (3, H, W)
+    for i in range(len(ora.specs) - 1):
+        r = taps[f"l{i}"][0].numpy()
+        g = net_x.layer_output(i).cpu().numpy()
+        assert g.shape == r.shape and np.abs(g - r).max() < 2e-4 * max(1.0, np.abs(r).max()), f"layer {i}"
+    assert np.abs(out - ref).max() / 255.0 < TOL / 10
+    f1 = synth.make_frame(H, W, 1)
+    assert np.abs(net_x.run_image(T(f1)).cpu().numpy() - ora.run_image(f1)).max() < TOL / 10
+
+
+def test_unsupported_padding_types_fail_loudly():
+    from fav_b200 import _lib, models_video
+
+    for ptype in ("reflect", "replicate", "none"):
+        with pytest.raises(_lib.FavError) as e:
+            models_video.StyleNet(synth.DEFAULT_ARCH, padding_type=ptype)
+        assert e.value.status == _lib.FAV_ERR_UNSUPPORTED
+
+
 def test_tcgen05_agrees_with_cuda_core_comparator(net):
     x = T(rand_input(96, 160, 3))[None]
     a = net.forward(x)
@@ -265,10 +303,12 @@ def test_video_driver_end_to_end_files(tmp_path):
     t7.write_checkpoint(f"{d}/checkpoint-candy-video.t7", synth.DEFAULT_ARCH, w)
     video.main(["-input_pattern", f"{d}/frame_%04d.ppm", "-flow_pattern", f"{d}/backward_[%d]_{{%d}}.flo",
                 "-occlusions_pattern", f"{d}/reliable_[%d]_{{%d}}.pgm", "-model_vid", f"{d}/checkpoint-candy-video.t7",
-                "-output_prefix", f"{d}/out", "-num_frames", str(n)])
+                "-output_prefix", f"{d}/out", "-num_frames", str(n), "-evaluate", "-evaluation_file", f"{d}/evaluation.txt",
+                "-flow_pattern_eval", f"{d}/backward_[%d]_{{%d}}.flo", "-occlusions_pattern_eval", f"{d}/reliable_[%d]_{{%d}}.pgm"])
     # oracle on the same files (frames are 8-bit PPMs here)
     ora = net_oracle.NetOracle(style="candy", dtype=torch.float64)
     prev = None
+    prev_prev, temporal_ref = None, []
     for i in range(1, n + 1):
         frame = np.asarray(Image.open(f"{d}/frame_{i:04d}.ppm"), np.float32).transpose(2, 0, 1) / 255.0
         if i == 1:
@@ -281,3 +321,15 @@ def test_video_driver_end_to_end_files(tmp_path):
         prev = ref.astype(np.float32)
         png = np.asarray(Image.open(f"{d}/out-{i:05d}.png"), np.float32).transpose(2, 0, 1) / 255.0
         assert np.abs(png - np.clip(ref, 0, 1)).max() <= 0.5 / 255 + TOL, i
+        if i >= 2:  # -evaluate's temporal loss (fast_artistic_video.lua:128-151) on the oracle trajectory
+            cert_eval = pyoracle.consistency(bw, fw).astype(np.float32) / 255.0
+            wp = pyoracle.warp_bdhw(prev_prev, synth.checker_to_lua(bw))
+            temporal_ref.append(float(np.mean(((wp - ref.astype(np.float32)) * cert_eval[None]).astype(np.float64) ** 2)))
+        prev_prev = ref.astype(np.float32)
+    rows = open(f"{d}/evaluation.txt").read().strip().split("\n")
+    assert len(rows) == 6  # style; content; temporal per frame, then the three averages (core.lua:231-238)
+    temporal = [float(v) for v in rows[2].split(";")]
+    assert len(temporal) == n and temporal[0] == 0.0
+    for got, want in zip(temporal[1:], temporal_ref):
+        assert abs(got - want) <= 1e-6 + 1e-2 * want, (got, want)  # GPU trajectory vs oracle trajectory (1e-5 apart)
+    assert abs(float(rows[5]) - sum(temporal) / n) < 1e-9
