@@ -307,7 +307,7 @@ __device__ __forceinline__ void temporal_pixels(
 }
 
 template <int VEC, bool FIRST, bool PACK = false>
-__global__ void __launch_bounds__(256, 2) temporal_input_kernel(
+__global__ void __launch_bounds__(256) temporal_input_kernel(
     const float *__restrict__ content, const float *__restrict__ prev, const float *__restrict__ flow,
     const float *__restrict__ cert, const float *__restrict__ fill, const float *__restrict__ flow_mask,
     float *__restrict__ out7, int H, int W, int border_mode, Operand dst = Operand(), int R = 0) {
@@ -333,16 +333,16 @@ __global__ void __launch_bounds__(256, 2) temporal_input_kernel(
 // ---- the WHOLE temporal-consistency stage in one kernel ---------------------------------------------------------------
 // north star: "BilinearSamplerBDHW warp of the previous stylized frame by the supplied optical flow, consistencyChecker's
 // forward/backward-flow occlusion test, and the channel concat ... become one fused sm_100a kernel ... that writes the
-// 7-channel tensor the net consumes directly".  Per 64 x 32 pixel tile (256 threads, 2 x 4 pixels each):
+// 7-channel tensor the net consumes directly".  Per 64 x 16 pixel tile (256 threads x 4 pixels):
 //   1. certainty of the tile + a (r/2)-pixel halo into shared memory: MODE 0 = the occlusion test itself
 //      (consistencyChecker.cpp:99-125, 3-argument mode; flow1 = the backward flow that also drives the warp, flow2 = forward
 //      flow) -- halo pixels are recomputed instead of exchanged; MODE 1 = a given certainty plane (func_load_cert output);
 //   2. utils.min_filter (utils.lua:161-169) as a separable r x r minimum in shared memory (pad cells = +inf);
 //   3. warp + preprocess + mask + concat of the thread's 4 pixels (temporal_pixels above).
 // Bit-identical to consistency_kernel -> min_filter_kernel -> temporal_input_kernel (tests/test_gpu_front.py).
-constexpr int TS_TX = 64, TS_TY = 32, TS_MAXP = 7;  // 64 x 32 tile: the 3-pixel halo costs 1.30x certainty evaluations (1.50x at 64 x 16)
+constexpr int TS_TX = 64, TS_TY = 16, TS_MAXP = 7;  // (64 x 32 tiles: 1.30x instead of 1.50x halo evaluations, but measured slower: 50.2 vs 47.5 us)
 template <bool PACK, int MODE>
-__global__ void __launch_bounds__(256, 2) temporal_stage_kernel(
+__global__ void __launch_bounds__(256) temporal_stage_kernel(
     const float *__restrict__ content, const float *__restrict__ prev, const float *__restrict__ flow,
     const float *__restrict__ fw_u, const float *__restrict__ fw_v, const float *__restrict__ cert_raw,
     const float *__restrict__ fill, const float *__restrict__ flow_mask, float *__restrict__ out7,

@@ -168,6 +168,19 @@ int fav_session_run_next_image_flows(fav_session_t *s, const float *content_host
   return session_step(s, 2, content_host, flow_bw_uv_host, flow_fw_uv_host, nullptr, min_filter_r, border_mode, out_host);
 }
 
+// the stylized frame of call number `frame_index` (0-based count of run_* calls on this session) has landed in its out_host
+// buffer; wait != 0 blocks until then.  (Each output slot has one "downloaded" event: if a later call already reused the
+// slot, this waits for that later frame -- never too short.)
+int fav_session_frame_done(fav_session_t *s, uint64_t frame_index, int wait) {
+  FAV_REQUIRE(s && frame_index < s->frame, "fav_session_frame_done: frame %llu was never enqueued", (unsigned long long)frame_index);
+  cudaEvent_t ev = s->downloaded[frame_index & 1];
+  if (wait) return check_cuda(cudaEventSynchronize(ev), "cudaEventSynchronize(downloaded)");
+  cudaError_t e = cudaEventQuery(ev);
+  if (e == cudaSuccess) return FAV_OK;
+  if (e == cudaErrorNotReady) { set_error("frame %llu still in flight", (unsigned long long)frame_index); return FAV_ERR_INVALID; }
+  return check_cuda(e, "cudaEventQuery(downloaded)");
+}
+
 int fav_session_sync(fav_session_t *s) {
   FAV_REQUIRE(s, "fav_session_sync: null session");
   FAV_TRY(check_cuda(cudaStreamSynchronize(s->s_h2d), "sync h2d"));

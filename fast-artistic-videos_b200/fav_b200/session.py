@@ -49,6 +49,16 @@ class Session:
                                                              _hp(flow_fw_uv_host), int(min_filter_r), border_mode,
                                                              _hp(out_host)))
 
+    def frame_done(self, frame_index: int, wait: bool = True) -> bool:
+        """The output of the frame_index-th run_* call (0-based) has landed in its host buffer."""
+        rc = _lib.lib.fav_session_frame_done(self._h, int(frame_index), 1 if wait else 0)
+        if rc == _lib.FAV_OK:
+            return True
+        if not wait and rc == _lib.FAV_ERR_INVALID:
+            return False
+        _lib.check(rc)
+        return False
+
     def sync(self):
         _lib.check(_lib.lib.fav_session_sync(self._h))
 

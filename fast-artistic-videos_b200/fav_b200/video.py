@@ -34,6 +34,7 @@ def build_parser():
     a("-evaluation_file", default="evaluation.txt"); a("-flow_pattern_eval", default=""); a("-occlusions_pattern_eval", default="")
     a("-invert_occlusion_eval", action="store_true"); a("-fix_occlusions_eval", action="store_true"); a("-backward_eval", action="store_true")
     a("-model_img_arch", default="")
+    a("-pipeline", type=int, default=1)  # 1: threaded decode / encode around the host-buffer session (f-2); 0: synchronous driver
     a("-arch", default=core.synth.DEFAULT_ARCH)
     return p
 
@@ -130,12 +131,120 @@ class Driver:
         return i == 1 or opt.create_inconsistent
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# f-2: the same driver as a PIPELINE on the host-buffer session (fav_session_*): decode threads fill pinned ring buffers
+# (frame PPM/PNG -> fp32 planes, .flo -> (dy,dx) planes, certainty PGM), the main thread only enqueues frames
+# (3 CUDA streams inside the session: H2D / compute / D2H), encoder threads wait for ONE frame each (fav_session_frame_done)
+# and write its PNG.  Filename patterns ([%d] / {%d}) and the wait-for-file protocol of the flow / occlusion producers
+# (utils.lua:74-80) are those of the synchronous driver; the PNGs are bit-identical to it (tests/test_gpu_net.py).
+# The reference decodes, uploads, computes, downloads and encodes strictly one after the other
+# (fast_artistic_video.lua:93-170); at B200 speeds that host work, not the GPU, bounds the frame rate.
+# ---------------------------------------------------------------------------------------------------------------------
+def _read_planes(path: str, channels: int, out: torch.Tensor) -> None:
+    """image.load(path, channels) into a preallocated (pinned) [C,H,W] tensor."""
+    if path.lower().endswith((".ppm", ".pgm", ".pnm")):
+        import ctypes as C
+
+        _lib.check(_lib.lib.fav_pnm_read_f32(path.encode(), C.c_void_p(out.data_ptr()), out.numel(), C.c_float(255.0)))
+    else:
+        out.copy_(load_image(path, channels))
+
+
+def _png_bytes(img: torch.Tensor) -> np.ndarray:
+    """the quantisation of save_image on a host tensor (same fp32 operations)"""
+    a = img.numpy()
+    return np.clip(np.floor(np.clip(a, 0.0, 1.0) * np.float32(255.0) + np.float32(0.5)), 0, 255).astype(np.uint8).transpose(1, 2, 0)
+
+
+def pipeline_eligible(opt) -> bool:
+    return not (opt.backward or opt.evaluate or opt.fix_occlusions or opt.create_inconsistent or opt.fill_occlusions != "vgg-mean"
+                or float(opt.scale_factor) != 1 or opt.continue_with != 1)
+
+
+def run_pipelined(opt, depth: int = 8, n_decode: int = 6, n_encode: int = 12, model_vid=None, model_img=None):
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    from PIL import Image
+
+    from . import session
+
+    n = 0
+    while n < opt.num_frames and utils.file_exists(opt.input_pattern % (n + 1)):  # func_load_image returns nil -> stop (:93-97)
+        n += 1
+    if n == 0:
+        return dict(frames=0, seconds=0.0)
+    first = load_image(opt.input_pattern % 1, 3)
+    H, W = first.shape[-2:]
+    dev = torch.device("cuda", max(0, int(opt.gpu)))
+    torch.cuda.set_device(dev)
+    model = model_vid if model_vid is not None else core.load_model(opt.model_vid, opt.arch)
+    if model_img is None and opt.model_img not in ("self", "", None):
+        model_img = core.load_model(opt.model_img, opt.model_img_arch or opt.arch, in_dim=3)
+    sess = session.Session(model, H, W)
+    if model_img is not None:
+        sess.set_image_model(model_img)
+    pin = lambda *shape: torch.empty(shape, dtype=torch.float32).pin_memory()
+    slots = [dict(content=pin(3, H, W), flow=pin(2, H, W), cert=pin(1, H, W), out=pin(3, H, W)) for _ in range(depth)]
+    d = os.path.dirname(opt.output_prefix)
+    if d and not os.path.isdir(d):
+        os.makedirs(d)
+
+    def decode(i, slot):  # i is the 1-based frame index
+        _read_planes(opt.input_pattern % i, 3, slot["content"])
+        if i > 1:
+            flowFileName = getFormatedFlowFileName(opt.flow_pattern, i - 1, i)
+            certFileName = getFormatedFlowFileName(opt.occlusions_pattern, i - 1, i)
+            utils.wait_for_file(certFileName)  # func_load_cert :101-102
+            _read_planes(certFileName, 1, slot["cert"])
+            if opt.invert_occlusion:
+                slot["cert"].mul_(-1.0).add_(1.0)
+            utils.wait_for_file(flowFileName)
+            flowFileLoader.load(flowFileName, out=slot["flow"].numpy())
+        return slot
+
+    def encode(i, k, slot):
+        sess.frame_done(k)  # this frame's D2H only; later frames keep flowing
+        out_path = "%s-%05d.png" % (opt.output_prefix, i)
+        Image.fromarray(_png_bytes(slot["out"])).save(out_path)
+        return slot
+
+    t0 = time.perf_counter()
+    free = list(slots)
+    with ThreadPoolExecutor(n_decode) as dpool, ThreadPoolExecutor(n_encode) as epool:
+        dec, enc = {}, []
+        nxt = 1
+        for i in range(1, n + 1):
+            while nxt <= n and free:  # keep the decoders `depth` frames ahead
+                dec[nxt] = dpool.submit(decode, nxt, free.pop())
+                nxt += 1
+            if i not in dec:  # every slot is in flight: wait for the oldest encoder to give one back
+                free.append(enc.pop(0).result())
+                dec[i] = dpool.submit(decode, i, free.pop())
+                nxt = max(nxt, i + 1)
+            slot = dec.pop(i).result()
+            if i == 1:
+                sess.run_image(slot["content"], slot["out"])
+            else:
+                sess.run_next_image(slot["content"], slot["flow"], slot["cert"][0], slot["out"], opt.occlusions_min_filter)
+            enc.append(epool.submit(encode, i, i - 1, slot))
+            while enc and enc[0].done():
+                free.append(enc.pop(0).result())
+        for f in enc:
+            f.result()
+    sess.sync()
+    dt = time.perf_counter() - t0
+    print("Stylized %d frames in %.3f s (%.1f frames/s, files -> PNG, pipelined)" % (n, dt, n / dt))
+    return dict(frames=n, seconds=dt)
+
+
 def main(argv=None):
     opt = build_parser().parse_args(argv)
     if opt.input_pattern == "":
         raise SystemExit("Must give -input_pattern")  # :177-179
     if not opt.create_inconsistent and (opt.flow_pattern == "" or opt.occlusions_pattern == ""):
         raise SystemExit("Must give -flow_pattern and -occlusions_pattern")  # :180-182
+    if opt.pipeline and pipeline_eligible(opt):
+        return run_pipelined(opt)
     d = Driver(opt)
     core.run_fast_neural_video(opt, d.func_load_image, d.func_load_cert, d.func_eval, d.func_make_last_frame_warped,
                                d.func_is_single_image, d.func_save_image)

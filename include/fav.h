@@ -152,9 +152,16 @@ FAV_API int fav_vr_blend_sides(const float *base, const float *const sides[4], c
                                float *out, int S, void *stream);
 
 /* a-3 / a-13  Middlebury .flo (HOST side)          flowFileLoader.lua:17-37, consistencyChecker.cpp:16-36
- * layout 0: [dy,dx] (Lua loader order); layout 1: [u,v] (checker order). out: host [2,H,W]. */
+ * layout 0: [dy,dx] (Lua loader order); layout 1: [u,v] (checker order). out: host [2,H,W] with room for capacity_floats
+ * floats: the header is re-validated against the file size AND the capacity (a producer may rewrite the file between
+ * fav_flo_read_header and fav_flo_read: utils.wait_for_file protocol); FAV_ERR_IO, never an exception, on any mismatch. */
 FAV_API int fav_flo_read_header(const char *path, int *W, int *H);
-FAV_API int fav_flo_read(const char *path, float *out_host, int layout);
+FAV_API int fav_flo_read(const char *path, float *out_host, size_t capacity_floats, int layout);
+/* f-2  binary PPM (P6) / PGM (P5) -> planar fp32 [C,H,W] = byte / divisor (HOST side)
+ * divisor 255: image.load(path, 3|1) (fast_artistic_video.lua:95,103); divisor 1: CTensor::readFromPPM planes 0..255
+ * (consistencyChecker/CTensor.h:888-936, '#' comment lines honoured). */
+FAV_API int fav_pnm_read_header(const char *path, int *W, int *H, int *C);
+FAV_API int fav_pnm_read_f32(const char *path, float *out_host, size_t capacity_floats, float divisor);
 
 /* ---------------------------------------------------------------------------------------------
  * a-N*  the stylization network                fast_artistic_video/models_video.lua:55-140
@@ -248,6 +255,10 @@ FAV_API int fav_session_run_next_image_flows(fav_session_t *s, const float *cont
                                              const float *flow_bw_uv_host,
                                              const float *flow_fw_uv_host, int min_filter_r,
                                              int border_mode, float *out_host);
+/* completion of ONE frame: call number frame_index (0-based) of fav_session_run_* on this session has landed in its out_host
+ * buffer (wait != 0 blocks; wait == 0 polls: FAV_OK / FAV_ERR_INVALID "still in flight").  Lets encoder threads consume
+ * frames while later ones are still being enqueued (file-driven pipeline, fav_b200/video.py). */
+FAV_API int fav_session_frame_done(fav_session_t *s, uint64_t frame_index, int wait);
 /* block until every queued frame has landed in its out_host buffer */
 FAV_API int fav_session_sync(fav_session_t *s);
 /* device time (ms, CUDA events on the compute stream) of the last frame's GPU work */

@@ -99,3 +99,42 @@ def test_flo_reader_matches_oracle(tmp_path):
         flowFileLoader.load(str(tmp_path / "trunc.flo"))
     with pytest.raises(Exception):
         flowFileLoader.load(str(tmp_path / "missing.flo"))
+    # hostile header (2^30 x 2^30) and a file that outgrew the caller's buffer: FAV_ERR_IO, never an exception / overflow
+    import struct
+
+    from fav_b200 import _lib
+
+    open(str(tmp_path / "huge.flo"), "wb").write(struct.pack("<fii", 202021.25, 1 << 30, 1 << 30) + b"\0" * 64)
+    with pytest.raises(_lib.FavError) as e:
+        flowFileLoader.load(str(tmp_path / "huge.flo"))
+    assert e.value.status == _lib.FAV_ERR_IO
+    small = np.empty((2, 10, 10), np.float32)
+    with pytest.raises(_lib.FavError) as e:
+        flowFileLoader.load(p, out=small)
+    assert e.value.status == _lib.FAV_ERR_IO
+
+
+def test_pnm_readers(tmp_path):
+    """image.load(ppm|pgm) = byte / 255 (fast_artistic_video.lua:95,103) and readFromPPM's 0..255 planes with comments."""
+    import ctypes as C
+
+    from fav_b200 import _lib, synth
+
+    H, W = 13, 21
+    img = synth.make_frame(H, W, 4)
+    p = str(tmp_path / "f.ppm")
+    synth.write_ppm(p, img)
+    u8 = np.clip(np.rint(img * 255.0), 0, 255).astype(np.uint8)
+    w_, h_, c_ = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(_lib.lib.fav_pnm_read_header(p.encode(), C.byref(w_), C.byref(h_), C.byref(c_)))
+    assert (w_.value, h_.value, c_.value) == (W, H, 3)
+    out = np.empty((3, H, W), np.float32)
+    _lib.check(_lib.lib.fav_pnm_read_f32(p.encode(), out.ctypes.data_as(C.c_void_p), out.size, C.c_float(255.0)))
+    assert np.array_equal(out, u8.astype(np.float32) / np.float32(255.0))
+    g = (np.random.default_rng(0).uniform(size=(H, W)) > 0.3).astype(np.uint8) * 255
+    pg = str(tmp_path / "c.pgm")
+    open(pg, "wb").write(b"P5\n# a comment line\n%d %d\n255\n" % (W, H) + g.tobytes())
+    outg = np.empty((1, H, W), np.float32)
+    _lib.check(_lib.lib.fav_pnm_read_f32(pg.encode(), outg.ctypes.data_as(C.c_void_p), outg.size, C.c_float(1.0)))
+    assert np.array_equal(outg[0], g.astype(np.float32))
+    assert _lib.lib.fav_pnm_read_f32(pg.encode(), outg.ctypes.data_as(C.c_void_p), 5, C.c_float(1.0)) == _lib.FAV_ERR_IO

@@ -212,10 +212,13 @@ def test_consistency_check_equals_reference_binary(fav, case):
     assert np.array_equal(fav.consistencyChecker.check(T(bw), T(fw), T(img255)).cpu().numpy(), ref4)
 
 
-def test_compute_corners_bit_exact(fav):
+@pytest.mark.parametrize("shape", [(100, 76), (360, 640), (33, 1100)])
+def test_compute_corners_bit_exact(fav, shape):
+    """4-argument mode's structure measure (computeCorners + CMatrix::normalize + avg): the parallel prefix-maximum evaluation
+    of the reference's `else if` min/max scan and the staged sequential fp32 mean vs the pinned C restatement, bit for bit."""
     from oracle import pyoracle
 
-    _, _, _, img255 = make_golden.consistency_inputs(100, 76, 3, 0.6, 2)
+    _, _, _, img255 = make_golden.consistency_inputs(shape[0], shape[1], 3, 0.6, 2)
     corners, avg = fav.consistencyChecker.compute_corners(T(img255))
     o = pyoracle.compute_corners(img255)
     assert np.array_equal(corners.cpu().numpy(), o)

@@ -305,6 +305,13 @@ def test_video_driver_end_to_end_files(tmp_path):
                 "-occlusions_pattern", f"{d}/reliable_[%d]_{{%d}}.pgm", "-model_vid", f"{d}/checkpoint-candy-video.t7",
                 "-output_prefix", f"{d}/out", "-num_frames", str(n), "-evaluate", "-evaluation_file", f"{d}/evaluation.txt",
                 "-flow_pattern_eval", f"{d}/backward_[%d]_{{%d}}.flo", "-occlusions_pattern_eval", f"{d}/reliable_[%d]_{{%d}}.pgm"])
+    # f-2: the pipelined driver (decode threads -> pinned ring -> fav_session_* -> encoder threads) writes the SAME PNGs
+    res = video.main(["-input_pattern", f"{d}/frame_%04d.ppm", "-flow_pattern", f"{d}/backward_[%d]_{{%d}}.flo",
+                      "-occlusions_pattern", f"{d}/reliable_[%d]_{{%d}}.pgm", "-model_vid", f"{d}/checkpoint-candy-video.t7",
+                      "-output_prefix", f"{d}/pipe", "-num_frames", str(n)])
+    assert res["frames"] == n
+    for i in range(1, n + 1):
+        assert np.array_equal(np.asarray(Image.open(f"{d}/pipe-{i:05d}.png")), np.asarray(Image.open(f"{d}/out-{i:05d}.png"))), i
     # oracle on the same files (frames are 8-bit PPMs here)
     ora = net_oracle.NetOracle(style="candy", dtype=torch.float64)
     prev = None
