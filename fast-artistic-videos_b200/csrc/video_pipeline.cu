@@ -1,0 +1,247 @@
+// video_pipeline.cu -- f-2: the file-driven frame loop of fast_artistic_video.lua:93-170 as a native host pipeline around the
+// host-buffer session (session.cu).  The reference decodes, uploads, stylizes, downloads and encodes one frame after the other
+// (image.load / flowFile.load in interpreted Lua, image.save); at B200 speeds that host work bounds the frame rate by two
+// orders of magnitude.  Here:
+//   decoder threads   frame PPM -> fp32 planes / 255, certainty PGM -> fp32 / 255, Middlebury .flo -> (dy,dx) planes, straight
+//                     into PINNED ring slots (cudaHostAlloc); the wait-for-file protocol of the flow / occlusion producers
+//                     (utils.lua:74-80) and the [fmt] / {fmt} filename patterns (fast_artistic_video.lua:70-77) are kept
+//   calling thread    only enqueues frames on the session (3 CUDA streams inside: H2D / compute / D2H)
+//   encoder threads   wait for ONE frame each (fav_session_frame_done), quantise like image.save (clamp, x255, round) and
+//                     write "<prefix>-%05d.png" (fast_artistic_video.lua:161) with zlib; any PNG decoder returns the same
+//                     pixels as the synchronous driver's files
+// Host code only (no kernels); compiled by nvcc for the CUDA runtime calls.
+#include <zlib.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <math.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include "fav_common.cuh"
+
+namespace fav {
+namespace {
+
+// {fmt} is formatted with the from-index, [fmt] with the to-index (fast_artistic_video.lua:70-77)
+std::string format_flow_name(const std::string &pattern, int fromIndex, int toIndex) {
+  std::string out;
+  for (size_t i = 0; i < pattern.size();) {
+    const char ch = pattern[i];
+    const char close = ch == '{' ? '}' : (ch == '[' ? ']' : 0);
+    size_t j = close ? pattern.find(close, i + 1) : std::string::npos;
+    if (close && j != std::string::npos) {
+      char buf[64];
+      snprintf(buf, sizeof(buf), pattern.substr(i + 1, j - i - 1).c_str(), ch == '{' ? fromIndex : toIndex);
+      out += buf;
+      i = j + 1;
+    } else {
+      out += ch;
+      ++i;
+    }
+  }
+  return out;
+}
+std::string format_index(const std::string &pattern, int idx) {
+  char buf[4096];
+  snprintf(buf, sizeof(buf), pattern.c_str(), idx);
+  return buf;
+}
+bool file_exists(const std::string &p) {
+  struct stat st;
+  return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode);
+}
+
+void put_be32(std::vector<unsigned char> &v, uint32_t x) {
+  v.push_back(x >> 24); v.push_back(x >> 16); v.push_back(x >> 8); v.push_back(x);
+}
+void png_chunk(std::vector<unsigned char> &out, const char type[4], const unsigned char *data, size_t n) {
+  put_be32(out, (uint32_t)n);
+  const size_t start = out.size();
+  out.insert(out.end(), type, type + 4);
+  if (n) out.insert(out.end(), data, data + n);
+  put_be32(out, (uint32_t)crc32(0, out.data() + start, (uInt)(n + 4)));
+}
+// 8-bit RGB PNG (colour type 2, no interlace); rows pre-filtered with Sub (type 1)
+int write_png(const std::string &path, const unsigned char *rgb, int W, int H, int level) {
+  std::vector<unsigned char> raw((size_t)H * (1 + 3 * W));
+  for (int y = 0; y < H; ++y) {
+    unsigned char *dst = raw.data() + (size_t)y * (1 + 3 * W);
+    const unsigned char *src = rgb + (size_t)y * 3 * W;
+    *dst++ = 1;
+    for (int i = 0; i < 3 * W; ++i) dst[i] = (unsigned char)(src[i] - (i >= 3 ? src[i - 3] : 0));
+  }
+  uLongf bound = compressBound((uLong)raw.size());
+  std::vector<unsigned char> z(bound);
+  if (compress2(z.data(), &bound, raw.data(), (uLong)raw.size(), level) != Z_OK) return FAV_ERR_IO;
+  std::vector<unsigned char> out;
+  out.reserve(bound + 64);
+  const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+  out.insert(out.end(), sig, sig + 8);
+  std::vector<unsigned char> ihdr;
+  put_be32(ihdr, (uint32_t)W); put_be32(ihdr, (uint32_t)H);
+  const unsigned char tail[5] = {8, 2, 0, 0, 0};
+  ihdr.insert(ihdr.end(), tail, tail + 5);
+  png_chunk(out, "IHDR", ihdr.data(), ihdr.size());
+  png_chunk(out, "IDAT", z.data(), bound);
+  png_chunk(out, "IEND", nullptr, 0);
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) return FAV_ERR_IO;
+  const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+  fclose(f);
+  return ok ? FAV_OK : FAV_ERR_IO;
+}
+
+struct Slot {
+  float *content = nullptr, *flow = nullptr, *cert = nullptr, *out = nullptr;  // pinned
+  int state = 0;  // 0 free, 1 decoded, 2 in flight on the GPU
+};
+
+}  // namespace
+}  // namespace fav
+
+using namespace fav;
+
+extern "C" {
+
+// Runs the whole clip; blocks until the last PNG is on disk.  Frames are <input_pattern % i>, i = 1..; the loop ends at
+// num_frames or at the first missing frame file (func_load_image returning nil, fast_artistic_video.lua:93-97).
+// frames_done / seconds (may be NULL) report what was processed.
+int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_pattern, const char *flow_pattern,
+                           const char *occlusions_pattern, const char *output_prefix, int num_frames, int min_filter_r,
+                           int invert_occlusion, int n_decode, int n_encode, int depth, int png_level, int *frames_done,
+                           double *seconds) {
+  FAV_REQUIRE(sess && input_pattern && flow_pattern && occlusions_pattern && output_prefix, "fav_video_pipeline_run: null argument");
+  FAV_REQUIRE(H > 0 && W > 0 && num_frames >= 0, "fav_video_pipeline_run: bad size");
+  n_decode = n_decode < 1 ? 1 : n_decode; n_encode = n_encode < 1 ? 1 : n_encode;
+  depth = depth < 4 ? 4 : depth;
+  png_level = png_level < 0 ? 1 : (png_level > 9 ? 9 : png_level);
+  int n = 0;
+  while (n < num_frames && file_exists(format_index(input_pattern, n + 1))) ++n;
+  if (frames_done) *frames_done = n;
+  if (seconds) *seconds = 0;
+  if (n == 0) return FAV_OK;
+  const size_t HW = (size_t)H * W;
+  std::vector<Slot> slots(depth);
+  auto free_slots = [&]() {
+    for (Slot &s : slots) { cudaFreeHost(s.content); cudaFreeHost(s.flow); cudaFreeHost(s.cert); cudaFreeHost(s.out); }
+  };
+  for (Slot &s : slots)
+    if (cudaHostAlloc((void **)&s.content, 3 * HW * 4, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&s.flow, 2 * HW * 4, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&s.cert, HW * 4, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&s.out, 3 * HW * 4, cudaHostAllocDefault) != cudaSuccess) {
+      (void)cudaGetLastError();
+      free_slots();
+      set_error("fav_video_pipeline_run: cannot allocate %d pinned frame slots", depth);
+      return FAV_ERR_CUDA;
+    }
+  std::mutex mu;
+  std::condition_variable cv;
+  std::atomic<int> next_decode{1}, next_encode{1};
+  std::vector<int> ready(n + 2, 0);  // per frame: 1 decoded, 2 enqueued on the GPU, 3 written
+  int err = FAV_OK;
+  std::string err_msg;
+  auto fail = [&](int code, const std::string &msg) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (err == FAV_OK) { err = code; err_msg = msg; }
+    cv.notify_all();
+  };
+  auto wait_for_file = [&](const std::string &path) {  // utils.lua:74-80
+    if (file_exists(path)) return true;
+    fprintf(stderr, "Waiting for file \"%s\"\n", path.c_str());
+    while (!file_exists(path)) {
+      { std::lock_guard<std::mutex> lk(mu); if (err != FAV_OK) return false; }
+      std::this_thread::sleep_for(std::chrono::seconds(1));
+    }
+    std::this_thread::sleep_for(std::chrono::seconds(1));
+    return true;
+  };
+  const std::string in_pat(input_pattern), flow_pat(flow_pattern), occ_pat(occlusions_pattern), out_prefix(output_prefix);
+
+  auto decoder = [&]() {
+    for (;;) {
+      const int i = next_decode.fetch_add(1);
+      if (i > n) return;
+      Slot &s = slots[(i - 1) % depth];
+      {  // the slot is free once frame i - depth has been written
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return err != FAV_OK || i <= depth || ready[i - depth] == 3; });
+        if (err != FAV_OK) return;
+      }
+      int rc = fav_pnm_read_f32(format_index(in_pat, i).c_str(), s.content, 3 * HW, 255.0f);
+      if (rc == FAV_OK && i > 1) {
+        const std::string cert_name = format_flow_name(occ_pat, i - 1, i), flow_name = format_flow_name(flow_pat, i - 1, i);
+        if (!wait_for_file(cert_name)) return;  // func_load_cert :99-103
+        rc = fav_pnm_read_f32(cert_name.c_str(), s.cert, HW, 255.0f);
+        if (rc == FAV_OK && invert_occlusion)
+          for (size_t k = 0; k < HW; ++k) s.cert[k] = 1.0f - s.cert[k];
+        if (rc == FAV_OK) {
+          if (!wait_for_file(flow_name)) return;
+          rc = fav_flo_read(flow_name.c_str(), s.flow, 2 * HW, 0);
+        }
+      }
+      if (rc != FAV_OK) { fail(rc, fav_last_error()); return; }
+      { std::lock_guard<std::mutex> lk(mu); ready[i] = 1; }
+      cv.notify_all();
+    }
+  };
+  auto encoder = [&]() {
+    std::vector<unsigned char> rgb(3 * HW);
+    for (;;) {
+      const int i = next_encode.fetch_add(1);
+      if (i > n) return;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return err != FAV_OK || ready[i] == 2; });
+        if (err != FAV_OK) return;
+      }
+      if (fav_session_frame_done(sess, (uint64_t)(i - 1), 1) != FAV_OK) { fail(FAV_ERR_CUDA, fav_last_error()); return; }
+      const Slot &s = slots[(i - 1) % depth];
+      for (size_t k = 0; k < HW; ++k)
+        for (int c = 0; c < 3; ++c) {  // image.save: clamp to [0,1], x255, round (same fp32 operations as the synchronous driver)
+          float v = s.out[(size_t)c * HW + k];
+          v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+          v = floorf(v * 255.0f + 0.5f);
+          rgb[3 * k + c] = (unsigned char)(v < 0.f ? 0.f : (v > 255.f ? 255.f : v));
+        }
+      char name[4096];
+      snprintf(name, sizeof(name), "%s-%05d.png", out_prefix.c_str(), i);
+      if (write_png(name, rgb.data(), W, H, png_level) != FAV_OK) { fail(FAV_ERR_IO, std::string("cannot write ") + name); return; }
+      { std::lock_guard<std::mutex> lk(mu); ready[i] = 3; }
+      cv.notify_all();
+    }
+  };
+
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> threads;
+  for (int t = 0; t < n_decode; ++t) threads.emplace_back(decoder);
+  for (int t = 0; t < n_encode; ++t) threads.emplace_back(encoder);
+  for (int i = 1; i <= n; ++i) {
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return err != FAV_OK || ready[i] == 1; });
+      if (err != FAV_OK) break;
+    }
+    Slot &s = slots[(i - 1) % depth];
+    const int rc = i == 1 ? fav_session_run_image(sess, s.content, s.out)
+                          : fav_session_run_next_image(sess, s.content, s.flow, s.cert, min_filter_r, FAV_BORDER_PER_TAP, s.out);
+    if (rc != FAV_OK) { fail(rc, fav_last_error()); break; }
+    { std::lock_guard<std::mutex> lk(mu); ready[i] = 2; }
+    cv.notify_all();
+  }
+  for (std::thread &t : threads) t.join();
+  fav_session_sync(sess);
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  free_slots();
+  if (seconds) *seconds = dt;
+  if (err != FAV_OK) { set_error("fav_video_pipeline_run: %s", err_msg.c_str()); return err; }
+  return FAV_OK;
+}
+}

@@ -161,6 +161,48 @@ def pipeline_eligible(opt) -> bool:
                 or float(opt.scale_factor) != 1 or opt.continue_with != 1)
 
 
+def _native_ok(opt) -> bool:
+    """the native pipeline decodes binary PPM / PGM only (what the reference's scripts extract with ffmpeg,
+    stylizeVideo_*.sh: frame_%04d.ppm, and what consistencyChecker writes)"""
+    return opt.input_pattern.lower().endswith(".ppm") and opt.occlusions_pattern.lower().endswith(".pgm")
+
+
+def run_native(opt, model_vid=None, model_img=None, n_decode=None, n_encode=None, depth=None, png_level=1):
+    """f-2 in C++ (csrc/video_pipeline.cu): decoder / encoder std::threads around the host-buffer session."""
+    import ctypes as C
+
+    from . import session
+
+    first = opt.input_pattern % 1
+    if not utils.file_exists(first):
+        return dict(frames=0, seconds=0.0)
+    w_, h_, c_ = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(_lib.lib.fav_pnm_read_header(first.encode(), C.byref(w_), C.byref(h_), C.byref(c_)))
+    H, W = h_.value, w_.value
+    torch.cuda.set_device(max(0, int(opt.gpu)))
+    model = model_vid if model_vid is not None else core.load_model(opt.model_vid, opt.arch)
+    if model_img is None and opt.model_img not in ("self", "", None):
+        model_img = core.load_model(opt.model_img, opt.model_img_arch or opt.arch, in_dim=3)
+    sess = session.Session(model, H, W)
+    if model_img is not None:
+        sess.set_image_model(model_img)
+    d = os.path.dirname(opt.output_prefix)
+    if d and not os.path.isdir(d):
+        os.makedirs(d)
+    cpus = os.cpu_count() or 8
+    n_decode = n_decode or max(2, min(16, cpus // 8))
+    n_encode = n_encode or max(4, min(64, cpus // 2))
+    depth = depth or (n_decode + n_encode + 4)
+    nfr, secs = C.c_int(), C.c_double()
+    _lib.check(_lib.lib.fav_video_pipeline_run(sess._h, H, W, opt.input_pattern.encode(), opt.flow_pattern.encode(),
+                                               opt.occlusions_pattern.encode(), opt.output_prefix.encode(), int(opt.num_frames),
+                                               int(opt.occlusions_min_filter), 1 if opt.invert_occlusion else 0, n_decode, n_encode,
+                                               depth, png_level, C.byref(nfr), C.byref(secs)))
+    if nfr.value:
+        print("Stylized %d frames in %.3f s (%.1f frames/s, files -> PNG, native pipeline)" % (nfr.value, secs.value, nfr.value / secs.value))
+    return dict(frames=nfr.value, seconds=secs.value)
+
+
 def run_pipelined(opt, depth: int = 8, n_decode: int = 6, n_encode: int = 12, model_vid=None, model_img=None):
     import time
     from concurrent.futures import ThreadPoolExecutor
@@ -244,7 +286,7 @@ def main(argv=None):
     if not opt.create_inconsistent and (opt.flow_pattern == "" or opt.occlusions_pattern == ""):
         raise SystemExit("Must give -flow_pattern and -occlusions_pattern")  # :180-182
     if opt.pipeline and pipeline_eligible(opt):
-        return run_pipelined(opt)
+        return run_native(opt) if _native_ok(opt) else run_pipelined(opt)
     d = Driver(opt)
     core.run_fast_neural_video(opt, d.func_load_image, d.func_load_cert, d.func_eval, d.func_make_last_frame_warped,
                                d.func_is_single_image, d.func_save_image)

@@ -259,6 +259,15 @@ FAV_API int fav_session_run_next_image_flows(fav_session_t *s, const float *cont
  * buffer (wait != 0 blocks; wait == 0 polls: FAV_OK / FAV_ERR_INVALID "still in flight").  Lets encoder threads consume
  * frames while later ones are still being enqueued (file-driven pipeline, fav_b200/video.py). */
 FAV_API int fav_session_frame_done(fav_session_t *s, uint64_t frame_index, int wait);
+/* f-2  the file-driven frame loop (fast_artistic_video.lua:93-170) as a native pipeline around this session: decoder threads
+ * (frame PPM, certainty PGM, .flo -> pinned ring slots; [fmt]/{fmt} patterns :70-77; wait-for-file protocol utils.lua:74-80),
+ * the calling thread enqueues frames, encoder threads wait per frame and write "<output_prefix>-%05d.png" (:161; zlib level
+ * png_level, pixels identical to the synchronous driver's files).  Frames i = 1.. until num_frames or the first missing frame
+ * file.  Blocks until the last PNG is written; frames_done / seconds may be NULL. */
+FAV_API int fav_video_pipeline_run(fav_session_t *s, int H, int W, const char *input_pattern, const char *flow_pattern,
+                                   const char *occlusions_pattern, const char *output_prefix, int num_frames, int min_filter_r,
+                                   int invert_occlusion, int n_decode, int n_encode, int depth, int png_level, int *frames_done,
+                                   double *seconds);
 /* block until every queued frame has landed in its out_host buffer */
 FAV_API int fav_session_sync(fav_session_t *s);
 /* device time (ms, CUDA events on the compute stream) of the last frame's GPU work */

@@ -309,9 +309,15 @@ def test_video_driver_end_to_end_files(tmp_path):
     res = video.main(["-input_pattern", f"{d}/frame_%04d.ppm", "-flow_pattern", f"{d}/backward_[%d]_{{%d}}.flo",
                       "-occlusions_pattern", f"{d}/reliable_[%d]_{{%d}}.pgm", "-model_vid", f"{d}/checkpoint-candy-video.t7",
                       "-output_prefix", f"{d}/pipe", "-num_frames", str(n)])
-    assert res["frames"] == n
+    assert res["frames"] == n  # native pipeline (csrc/video_pipeline.cu): PPM / PGM / .flo inputs
+    opt2 = video.build_parser().parse_args(["-input_pattern", f"{d}/frame_%04d.ppm", "-flow_pattern", f"{d}/backward_[%d]_{{%d}}.flo",
+                                            "-occlusions_pattern", f"{d}/reliable_[%d]_{{%d}}.pgm", "-model_vid", f"{d}/checkpoint-candy-video.t7",
+                                            "-output_prefix", f"{d}/pyp", "-num_frames", str(n)])
+    assert video.run_pipelined(opt2, depth=4, n_decode=2, n_encode=2)["frames"] == n  # Python-thread variant (any image format)
     for i in range(1, n + 1):
-        assert np.array_equal(np.asarray(Image.open(f"{d}/pipe-{i:05d}.png")), np.asarray(Image.open(f"{d}/out-{i:05d}.png"))), i
+        ref_png = np.asarray(Image.open(f"{d}/out-{i:05d}.png"))
+        assert np.array_equal(np.asarray(Image.open(f"{d}/pipe-{i:05d}.png")), ref_png), i
+        assert np.array_equal(np.asarray(Image.open(f"{d}/pyp-{i:05d}.png")), ref_png), i
     # oracle on the same files (frames are 8-bit PPMs here)
     ora = net_oracle.NetOracle(style="candy", dtype=torch.float64)
     prev = None
