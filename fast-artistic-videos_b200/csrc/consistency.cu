@@ -100,6 +100,22 @@ __global__ void __launch_bounds__(256) structure_tensor_kernel(const float *__re
 }
 
 struct IirC { float k, pm, pp, e2, te; };
+constexpr int kIirChunk = 16;
+
+// 32 x 32 tiled transpose of 3 planes (blockIdx.z): the X pass of the IIR runs on the transposed matrices so that the
+// one-thread-per-line recurrence reads and writes coalesced (neighbouring threads = neighbouring lines = neighbouring addresses)
+__global__ void __launch_bounds__(256) transpose3_kernel(const float *__restrict__ in, float *__restrict__ out, int rows, int cols,
+                                                         int64_t plane) {
+  __shared__ float tile[32][33];
+  const float *src = in + blockIdx.z * plane;
+  float *dst = out + blockIdx.z * plane;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    if (by + r < rows && bx + tx < cols) tile[r][tx] = src[(int64_t)(by + r) * cols + bx + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (bx + r < cols && by + tx < rows) dst[(int64_t)(bx + r) * rows + by + tx] = tile[tx][r];
+}
 
 // one thread per line; `stride` between consecutive samples of the line, `pitch` between lines.
 // v1 scratch holds the causal pass (CFilter.h:1428-1431), the anti-causal pass (:1432-1435) is fused
@@ -120,14 +136,22 @@ __global__ void __launch_bounds__(128) iir_kernel(float *__restrict__ m0, float 
   float s_prev = S(0), s_cur = S(1);
   float a1 = __fadd_rn(__fmul_rn(k, __fadd_rn(s_cur, __fmul_rn(pm, s_prev))), __fmul_rn(__fsub_rn(te, e2), a0));
   V1(1) = a1;
-  for (int x = 2; x < n; ++x) {
-    s_prev = s_cur;
-    s_cur = S(x);
-    float a = __fsub_rn(__fadd_rn(__fmul_rn(k, __fadd_rn(s_cur, __fmul_rn(pm, s_prev))), __fmul_rn(te, a1)),
-                        __fmul_rn(e2, a0));
-    V1(x) = a;
-    a0 = a1;
-    a1 = a;
+  // the recurrence is sequential per line, the memory accesses are not: kIirChunk samples are requested ahead of the chain
+  for (int xb = 2; xb < n; xb += kIirChunk) {
+    float sv[kIirChunk];
+#pragma unroll
+    for (int j = 0; j < kIirChunk; ++j) sv[j] = xb + j < n ? S(xb + j) : 0.f;
+#pragma unroll
+    for (int j = 0; j < kIirChunk; ++j) {
+      if (xb + j >= n) break;
+      s_prev = s_cur;
+      s_cur = sv[j];
+      float a = __fsub_rn(__fadd_rn(__fmul_rn(k, __fadd_rn(s_cur, __fmul_rn(pm, s_prev))), __fmul_rn(te, a1)),
+                          __fmul_rn(e2, a0));
+      V1(xb + j) = a;
+      a0 = a1;
+      a1 = a;
+    }
   }
   // anti-causal
   float sN1 = S(n - 1);
@@ -137,15 +161,21 @@ __global__ void __launch_bounds__(128) iir_kernel(float *__restrict__ m0, float 
   S(n - 1) = __fadd_rn(V1(n - 1), b0);
   // S(n-2) is still needed as S(x+1) for x = n-3: it is cached in s_p1
   S(n - 2) = __fadd_rn(V1(n - 2), b1);
-  for (int x = n - 3; x >= 0; --x) {
-    float sx = S(x);
-    float b = __fsub_rn(__fadd_rn(__fmul_rn(k, __fsub_rn(__fmul_rn(pp, s_p1), __fmul_rn(e2, s_p2))), __fmul_rn(te, b1)),
-                        __fmul_rn(e2, b0));
-    S(x) = __fadd_rn(V1(x), b);
-    s_p2 = s_p1;
-    s_p1 = sx;
-    b0 = b1;
-    b1 = b;
+  for (int xb = n - 3; xb >= 0; xb -= kIirChunk) {
+    float sv[kIirChunk], vv[kIirChunk];
+#pragma unroll
+    for (int j = 0; j < kIirChunk; ++j) { sv[j] = xb - j >= 0 ? S(xb - j) : 0.f; vv[j] = xb - j >= 0 ? V1(xb - j) : 0.f; }
+#pragma unroll
+    for (int j = 0; j < kIirChunk; ++j) {
+      if (xb - j < 0) break;
+      float b = __fsub_rn(__fadd_rn(__fmul_rn(k, __fsub_rn(__fmul_rn(pp, s_p1), __fmul_rn(e2, s_p2))), __fmul_rn(te, b1)),
+                          __fmul_rn(e2, b0));
+      S(xb - j) = __fadd_rn(vv[j], b);
+      s_p2 = s_p1;
+      s_p1 = sv[j];
+      b0 = b1;
+      b1 = b;
+    }
   }
 #undef S
 #undef V1
@@ -311,9 +341,9 @@ int fav_consistency_check(const float *flow1, const float *flow2, const float *s
 
 size_t fav_compute_corners_workspace(int Z, int W, int H) {
   (void)Z;
-  // dxx,dyy,dxy + 3 scratch planes + minmax + the per-block maxima / carries / minima of the normalize scan
+  // dxx,dyy,dxy + 3 scratch planes + 3 transposed planes + minmax + the per-block maxima / carries / minima of the normalize scan
   const size_t nb = ((size_t)W * H + 1023) / 1024;
-  return (size_t)6 * W * H * sizeof(float) + (8 + 3 * nb + 8) * sizeof(float) + 256;
+  return (size_t)9 * W * H * sizeof(float) + (8 + 3 * nb + 8) * sizeof(float) + 256;  // dxx,dyy,dxy + v1 scratch x3 + transposed x3
 }
 
 int fav_compute_corners(const float *image, int Z, int W, int H, float rho, float *corners, float *avg_out,
@@ -323,7 +353,7 @@ int fav_compute_corners(const float *image, int Z, int W, int H, float rho, floa
   FAV_TRY(require_device());
   cudaStream_t st = (cudaStream_t)stream;
   int64_t n = (int64_t)W * H;
-  float *dxx = (float *)workspace, *dyy = dxx + n, *dxy = dyy + n, *scr = dxy + n, *minmax = scr + 3 * n;
+  float *dxx = (float *)workspace, *dyy = dxx + n, *dxy = dyy + n, *scr = dxy + n, *minmax = scr + 6 * n;
   dim3 b2(32, 8), g2(ceil_div(W, 32), ceil_div(H, 8));
   structure_tensor_kernel<<<g2, b2, 0, st>>>(image, Z, W, H, dxx, dyy, dxy);
   FAV_TRY(post_launch("computeCorners.structure"));
@@ -337,8 +367,14 @@ int fav_compute_corners(const float *image, int Z, int W, int H, float rho, floa
   c.pm = (float)((double)e * ((double)alpha - 1.0));
   c.pp = (float)((double)e * ((double)alpha + 1.0));
   // X: one thread per row (stride 1, pitch W); Y: one thread per column (stride W, pitch 1)
-  iir_kernel<<<dim3(ceil_div(H, 128), 3), 128, 0, st>>>(dxx, dyy, dxy, scr, W, H, 1, W, n, c);
+  // X pass: lines = rows.  Run it on the transposed matrices (coalesced), transpose back.
+  float *tr = scr + 3 * n;
+  transpose3_kernel<<<dim3(ceil_div(W, 32), ceil_div(H, 32), 3), 256, 0, st>>>(dxx, tr, H, W, n);
+  FAV_TRY(post_launch("computeCorners.transpose"));
+  iir_kernel<<<dim3(ceil_div(H, 128), 3), 128, 0, st>>>(tr, tr + n, tr + 2 * n, scr, W, H, H, 1, n, c);
   FAV_TRY(post_launch("computeCorners.iirX"));
+  transpose3_kernel<<<dim3(ceil_div(H, 32), ceil_div(W, 32), 3), 256, 0, st>>>(tr, dxx, W, H, n);
+  FAV_TRY(post_launch("computeCorners.transposeBack"));
   iir_kernel<<<dim3(ceil_div(W, 128), 3), 128, 0, st>>>(dxx, dyy, dxy, scr, H, W, W, 1, n, c);
   FAV_TRY(post_launch("computeCorners.iirY"));
   eigen_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(dxx, dxy, dyy, corners, n);

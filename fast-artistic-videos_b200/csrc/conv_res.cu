@@ -54,60 +54,47 @@ __device__ __forceinline__ void res_trace(const ResJob &job, int word, long long
   if (job.trace) job.trace[(size_t)blockIdx.x * kTraceWords + word] = (unsigned long long)v;
 }
 
-// One (patch row, channel block) slab of a norm-on-load stage: raw fp32 planes -> InstanceNorm (+ReLU) [+ skip] -> fp16 hi/lo,
-// stored MMA-ready at drow (hi) / drow + kResStageBytes (lo); lanes run along x.  G pixels per lane are in flight at a time
-// (all their loads are requested before the first is used).  SKIP: add the previous block's input (operand hi + lo joined in
-// fp32, exactly in_apply_kernel's arithmetic) and write the result back for the first `own` pixels of the slab.
-template <int G, bool SKIP>
+// One (patch row, channel block) slab of a norm-on-load stage: raw fp32 planes -> InstanceNorm (+ReLU) -> fp16 hi/lo, stored
+// MMA-ready at drow (hi) / drow + kResStageBytes (lo); lanes run along x, all loads of the slab (up to 40 independent
+// 128-byte-coalesced requests per lane) are requested before the first is used.
+// (Tried and removed: also adding the previous block's skip here and writing the block input back, which would delete the
+// in_apply pass BETWEEN residual blocks -- with 16 more registers of skip data per pixel only 2 pixels per lane fit in flight,
+// the slab needs two latency-exposed passes and the conv became producer bound: 70 us against 45.5 + 23 us. DESIGN.md 9.)
 __device__ __forceinline__ void nl_slab(const ResJob &job, const float *nl_tab, uint8_t *drow, int cb, int ry, bool row_ok, int xb,
-                                        int npx, int lane, int64_t pstride, int own) {
+                                        int npx, int lane, int64_t pstride) {
   const float *p0 = job.nl_raw + ((int64_t)(cb * 8) * job.nl_Hp + (row_ok ? ry : 0)) * job.nl_Wp;
   float tm[8], ts[8], tb[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { tm[i] = nl_tab[cb * 8 + i]; ts[i] = nl_tab[kResNlMaxC + cb * 8 + i]; tb[i] = nl_tab[2 * kResNlMaxC + cb * 8 + i]; }
-  const int64_t sk_row = SKIP ? ((int64_t)((row_ok ? ry : 0) + job.sk_row0) * job.sk_Cb + cb) * job.sk_slab16 + job.sk_col0 : 0;
-  const int64_t wb_row = SKIP ? ((int64_t)(ry + job.wb_row0) * job.wb_Cb + cb) * job.wb_slab16 + job.wb_col0 : 0;
-  for (int k0 = 0; k0 * 32 < npx; k0 += G) {
-    float v[G][8];
-    uint4 sh[G], sl[G];
+  float v[kResNlPx][8];
 #pragma unroll
-    for (int k = 0; k < G; ++k)
-      if ((k0 + k) * 32 < npx) {
-        const int x = xb + (k0 + k) * 32 + lane;
-        const int xc = x < 0 ? 0 : (x < job.nl_W ? x : job.nl_W - 1);  // clamped (always valid) addresses
+  for (int k = 0; k < kResNlPx; ++k)
+    if (k * 32 < npx) {
+      const int x = xb + k * 32 + lane;
+      const int xc = x < 0 ? 0 : (x < job.nl_W ? x : job.nl_W - 1);  // clamped (always valid) addresses
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[k][i] = __ldg(p0 + i * pstride + xc);
-        if (SKIP) { sh[k] = __ldg(job.sk_hi + sk_row + xc); sl[k] = __ldg(job.sk_lo + sk_row + xc); }
+      for (int i = 0; i < 8; ++i) v[k][i] = __ldg(p0 + i * pstride + xc);
+    }
+#pragma unroll
+  for (int k = 0; k < kResNlPx; ++k) {
+    const int p = k * 32 + lane, x = xb + p;
+    if (p < npx) {
+      const bool ok = row_ok && x >= 0 && x < job.nl_W;  // outside the image: zero (never normalised)
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a = (v[k][2 * i] - tm[2 * i]) * ts[2 * i] + tb[2 * i], b = (v[k][2 * i + 1] - tm[2 * i + 1]) * ts[2 * i + 1] + tb[2 * i + 1];
+        if (job.nl_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+        if (!ok) { a = 0.f; b = 0.f; }
+        a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);  // same values as split_store8
+        const __half2 hh = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+        h[i] = *reinterpret_cast<const uint32_t *>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t *>(&ll);
       }
-#pragma unroll
-    for (int k = 0; k < G; ++k) {
-      const int p = (k0 + k) * 32 + lane, x = xb + p;
-      if (p < npx) {
-        const bool ok = row_ok && x >= 0 && x < job.nl_W;  // outside the image: zero (never normalised)
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float a = (v[k][2 * i] - tm[2 * i]) * ts[2 * i] + tb[2 * i], b = (v[k][2 * i + 1] - tm[2 * i + 1]) * ts[2 * i + 1] + tb[2 * i + 1];
-          if (job.nl_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-          if (SKIP) {  // ConcatTable{conv_block, ShaveImage(2)} -> CAddTable (models_video.lua:41-53)
-            const uint32_t hw = i == 0 ? sh[k].x : (i == 1 ? sh[k].y : (i == 2 ? sh[k].z : sh[k].w));
-            const uint32_t lw = i == 0 ? sl[k].x : (i == 1 ? sl[k].y : (i == 2 ? sl[k].z : sl[k].w));
-            a += __half2float(__ushort_as_half((unsigned short)(hw & 0xffff))) + __half2float(__ushort_as_half((unsigned short)(lw & 0xffff)));
-            b += __half2float(__ushort_as_half((unsigned short)(hw >> 16))) + __half2float(__ushort_as_half((unsigned short)(lw >> 16)));
-          }
-          if (!ok) { a = 0.f; b = 0.f; }
-          a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);  // same values as split_store8
-          const __half2 hh = __floats2half2_rn(a, b);
-          const float2 hf = __half22float2(hh);
-          const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
-          h[i] = *reinterpret_cast<const uint32_t *>(&hh);
-          l[i] = *reinterpret_cast<const uint32_t *>(&ll);
-        }
-        const uint4 H4 = make_uint4(h[0], h[1], h[2], h[3]), L4 = make_uint4(l[0], l[1], l[2], l[3]);
-        *reinterpret_cast<uint4 *>(drow + (uint32_t)p * 16u) = H4;
-        *reinterpret_cast<uint4 *>(drow + kResStageBytes + (uint32_t)p * 16u) = L4;
-        if (SKIP && ok && p < own) { job.wb_hi[wb_row + x] = H4; job.wb_lo[wb_row + x] = L4; }
-      }
+      *reinterpret_cast<uint4 *>(drow + (uint32_t)p * 16u) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4 *>(drow + kResStageBytes + (uint32_t)p * 16u) = make_uint4(l[0], l[1], l[2], l[3]);
     }
   }
 }
@@ -175,15 +162,7 @@ __global__ void __launch_bounds__(kResThreads, 1) conv_res_kernel(const __grid_c
           const int ry = t.y + ri - job.nl_pad;
           const bool row_ok = ry >= 0 && ry < job.nl_H;
           uint8_t *drow = stage + (uint32_t)(rc * kResPslab) * 16u;
-          if (job.nl == 2) {
-            // the tile owns (writes back) patch rows 0-1, rows 2-3 too in the last row pair; columns [0, nt), the two halo
-            // columns too in the last tile of a row: every pixel of x_{b+1} is written exactly once across the grid
-            const bool own_row = ri < 2 || t.y + 2 >= job.Ho;
-            const int own_px = (t.x0 + t.nt >= job.Wo) ? npx : t.nt;
-            nl_slab<2, true>(job, sh->nl_tab, drow, cb, ry, row_ok, xb, npx, lane, pstride, own_row ? own_px : 0);
-          } else {
-            nl_slab<kResNlPx, false>(job, sh->nl_tab, drow, cb, ry, row_ok, xb, npx, lane, pstride, 0);
-          }
+          nl_slab(job, sh->nl_tab, drow, cb, ry, row_ok, xb, npx, lane, pstride);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to tcgen05.mma
         __syncwarp();

@@ -39,14 +39,7 @@ struct ResJob {
   int a_Cb, a_slab16, in_row0, in_col0;
   // input: PLANAR raw fp32 of the previous convolution, normalised on load (nl == 1; InstanceNorm + ReLU + hi/lo split in the
   // producer warps, same arithmetic as in_apply_kernel).  Logical input pixel of tap (ky,kx): (y + ky - nl_pad, x + kx - nl_pad)
-  // nl == 2: additionally the previous residual block's skip is added (x_{b+1} = IN(raw) + ShaveImage(x_b), models_video.lua
-  // :41-53) and x_{b+1} -- this block's input, which the NEXT block needs as its skip -- is written back as an operand by the
-  // tile that owns the pixel: the separate in_apply pass between two residual blocks disappears.
   int nl, nl_pad, nl_Hp, nl_Wp, nl_H, nl_W, nl_relu, nl_C;
-  const uint4 *sk_hi, *sk_lo;  // skip operand x_b: storage offset of logical (ry, x), channel block cb:
-  int sk_Cb, sk_slab16, sk_row0, sk_col0;  //   ((ry + sk_row0) * sk_Cb + cb) * sk_slab16 + x + sk_col0   (row0 / col0 include the shave)
-  uint4 *wb_hi, *wb_lo;        // write-back operand x_{b+1}
-  int wb_Cb, wb_slab16, wb_row0, wb_col0;
   const float *nl_raw;
   const double *nl_sums;
   const float *nl_gamma, *nl_beta;

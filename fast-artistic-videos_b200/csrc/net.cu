@@ -362,26 +362,6 @@ static int build_plan(fav_net *net, int H, int W, Plan **out) {
         if (cm.phases.size() == 1 && conv_res_eligible(cm, cm.phases[0])) { cs.raw.planar = 1; cs.raw.Wp = round_up(wo, 16); }
       }
       FAV_TRY(build_conv_jobs(net, *pl, cs, c, last, nullptr));
-      // first conv of a residual block that follows another residual block: the InstanceNorm + skip-add pass between the two
-      // blocks (x_{b+1} = IN(raw2_b) + ShaveImage(x_b)) moves into this conv's patch producers, which also write x_{b+1} back
-      // as the operand the NEXT block needs for its own skip (conv_res.cu, nl == 2)
-      if (op.kind == 1 && i == 0 && !cs.res.empty() && !pl->steps.empty() && pl->steps.back().kind == 1 &&
-          !getenv("FAV_NO_NL") && !getenv("FAV_NO_NL2")) {
-        PlanStep &ap = pl->steps.back();
-        const InDef &n = net->inorms[ap.inorm];
-        if (ap.skip >= 0 && ap.raw.planar && ap.dst == cs.src && n.C <= 256 && n.C == pl->ops[cs.src].C && c.pad == 0) {
-          ResJob &r = cs.res[0];
-          const Operand &sk = pl->ops[ap.skip], &wb = pl->ops[ap.dst];
-          r.nl = 2; r.nl_pad = c.pad; r.nl_raw = ap.raw.p; r.nl_Hp = ap.raw.Hp; r.nl_Wp = ap.raw.Wp; r.nl_H = ap.raw.H; r.nl_W = ap.raw.W;
-          r.nl_relu = ap.relu; r.nl_C = n.C; r.nl_sums = pl->stats + ap.stats_off; r.nl_gamma = n.d_gamma; r.nl_beta = n.d_beta;
-          r.nl_inv_count = 1.0 / ((double)ap.raw.H * ap.raw.W); r.nl_eps = 1e-5;
-          r.sk_hi = reinterpret_cast<const uint4 *>(sk.hi); r.sk_lo = reinterpret_cast<const uint4 *>(sk.lo);
-          r.sk_Cb = sk.Cb; r.sk_slab16 = sk.slab16(); r.sk_row0 = sk.padT + ap.shave; r.sk_col0 = sk.padL + ap.shave;
-          r.wb_hi = reinterpret_cast<uint4 *>(wb.hi); r.wb_lo = reinterpret_cast<uint4 *>(wb.lo);
-          r.wb_Cb = wb.Cb; r.wb_slab16 = wb.slab16(); r.wb_row0 = wb.padT; r.wb_col0 = wb.padL;
-          if (!sk.parity && !wb.parity) ap.fused_nl = true; else r.nl = 0;
-        }
-      }
       // second conv of a residual block: fold the preceding InstanceNorm + ReLU pass into its patch producers
       if (op.kind == 1 && i == 1 && !pl->steps.empty() && pl->steps.back().kind == 1 && !getenv("FAV_NO_NL")) {
         PlanStep &ap = pl->steps.back();

@@ -30,6 +30,8 @@ struct fav_session {
   } in[2];
   float *out[2] = {nullptr, nullptr};
   cudaEvent_t computed[2] = {nullptr, nullptr}, downloaded[2] = {nullptr, nullptr};
+  static constexpr int kDoneRing = 64;  // per-frame completion events for host threads (fav_session_frame_done)
+  cudaEvent_t done[kDoneRing] = {};
   bool out_used[2] = {false, false};
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   uint64_t frame = 0;
@@ -57,6 +59,8 @@ void fav_session_destroy(fav_session_t *s) {
     if (s->computed[i]) cudaEventDestroy(s->computed[i]);
     if (s->downloaded[i]) cudaEventDestroy(s->downloaded[i]);
   }
+  for (cudaEvent_t e : s->done)
+    if (e) cudaEventDestroy(e);
   if (s->t0) cudaEventDestroy(s->t0);
   if (s->t1) cudaEventDestroy(s->t1);
   if (s->s_h2d) cudaStreamDestroy(s->s_h2d);
@@ -89,6 +93,8 @@ int fav_session_create(fav_net_t *net, int H, int W, fav_session_t **out) {
     FAV_TRY(check_cuda(cudaEventCreateWithFlags(&s->computed[i], cudaEventDisableTiming), "cudaEventCreate"));
     FAV_TRY(check_cuda(cudaEventCreateWithFlags(&s->downloaded[i], cudaEventDisableTiming), "cudaEventCreate"));
   }
+  for (int i = 0; i < fav_session::kDoneRing; ++i)  // waited on by host threads: block, do not spin
+    FAV_TRY(check_cuda(cudaEventCreateWithFlags(&s->done[i], cudaEventDisableTiming | cudaEventBlockingSync), "cudaEventCreate"));
   FAV_TRY(check_cuda(cudaEventCreate(&s->t0), "cudaEventCreate"));
   FAV_TRY(check_cuda(cudaEventCreate(&s->t1), "cudaEventCreate"));
   *out = s.release();
@@ -140,6 +146,7 @@ static int session_step(fav_session *s, int mode, const float *content_host, con
   FAV_TRY(check_cuda(cudaStreamWaitEvent(s->s_d2h, s->computed[so], 0), "cudaStreamWaitEvent"));
   FAV_TRY(check_cuda(cudaMemcpyAsync(out_host, s->out[so], 3 * HW * 4, cudaMemcpyDeviceToHost, s->s_d2h), "D2H out"));
   FAV_TRY(check_cuda(cudaEventRecord(s->downloaded[so], s->s_d2h), "cudaEventRecord"));
+  FAV_TRY(check_cuda(cudaEventRecord(s->done[s->frame % fav_session::kDoneRing], s->s_d2h), "cudaEventRecord"));
   s->out_used[so] = true;
   s->have_prev = true;
   s->frame++;
@@ -169,16 +176,16 @@ int fav_session_run_next_image_flows(fav_session_t *s, const float *content_host
 }
 
 // the stylized frame of call number `frame_index` (0-based count of run_* calls on this session) has landed in its out_host
-// buffer; wait != 0 blocks until then.  (Each output slot has one "downloaded" event: if a later call already reused the
-// slot, this waits for that later frame -- never too short.)
+// buffer; wait != 0 blocks until then.  One completion event per frame in a ring of 64: frames older than that have landed
+// long ago (the ring slot then belongs to a later frame, and waiting for it is never too short).
 int fav_session_frame_done(fav_session_t *s, uint64_t frame_index, int wait) {
   FAV_REQUIRE(s && frame_index < s->frame, "fav_session_frame_done: frame %llu was never enqueued", (unsigned long long)frame_index);
-  cudaEvent_t ev = s->downloaded[frame_index & 1];
-  if (wait) return check_cuda(cudaEventSynchronize(ev), "cudaEventSynchronize(downloaded)");
+  cudaEvent_t ev = s->done[frame_index % fav_session::kDoneRing];
+  if (wait) return check_cuda(cudaEventSynchronize(ev), "cudaEventSynchronize(frame done)");
   cudaError_t e = cudaEventQuery(ev);
   if (e == cudaSuccess) return FAV_OK;
   if (e == cudaErrorNotReady) { set_error("frame %llu still in flight", (unsigned long long)frame_index); return FAV_ERR_INVALID; }
-  return check_cuda(e, "cudaEventQuery(downloaded)");
+  return check_cuda(e, "cudaEventQuery(frame done)");
 }
 
 int fav_session_sync(fav_session_t *s) {

@@ -25,7 +25,7 @@ net = models_video.synthetic_model("candy")
 opt = video.build_parser().parse_args(["-input_pattern", f"{d}/frame_%04d.ppm", "-flow_pattern", f"{d}/backward_[%d]_{{%d}}.flo",
                                        "-occlusions_pattern", f"{d}/reliable_[%d]_{{%d}}.pgm", "-output_prefix", f"{d}/out", "-num_frames", str(N)])
 out = {}
-for nd, ne, lvl in ((8, 32, 1), (16, 64, 1), (16, 96, 1), (16, 64, 6)):
+for nd, ne, lvl in ((8, 24, 1), (12, 40, 1), (16, 40, 1), (12, 40, 6)):
     video.run_native(opt, model_vid=net, n_decode=nd, n_encode=ne, png_level=lvl)
     r = video.run_native(opt, model_vid=net, n_decode=nd, n_encode=ne, png_level=lvl)
     out[f"native_dec{nd}_enc{ne}_z{lvl}"] = r["frames"] / r["seconds"]
