@@ -294,28 +294,34 @@ __global__ void __launch_bounds__(256) normalize_apply_kernel(float *__restrict_
 // streams the data through shared memory (double buffered, coalesced) so that the summing thread never waits for DRAM.
 constexpr int kAvgChunk = 4096;
 __global__ void __launch_bounds__(256) avg_scan_kernel(const float *__restrict__ m, int64_t n, float *__restrict__ avg) {
-  __shared__ float buf[2][kAvgChunk];
+  __shared__ __align__(16) float buf[2][kAvgChunk + 16];  // +16: the summing thread prefetches one batch past the chunk
   const int64_t nchunks = (n + kAvgChunk - 1) / kAvgChunk;
-  auto load = [&](int64_t c, int s) {
-    for (int i = threadIdx.x; i < kAvgChunk; i += 256) {
+  auto load = [&](int64_t c, int s, int first, int stride) {  // the tail of the last chunk is +0.0f: a + 0 = a exactly
+    for (int i = first; i < kAvgChunk; i += stride) {
       const int64_t g = c * kAvgChunk + i;
       buf[s][i] = g < n ? m[g] : 0.f;
     }
   };
-  load(0, 0);
+  if (threadIdx.x < 32) buf[threadIdx.x >> 4][kAvgChunk + (threadIdx.x & 15)] = 0.f;
+  load(0, 0, threadIdx.x, 256);
   __syncthreads();
   float a = 0.f;
   for (int64_t c = 0; c < nchunks; ++c) {
     const int s = (int)(c & 1);
     if (threadIdx.x == 0) {
-      const int cnt = (int)min((int64_t)kAvgChunk, n - c * kAvgChunk);
-#pragma unroll 8
-      for (int i = 0; i < cnt; ++i) a = __fadd_rn(a, buf[s][i]);
-    } else if (c + 1 < nchunks) {
-      for (int i = threadIdx.x - 1; i < kAvgChunk; i += 255) {
-        const int64_t g = (c + 1) * kAvgChunk + i;
-        buf[s ^ 1][i] = g < n ? m[g] : 0.f;
+      // 16 values per batch, the next batch's four LDS.128 are in flight while this batch's 16 dependent FADDs retire
+      const float4 *b4 = reinterpret_cast<const float4 *>(buf[s]);
+      float4 r0 = b4[0], r1 = b4[1], r2 = b4[2], r3 = b4[3];
+      for (int i = 0; i < kAvgChunk / 16; ++i) {
+        const float4 n0 = b4[4 * i + 4], n1 = b4[4 * i + 5], n2 = b4[4 * i + 6], n3 = b4[4 * i + 7];
+        a = __fadd_rn(a, r0.x); a = __fadd_rn(a, r0.y); a = __fadd_rn(a, r0.z); a = __fadd_rn(a, r0.w);
+        a = __fadd_rn(a, r1.x); a = __fadd_rn(a, r1.y); a = __fadd_rn(a, r1.z); a = __fadd_rn(a, r1.w);
+        a = __fadd_rn(a, r2.x); a = __fadd_rn(a, r2.y); a = __fadd_rn(a, r2.z); a = __fadd_rn(a, r2.w);
+        a = __fadd_rn(a, r3.x); a = __fadd_rn(a, r3.y); a = __fadd_rn(a, r3.z); a = __fadd_rn(a, r3.w);
+        r0 = n0; r1 = n1; r2 = n2; r3 = n3;
       }
+    } else if (c + 1 < nchunks) {
+      load(c + 1, s ^ 1, threadIdx.x - 1, 255);
     }
     __syncthreads();
   }

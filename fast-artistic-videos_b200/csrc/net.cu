@@ -821,8 +821,10 @@ int fav_run_next_image_flows(fav_net_t *net, const float *content, const float *
   Plan *pl;
   FAV_TRY(build_plan(net, H, W, &pl));
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = launch_temporal_stage(content, prev_rgb, flow_bw, flow_fw_uv, cert_raw, fill, flow_mask, nullptr, nullptr, &pl->ops[0],
-                                 net->reflect_pad, H, W, min_filter_r, border_mode, st);
+  static const bool no_stage = getenv("FAV_NO_STAGE") != nullptr;  // A/B timing: the three separate kernels
+  int rc = no_stage ? FAV_ERR_UNSUPPORTED
+                    : launch_temporal_stage(content, prev_rgb, flow_bw, flow_fw_uv, cert_raw, fill, flow_mask, nullptr, nullptr,
+                                            &pl->ops[0], net->reflect_pad, H, W, min_filter_r, border_mode, st);
   if (rc == FAV_ERR_UNSUPPORTED) {  // unaligned planes / W % 4 != 0: the three separate kernels
     const int64_t HW = (int64_t)H * W;
     if (!pl->cert_a) {

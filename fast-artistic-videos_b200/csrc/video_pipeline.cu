@@ -6,9 +6,11 @@
 //                     into PINNED ring slots (cudaHostAlloc); the wait-for-file protocol of the flow / occlusion producers
 //                     (utils.lua:74-80) and the [fmt] / {fmt} filename patterns (fast_artistic_video.lua:70-77) are kept
 //   calling thread    only enqueues frames on the session (3 CUDA streams inside: H2D / compute / D2H)
-//   encoder threads   wait for ONE frame each (fav_session_frame_done), quantise like image.save (clamp, x255, round) and
+//   completer thread  waits for the session's per-frame completion events in order (fav_session_frame_done)
+//   encoder threads   quantise a landed frame like image.save (clamp, x255, round) straight into Sub-filtered scanlines and
 //                     write "<prefix>-%05d.png" (fast_artistic_video.lua:161) with zlib; any PNG decoder returns the same
 //                     pixels as the synchronous driver's files
+// FAV_PIPE_STATS=1 prints where the host time went.
 // Host code only (no kernels); compiled by nvcc for the CUDA runtime calls.
 #include <zlib.h>
 
@@ -68,20 +70,23 @@ void png_chunk(std::vector<unsigned char> &out, const char type[4], const unsign
   if (n) out.insert(out.end(), data, data + n);
   put_be32(out, (uint32_t)crc32(0, out.data() + start, (uInt)(n + 4)));
 }
-// 8-bit RGB PNG (colour type 2, no interlace); rows pre-filtered with Sub (type 1)
-int write_png(const std::string &path, const unsigned char *rgb, int W, int H, int level) {
-  std::vector<unsigned char> raw((size_t)H * (1 + 3 * W));
-  for (int y = 0; y < H; ++y) {
-    unsigned char *dst = raw.data() + (size_t)y * (1 + 3 * W);
-    const unsigned char *src = rgb + (size_t)y * 3 * W;
-    *dst++ = 1;
-    for (int i = 0; i < 3 * W; ++i) dst[i] = (unsigned char)(src[i] - (i >= 3 ? src[i - 3] : 0));
-  }
-  uLongf bound = compressBound((uLong)raw.size());
-  std::vector<unsigned char> z(bound);
-  if (compress2(z.data(), &bound, raw.data(), (uLong)raw.size(), level) != Z_OK) return FAV_ERR_IO;
-  std::vector<unsigned char> out;
-  out.reserve(bound + 64);
+// 8-bit RGB PNG (colour type 2, no interlace) from scanlines that are already Sub-filtered (filter byte 1 + 3W bytes per row).
+// level 0 = stored; level 1 = zlib level 1 with Z_RLE (what libpng recommends for filtered rows when speed matters: on a
+// stylized 720p frame 32 ms instead of 72 ms at the same size); level >= 2 = that zlib level with Z_FILTERED.
+int write_png(const std::string &path, const unsigned char *raw, size_t raw_bytes, int W, int H, int level,
+              std::vector<unsigned char> &z, std::vector<unsigned char> &out) {
+  z_stream zs;
+  memset(&zs, 0, sizeof(zs));
+  if (deflateInit2(&zs, level, Z_DEFLATED, 15, 9, level <= 1 ? Z_RLE : Z_FILTERED) != Z_OK) return FAV_ERR_IO;
+  z.resize(deflateBound(&zs, (uLong)raw_bytes));
+  zs.next_in = const_cast<unsigned char *>(raw); zs.avail_in = (uInt)raw_bytes;
+  zs.next_out = z.data(); zs.avail_out = (uInt)z.size();
+  const int zrc = deflate(&zs, Z_FINISH);
+  const size_t zn = zs.total_out;
+  deflateEnd(&zs);
+  if (zrc != Z_STREAM_END) return FAV_ERR_IO;
+  out.clear();
+  out.reserve(zn + 64);
   const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
   out.insert(out.end(), sig, sig + 8);
   std::vector<unsigned char> ihdr;
@@ -89,7 +94,7 @@ int write_png(const std::string &path, const unsigned char *rgb, int W, int H, i
   const unsigned char tail[5] = {8, 2, 0, 0, 0};
   ihdr.insert(ihdr.end(), tail, tail + 5);
   png_chunk(out, "IHDR", ihdr.data(), ihdr.size());
-  png_chunk(out, "IDAT", z.data(), bound);
+  png_chunk(out, "IDAT", z.data(), zn);
   png_chunk(out, "IEND", nullptr, 0);
   FILE *f = fopen(path.c_str(), "wb");
   if (!f) return FAV_ERR_IO;
@@ -97,6 +102,29 @@ int write_png(const std::string &path, const unsigned char *rgb, int W, int H, i
   fclose(f);
   return ok ? FAV_OK : FAV_ERR_IO;
 }
+
+// image.save's quantisation (clamp to [0,1], x255, round; the same fp32 operations as the synchronous driver) of planar fp32
+// rows, written as Sub-filtered PNG scanlines
+void quantize_filter_rows(const float *planes, size_t HW, int W, int H, unsigned char *raw) {
+  for (int y = 0; y < H; ++y) {
+    unsigned char *dst = raw + (size_t)y * (1 + 3 * (size_t)W);
+    *dst++ = 1;
+    for (int c = 0; c < 3; ++c) {
+      const float *src = planes + (size_t)c * HW + (size_t)y * W;
+      unsigned char pv = 0;
+      for (int x = 0; x < W; ++x) {
+        float v = src[x];
+        v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+        v = floorf(v * 255.0f + 0.5f);
+        const unsigned char q = (unsigned char)(v < 0.f ? 0.f : (v > 255.f ? 255.f : v));
+        dst[3 * x + c] = (unsigned char)(q - pv);
+        pv = q;
+      }
+    }
+  }
+}
+
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct Slot {
   float *content = nullptr, *flow = nullptr, *cert = nullptr, *out = nullptr;  // pinned
@@ -143,7 +171,7 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
       return FAV_ERR_CUDA;
     }
   std::mutex mu;
-  std::condition_variable cv;
+  std::condition_variable cv_free, cv_dec, cv_enq, cv_done;  // one per class of waiter (no thundering herd of ~50 threads)
   std::atomic<int> next_decode{1}, next_encode{1};
   std::vector<int> ready(n + 2, 0);  // per frame: 1 decoded, 2 enqueued on the GPU, 3 landed in host memory, 4 written
   int err = FAV_OK;
@@ -151,7 +179,7 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
   auto fail = [&](int code, const std::string &msg) {
     std::lock_guard<std::mutex> lk(mu);
     if (err == FAV_OK) { err = code; err_msg = msg; }
-    cv.notify_all();
+    cv_free.notify_all(); cv_dec.notify_all(); cv_enq.notify_all(); cv_done.notify_all();
   };
   auto wait_for_file = [&](const std::string &path) {  // utils.lua:74-80
     if (file_exists(path)) return true;
@@ -165,16 +193,20 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
   };
   const std::string in_pat(input_pattern), flow_pat(flow_pattern), occ_pat(occlusions_pattern), out_prefix(output_prefix);
 
+  std::atomic<long long> t_decode{0}, t_quant{0}, t_png{0}, t_enc_wait{0}, t_dec_wait{0}, t_enq_wait{0};  // microseconds, all threads
+  auto us = [](double a, double b) { return (long long)((b - a) * 1e6); };
   auto decoder = [&]() {
     for (;;) {
       const int i = next_decode.fetch_add(1);
       if (i > n) return;
       Slot &s = slots[(i - 1) % depth];
+      const double w0 = now_s();
       {  // the slot is free once frame i - depth has been written
         std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return err != FAV_OK || i <= depth || ready[i - depth] == 4; });
+        cv_free.wait(lk, [&] { return err != FAV_OK || i <= depth || ready[i - depth] == 4; });
         if (err != FAV_OK) return;
       }
+      const double w1 = now_s();
       int rc = fav_pnm_read_f32(format_index(in_pat, i).c_str(), s.content, 3 * HW, 255.0f);
       if (rc == FAV_OK && i > 1) {
         const std::string cert_name = format_flow_name(occ_pat, i - 1, i), flow_name = format_flow_name(flow_pat, i - 1, i);
@@ -189,32 +221,32 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
       }
       if (rc != FAV_OK) { fail(rc, fav_last_error()); return; }
       { std::lock_guard<std::mutex> lk(mu); ready[i] = 1; }
-      cv.notify_all();
+      cv_dec.notify_all();
+      t_dec_wait += us(w0, w1); t_decode += us(w1, now_s());
     }
   };
   auto encoder = [&]() {
-    std::vector<unsigned char> rgb(3 * HW);
+    const size_t raw_bytes = (size_t)H * (1 + 3 * (size_t)W);
+    std::vector<unsigned char> raw(raw_bytes), z, file;
     for (;;) {
       const int i = next_encode.fetch_add(1);
       if (i > n) return;
+      const double w0 = now_s();
       {
         std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return err != FAV_OK || ready[i] == 3; });
+        cv_done.wait(lk, [&] { return err != FAV_OK || ready[i] == 3; });
         if (err != FAV_OK) return;
       }
+      const double w1 = now_s();
       const Slot &s = slots[(i - 1) % depth];
-      for (size_t k = 0; k < HW; ++k)
-        for (int c = 0; c < 3; ++c) {  // image.save: clamp to [0,1], x255, round (same fp32 operations as the synchronous driver)
-          float v = s.out[(size_t)c * HW + k];
-          v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
-          v = floorf(v * 255.0f + 0.5f);
-          rgb[3 * k + c] = (unsigned char)(v < 0.f ? 0.f : (v > 255.f ? 255.f : v));
-        }
+      quantize_filter_rows(s.out, HW, W, H, raw.data());
+      const double w2 = now_s();
       char name[4096];
       snprintf(name, sizeof(name), "%s-%05d.png", out_prefix.c_str(), i);
-      if (write_png(name, rgb.data(), W, H, png_level) != FAV_OK) { fail(FAV_ERR_IO, std::string("cannot write ") + name); return; }
+      if (write_png(name, raw.data(), raw_bytes, W, H, png_level, z, file) != FAV_OK) { fail(FAV_ERR_IO, std::string("cannot write ") + name); return; }
       { std::lock_guard<std::mutex> lk(mu); ready[i] = 4; }
-      cv.notify_all();
+      cv_free.notify_all();
+      t_enc_wait += us(w0, w1); t_quant += us(w1, w2); t_png += us(w2, now_s());
     }
   };
   // frames complete in order: ONE thread waits on the session's per-frame events (dozens of encoder threads blocking in the
@@ -223,12 +255,12 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
     for (int i = 1; i <= n; ++i) {
       {
         std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return err != FAV_OK || ready[i] == 2; });
+        cv_enq.wait(lk, [&] { return err != FAV_OK || ready[i] == 2; });
         if (err != FAV_OK) return;
       }
       if (fav_session_frame_done(sess, (uint64_t)(i - 1), 1) != FAV_OK) { fail(FAV_ERR_CUDA, fav_last_error()); return; }
       { std::lock_guard<std::mutex> lk(mu); ready[i] = 3; }
-      cv.notify_all();
+      cv_done.notify_all();
     }
   };
 
@@ -239,8 +271,10 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
   threads.emplace_back(completer);
   for (int i = 1; i <= n; ++i) {
     {
+      const double w0 = now_s();
       std::unique_lock<std::mutex> lk(mu);
-      cv.wait(lk, [&] { return err != FAV_OK || ready[i] == 1; });
+      cv_dec.wait(lk, [&] { return err != FAV_OK || ready[i] == 1; });
+      t_enq_wait += us(w0, now_s());
       if (err != FAV_OK) break;
     }
     Slot &s = slots[(i - 1) % depth];
@@ -248,13 +282,19 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
                           : fav_session_run_next_image(sess, s.content, s.flow, s.cert, min_filter_r, FAV_BORDER_PER_TAP, s.out);
     if (rc != FAV_OK) { fail(rc, fav_last_error()); break; }
     { std::lock_guard<std::mutex> lk(mu); ready[i] = 2; }
-    cv.notify_all();
+    cv_enq.notify_all();
   }
   for (std::thread &t : threads) t.join();
   fav_session_sync(sess);
   const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   free_slots();
   if (seconds) *seconds = dt;
+  if (getenv("FAV_PIPE_STATS"))  // where the host time went: per-frame averages over all worker threads
+    fprintf(stderr, "{\"pipeline_stats\": {\"frames\": %d, \"seconds\": %.4f, \"decode_ms\": %.2f, \"decode_wait_slot_ms\": %.2f, "
+            "\"quantize_filter_ms\": %.2f, \"deflate_write_ms\": %.2f, \"encode_wait_frame_ms\": %.2f, \"enqueue_wait_decode_ms\": %.2f, "
+            "\"n_decode\": %d, \"n_encode\": %d, \"depth\": %d, \"png_level\": %d}}\n",
+            n, dt, t_decode / 1e3 / n, t_dec_wait / 1e3 / n, t_quant / 1e3 / n, t_png / 1e3 / n, t_enc_wait / 1e3 / n,
+            t_enq_wait / 1e3 / n, n_decode, n_encode, depth, png_level);
   if (err != FAV_OK) { set_error("fav_video_pipeline_run: %s", err_msg.c_str()); return err; }
   return FAV_OK;
 }

@@ -80,7 +80,12 @@ def stream_clips(num_clips, n_frames, chunk, in_shapes, out_shape, load_chunk, p
     """in_shapes: per-frame shapes of the input tensors of a clip, e.g. [(3,H,W), (2,H,W), (2,H,W)]; out_shape e.g. (3,H,W).
     load_chunk(clip, f0, f1) -> list of tensors [f1-f0, *shape] (rank src only; host or device; moved to `device`),
     process_chunk(clip, f0, inputs) -> tensor [f1-f0, *out_shape] on `device` (owner ranks, called in frame order),
-    store_chunk(clip, f0, out) (rank src only).  Returns dict(comm_wait_s, steps, bytes_in, bytes_out) of this rank."""
+    store_chunk(clip, f0, out) (rank src only).  Returns dict(comm_wait_s, steps, bytes_in, bytes_out) of this rank.
+
+    On a CUDA device three streams are used: the caller's current stream runs process_chunk only; a transfer stream carries
+    the uploads of load_chunk and the NCCL sends / receives (so chunk k+1 travels while chunk k is processed); a third stream
+    carries store_chunk (the D2H of results).  The host is never more than two chunk steps ahead of the device."""
+    import contextlib
     import time
 
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -90,6 +95,15 @@ def stream_clips(num_clips, n_frames, chunk, in_shapes, out_shape, load_chunk, p
     inbuf = {}   # (clip, k) -> list of device tensors
     outbuf = {}  # (clip, k) -> device tensor
     stats = dict(comm_wait_s=0.0, steps=nsteps, bytes_in=0, bytes_out=0)
+    use_cuda = device is not None and torch.device(device).type == "cuda"
+    if use_cuda:
+        main = torch.cuda.current_stream(device)
+        xs, ss = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        xs.wait_stream(main); ss.wait_stream(main)
+    done_ev, xfer_ev = {}, {}  # step -> event: chunk processed (main stream) / transfers of the step complete (transfer stream)
+
+    def on(stream):
+        return torch.cuda.stream(stream) if use_cuda else contextlib.nullcontext()
 
     def to_dev(t):
         return t.to(device, non_blocking=True) if device is not None else t
@@ -97,53 +111,70 @@ def stream_clips(num_clips, n_frames, chunk, in_shapes, out_shape, load_chunk, p
     def exchange(k):
         """post the transfers of step k: inputs of chunk k (src -> owners) and outputs of chunk k-2 (owners -> src)"""
         ops = []
-        if 0 <= k < nsteps:
-            f0, f1 = span(k)
-            for c in range(num_clips):
-                o = owner(c, world)
-                if rank == src:
-                    ts = [to_dev(t) for t in load_chunk(c, f0, f1)]
-                    if o == src:
-                        inbuf[(c, k)] = ts
-                    else:
-                        for t in ts:
-                            ops.append(dist.P2POp(dist.isend, t.contiguous(), o))
-                            stats["bytes_in"] += t.numel() * t.element_size()
-                        inbuf[(c, k)] = ts  # keep alive until the send completes
-                elif rank == o:
-                    ts = [torch.empty((f1 - f0,) + tuple(s), dtype=dtype, device=device) for s in in_shapes]
-                    for t in ts:
-                        ops.append(dist.P2POp(dist.irecv, t, src))
-                    inbuf[(c, k)] = ts
         kk = k - 2
-        if 0 <= kk < nsteps:
-            f0, f1 = span(kk)
-            for c in range(num_clips):
-                o = owner(c, world)
-                if o == src:
-                    continue
-                if rank == o:
-                    ops.append(dist.P2POp(dist.isend, outbuf[(c, kk)].contiguous(), src))
-                    stats["bytes_out"] += outbuf[(c, kk)].numel() * outbuf[(c, kk)].element_size()
-                elif rank == src:
-                    t = torch.empty((f1 - f0,) + tuple(out_shape), dtype=dtype, device=device)
-                    ops.append(dist.P2POp(dist.irecv, t, o))
-                    outbuf[(c, kk)] = t
-        return dist.batch_isend_irecv(ops) if ops else []
+        with on(xs if use_cuda else None):
+            if use_cuda and kk in done_ev:
+                xs.wait_event(done_ev[kk])  # the outputs of chunk k-2 are sent from this stream
+            if 0 <= k < nsteps:
+                f0, f1 = span(k)
+                for c in range(num_clips):
+                    o = owner(c, world)
+                    if rank == src:
+                        ts = [to_dev(t) for t in load_chunk(c, f0, f1)]
+                        if o == src:
+                            inbuf[(c, k)] = ts
+                        else:
+                            for t in ts:
+                                ops.append(dist.P2POp(dist.isend, t.contiguous(), o))
+                                stats["bytes_in"] += t.numel() * t.element_size()
+                            inbuf[(c, k)] = ts  # keep alive until the send completes
+                    elif rank == o:
+                        ts = [torch.empty((f1 - f0,) + tuple(s), dtype=dtype, device=device) for s in in_shapes]
+                        for t in ts:
+                            ops.append(dist.P2POp(dist.irecv, t, src))
+                        inbuf[(c, k)] = ts
+            if 0 <= kk < nsteps:
+                f0, f1 = span(kk)
+                for c in range(num_clips):
+                    o = owner(c, world)
+                    if o == src:
+                        continue
+                    if rank == o:
+                        t = outbuf[(c, kk)].contiguous()
+                        if use_cuda:
+                            t.record_stream(xs)
+                        ops.append(dist.P2POp(dist.isend, t, src))
+                        stats["bytes_out"] += t.numel() * t.element_size()
+                    elif rank == src:
+                        t = torch.empty((f1 - f0,) + tuple(out_shape), dtype=dtype, device=device)
+                        ops.append(dist.P2POp(dist.irecv, t, o))
+                        outbuf[(c, kk)] = t
+            return dist.batch_isend_irecv(ops) if ops else []
 
     def finish(works, k):
         t0 = time.perf_counter()
-        for w in works:
-            w.wait()
+        with on(xs if use_cuda else None):
+            for w in works:
+                w.wait()  # gloo: the host waits; NCCL: the transfer stream waits
+            if use_cuda:
+                xfer_ev[k] = xs.record_event()
         stats["comm_wait_s"] += time.perf_counter() - t0
         kk = k - 2
         if 0 <= kk < nsteps:
             f0, _ = span(kk)
-            for c in range(num_clips):
-                if rank == src:
-                    store_chunk(c, f0, outbuf.pop((c, kk)))
-                elif owner(c, world) == rank:
-                    outbuf.pop((c, kk), None)
+            with on(ss if use_cuda else None):
+                if use_cuda:
+                    ss.wait_event(xfer_ev[k])      # outputs received from the other ranks
+                    if kk in done_ev:
+                        ss.wait_event(done_ev[kk])  # outputs computed here
+                for c in range(num_clips):
+                    if rank == src:
+                        t = outbuf.pop((c, kk))
+                        if use_cuda:
+                            t.record_stream(ss)
+                        store_chunk(c, f0, t)
+                    elif owner(c, world) == rank:
+                        outbuf.pop((c, kk), None)
         if rank == src and 0 <= k < nsteps:  # remote clips' staging buffers of step k are on the wire no longer
             for c in range(num_clips):
                 if owner(c, world) != src:
@@ -155,7 +186,19 @@ def stream_clips(num_clips, n_frames, chunk, in_shapes, out_shape, load_chunk, p
         pending = exchange(k + 1)          # in flight while chunk k is processed
         if k < nsteps:
             f0, _ = span(k)
+            if use_cuda:
+                main.wait_event(xfer_ev[k])
+                if k - 2 in done_ev:
+                    done_ev[k - 2].synchronize()  # throttle: the host stays at most two chunk steps ahead
             for c in mine:
-                outbuf[(c, k)] = process_chunk(c, f0, inbuf.pop((c, k)))
+                ts = inbuf.pop((c, k))
+                if use_cuda:
+                    for t in ts:
+                        t.record_stream(main)
+                outbuf[(c, k)] = process_chunk(c, f0, ts)
+            if use_cuda:
+                done_ev[k] = main.record_event()
         finish(pending, k + 1)
+    if use_cuda:
+        main.wait_stream(xs); main.wait_stream(ss)
     return stats

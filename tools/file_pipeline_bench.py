@@ -25,7 +25,8 @@ net = models_video.synthetic_model("candy")
 opt = video.build_parser().parse_args(["-input_pattern", f"{d}/frame_%04d.ppm", "-flow_pattern", f"{d}/backward_[%d]_{{%d}}.flo",
                                        "-occlusions_pattern", f"{d}/reliable_[%d]_{{%d}}.pgm", "-output_prefix", f"{d}/out", "-num_frames", str(N)])
 out = {}
-for nd, ne, lvl in ((8, 24, 1), (12, 40, 1), (16, 40, 1), (12, 40, 6)):
+os.environ["FAV_PIPE_STATS"] = "1"
+for nd, ne, lvl in ((8, 24, 1), (16, 40, 1), (16, 40, 0), (16, 40, 6)):
     video.run_native(opt, model_vid=net, n_decode=nd, n_encode=ne, png_level=lvl)
     r = video.run_native(opt, model_vid=net, n_decode=nd, n_encode=ne, png_level=lvl)
     out[f"native_dec{nd}_enc{ne}_z{lvl}"] = r["frames"] / r["seconds"]
@@ -45,6 +46,10 @@ core.run_fast_neural_video(opt_s, drv.func_load_image, drv.func_load_cert, None,
                            drv.func_save_image, model_vid=net)
 torch.cuda.synchronize()
 out["synchronous_driver"] = ns / (time.perf_counter() - t0)
-out["frames"] = N; out["cpus"] = os.cpu_count()
+out["frames"] = N; out["cpus"] = os.cpu_count(); out["cpus_affinity"] = len(os.sched_getaffinity(0))
+try:
+    out["cgroup_cpu_max"] = open("/sys/fs/cgroup/cpu.max").read().strip()
+except OSError:
+    out["cgroup_cpu_max"] = None
 print(json.dumps(out))
 shutil.rmtree(d, ignore_errors=True)
