@@ -86,12 +86,7 @@ __device__ __forceinline__ void nl_slab(const ResJob &job, const float *nl_tab, 
         float a = (v[k][2 * i] - tm[2 * i]) * ts[2 * i] + tb[2 * i], b = (v[k][2 * i + 1] - tm[2 * i + 1]) * ts[2 * i + 1] + tb[2 * i + 1];
         if (job.nl_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
         if (!ok) { a = 0.f; b = 0.f; }
-        a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);  // same values as split_store8
-        const __half2 hh = __floats2half2_rn(a, b);
-        const float2 hf = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
-        h[i] = *reinterpret_cast<const uint32_t *>(&hh);
-        l[i] = *reinterpret_cast<const uint32_t *>(&ll);
+        split_pair(a, b, h[i], l[i]);  // same values as split_store8
       }
       *reinterpret_cast<uint4 *>(drow + (uint32_t)p * 16u) = make_uint4(h[0], h[1], h[2], h[3]);
       *reinterpret_cast<uint4 *>(drow + kResStageBytes + (uint32_t)p * 16u) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -139,11 +134,8 @@ __global__ void __launch_bounds__(kResThreads, 1) conv_res_kernel(const __grid_c
     {
       const int c = (int)threadIdx.x - 128;
       if (c < job.nl_C) {
-        const double mean = job.nl_sums[c] * job.nl_inv_count;
-        double var = job.nl_sums[job.nl_C + c] * job.nl_inv_count - mean * mean;
-        if (var < 0) var = 0;
-        sh->nl_tab[c] = (float)mean;
-        sh->nl_tab[kResNlMaxC + c] = (float)((double)job.nl_gamma[c] / sqrt(var + job.nl_eps));
+        in_finalize(job.nl_sums[c], job.nl_sums[job.nl_C + c], job.nl_inv_count, job.nl_eps, job.nl_gamma[c], sh->nl_tab[c],
+                    sh->nl_tab[kResNlMaxC + c]);
         sh->nl_tab[2 * kResNlMaxC + c] = job.nl_beta[c];
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");

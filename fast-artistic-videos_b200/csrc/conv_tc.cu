@@ -151,11 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   float *nl_tab = reinterpret_cast<float *>(sh + 1) + (256 + 8 * 2 * 128);
   if (job.nl && (int)threadIdx.x < job.nl_C) {
     const int c = threadIdx.x;
-    const double mean = job.nl_sums[c] * job.nl_inv_count;
-    double var = job.nl_sums[job.nl_C + c] * job.nl_inv_count - mean * mean;
-    if (var < 0) var = 0;
-    nl_tab[c] = (float)mean;
-    nl_tab[kNlMaxC + c] = (float)((double)job.nl_gamma[c] / sqrt(var + job.nl_eps));
+    in_finalize(job.nl_sums[c], job.nl_sums[job.nl_C + c], job.nl_inv_count, job.nl_eps, job.nl_gamma[c], nl_tab[c], nl_tab[kNlMaxC + c]);
     nl_tab[2 * kNlMaxC + c] = job.nl_beta[c];
   }
   tc_fence_before();
@@ -221,12 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               uint32_t h[4], l[4];  // same values as split_store8 (net_kernels.cu), packed two per conversion
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float a = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
-                const __half2 hh = __floats2half2_rn(a, b);
-                const float2 hf = __half22float2(hh);
-                const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
-                h[i] = *reinterpret_cast<const uint32_t *>(&hh);
-                l[i] = *reinterpret_cast<const uint32_t *>(&ll);
+                split_pair(v[2 * i], v[2 * i + 1], h[i], l[i]);
               }
               *reinterpret_cast<uint4 *>(drow + (uint32_t)p * 16u) = make_uint4(h[0], h[1], h[2], h[3]);
               *reinterpret_cast<uint4 *>(drow + a_stage_bytes + (uint32_t)p * 16u) = make_uint4(l[0], l[1], l[2], l[3]);

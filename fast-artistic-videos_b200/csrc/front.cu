@@ -352,20 +352,47 @@ __global__ void __launch_bounds__(256) temporal_stage_kernel(
   const int p = r / 2, bx = blockIdx.x * TS_TX, by = blockIdx.y * TS_TY;
   const int tw = TS_TX + 2 * p, th = TS_TY + 2 * p;
   const int64_t HW = (int64_t)H * W;
-  for (int i = threadIdx.x; i < tw * th; i += 256) {
-    const int ty = i / tw, tx = i - ty * tw;
-    const int gy = by + ty - p, gx = bx + tx - p;
-    float v = INFINITY;  // outside the image: ignored by the max-pooling of utils.min_filter (-inf padding)
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      const int64_t o = (int64_t)gy * W + gx;
-      if (MODE == 0) {
-        // flow = (dy, dx) = (v, u) of the backward flow = flow1 of the checker
-        v = check_pixel(fw_u, fw_v, __ldg(flow + HW + o), __ldg(flow + o), gx, gy, W, H, nullptr, 0.f) ? 1.f : 0.f;
-      } else {
-        v = __ldg(cert_raw + o);
+  if (MODE == 0) {
+    // kTsBatch pixels per thread and pass: first the (coalesced) backward-flow loads of all of them, then all their forward-flow
+    // gathers, then the arithmetic -- up to 8 * kTsBatch loads in flight per thread instead of one pixel's dependent chain
+    constexpr int kTsBatch = 3;
+    for (int i0 = threadIdx.x; i0 < tw * th; i0 += 256 * kTsBatch) {
+      int gx[kTsBatch], gy[kTsBatch], ty[kTsBatch], tx[kTsBatch];
+      float u2[kTsBatch], v2[kTsBatch];
+      bool in[kTsBatch];
+#pragma unroll
+      for (int k = 0; k < kTsBatch; ++k) {
+        const int i = i0 + k * 256;
+        ty[k] = i / tw; tx[k] = i - ty[k] * tw;
+        gy[k] = by + ty[k] - p; gx[k] = bx + tx[k] - p;
+        in[k] = i < tw * th && gy[k] >= 0 && gy[k] < H && gx[k] >= 0 && gx[k] < W;
+        u2[k] = v2[k] = 0.f;
+        if (in[k]) {  // flow = (dy, dx) = (v, u) of the backward flow = flow1 of the checker
+          const int64_t o = (int64_t)gy[k] * W + gx[k];
+          u2[k] = __ldg(flow + HW + o); v2[k] = __ldg(flow + o);
+        }
+      }
+      CheckTaps t[kTsBatch];
+#pragma unroll
+      for (int k = 0; k < kTsBatch; ++k) {
+        t[k].inside = false;
+        if (in[k]) t[k] = check_load(fw_u, fw_v, u2[k], v2[k], gx[k], gy[k], W, H);
+      }
+#pragma unroll
+      for (int k = 0; k < kTsBatch; ++k) {
+        if (i0 + k * 256 >= tw * th) break;
+        // outside the image: ignored by the max-pooling of utils.min_filter (-inf padding)
+        cs[ty[k]][tx[k]] = in[k] ? (check_eval(t[k], u2[k], v2[k], gx[k], gy[k], W, nullptr, 0.f) ? 1.f : 0.f) : INFINITY;
       }
     }
-    cs[ty][tx] = v;
+  } else {
+    for (int i = threadIdx.x; i < tw * th; i += 256) {
+      const int ty = i / tw, tx = i - ty * tw;
+      const int gy = by + ty - p, gx = bx + tx - p;
+      float v = INFINITY;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(cert_raw + (int64_t)gy * W + gx);
+      cs[ty][tx] = v;
+    }
   }
   __syncthreads();
   if (p > 0) {

@@ -103,25 +103,28 @@ int launch_in_stats(const RawTensor &raw, double *sums, cudaStream_t st) {
 // ---- in_apply ----------------------------------------------------------------------------------------
 // mean / gamma*rstd / beta of the block's 8 channels are derived from the (double) sums by the first 8 threads:
 // biased variance, eps inside the sqrt (nn.SpatialBatchNormalization in training mode, InstanceNormalization.lua:39-50)
+template <int ITER>
 __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const double *__restrict__ sums,
                                                        const float *__restrict__ gamma, const float *__restrict__ beta,
                                                        double inv_count, double eps, int relu, Operand skip, int has_skip,
                                                        int shave, Operand dst) {
   __shared__ float s_mean[8], s_scale[8], s_beta[8];
-  const int xbase = blockIdx.x * (128 * kApplyIter) + threadIdx.x;
+  const int xbase = blockIdx.x * (128 * ITER) + threadIdx.x;
   const int y = blockIdx.y, cb = blockIdx.z;
   // 1. every streaming load of the thread is requested first (they do not depend on the statistics): the per-block
   //    finalisation below (dependent global loads + double sqrt / divide on 8 threads) then runs in their shadow
-  float v[kApplyIter][8];
-  uint4 skh[kApplyIter], skl[kApplyIter];
+  float v[ITER][8];
+  uint4 skh[ITER], skl[ITER];
   const float4 *rp = reinterpret_cast<const float4 *>(raw.p);
 #pragma unroll
-  for (int it = 0; it < kApplyIter; ++it) {
+  for (int it = 0; it < ITER; ++it) {
     const int x = xbase + it * 128;
     if (x < raw.W) {
       if (raw.planar) {  // output of conv_res.cu: one plane per channel, lanes run along x (128-byte coalesced per plane)
+        const float *p0 = raw.p + raw.offp(cb * 8, y, x);
+        const int64_t plane = (int64_t)raw.Hp * raw.Wp;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[it][i] = __ldg(raw.p + raw.offp(cb * 8 + i, y, x));
+        for (int i = 0; i < 8; ++i) v[it][i] = __ldg(p0 + i * plane);
       } else {
         const float4 a = __ldg(rp + raw.off4(y, 2 * cb, x)), b = __ldg(rp + raw.off4(y, 2 * cb + 1, x));
         v[it][0] = a.x; v[it][1] = a.y; v[it][2] = a.z; v[it][3] = a.w; v[it][4] = b.x; v[it][5] = b.y; v[it][6] = b.z; v[it][7] = b.w;
@@ -136,17 +139,13 @@ __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const doub
   // 2. mean / gamma * rstd / beta of the block's 8 channels
   if (threadIdx.x < 8) {
     int c = cb * 8 + threadIdx.x;
-    double mean = sums[c] * inv_count;
-    double var = sums[raw.C + c] * inv_count - mean * mean;
-    if (var < 0) var = 0;
-    s_mean[threadIdx.x] = (float)mean;
-    s_scale[threadIdx.x] = (float)((double)gamma[c] / sqrt(var + eps));
+    in_finalize(sums[c], sums[raw.C + c], inv_count, eps, gamma[c], s_mean[threadIdx.x], s_scale[threadIdx.x]);
     s_beta[threadIdx.x] = beta[c];
   }
   __syncthreads();
   // 3. normalise (+ReLU) (+skip), split into fp16 hi / lo, store the next operand
 #pragma unroll
-  for (int it = 0; it < kApplyIter; ++it) {
+  for (int it = 0; it < ITER; ++it) {
     const int x = xbase + it * 128;
     if (x >= raw.W) break;
 #pragma unroll
@@ -171,10 +170,18 @@ __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const doub
 
 int launch_in_apply(const RawTensor &raw, const double *sums, const float *gamma, const float *beta, float eps, int relu,
                     const Operand *skip, int shave, const Operand &dst, cudaStream_t st) {
-  dim3 grid(ceil_div(raw.W, 128 * kApplyIter), raw.H, raw.C / 8);
+  // pixels per thread: amortises the per-block finalisation against registers (occupancy); FAV_APPLY_ITER = 2|3|4 for A/B timing
+  static const int forced = getenv("FAV_APPLY_ITER") ? atoi(getenv("FAV_APPLY_ITER")) : 0;
+  const int iter = forced >= 2 && forced <= 4 ? forced : kApplyIter;
+  dim3 grid(ceil_div(raw.W, 128 * iter), raw.H, raw.C / 8);
   Operand sk = skip ? *skip : Operand();
-  in_apply_kernel<<<grid, 128, 0, st>>>(raw, sums, gamma, beta, 1.0 / ((double)raw.H * raw.W), (double)eps, relu, sk,
-                                        skip ? 1 : 0, shave, dst);
+  const double inv = 1.0 / ((double)raw.H * raw.W);
+  if (iter == 2)
+    in_apply_kernel<2><<<grid, 128, 0, st>>>(raw, sums, gamma, beta, inv, (double)eps, relu, sk, skip ? 1 : 0, shave, dst);
+  else if (iter == 3)
+    in_apply_kernel<3><<<grid, 128, 0, st>>>(raw, sums, gamma, beta, inv, (double)eps, relu, sk, skip ? 1 : 0, shave, dst);
+  else
+    in_apply_kernel<4><<<grid, 128, 0, st>>>(raw, sums, gamma, beta, inv, (double)eps, relu, sk, skip ? 1 : 0, shave, dst);
   return post_launch("in_apply");
 }
 
@@ -224,11 +231,7 @@ __global__ void __launch_bounds__(128) up_apply_kernel(Operand src, const double
   const int y = blockIdx.y, cb = blockIdx.z;
   if (threadIdx.x < 8) {
     int c = cb * 8 + threadIdx.x;
-    double mean = sums[c] * inv_count;
-    double var = sums[src.C + c] * inv_count - mean * mean;
-    if (var < 0) var = 0;
-    s_mean[threadIdx.x] = (float)mean;
-    s_scale[threadIdx.x] = (float)((double)gamma[c] / sqrt(var + eps));
+    in_finalize(sums[c], sums[src.C + c], inv_count, eps, gamma[c], s_mean[threadIdx.x], s_scale[threadIdx.x]);
     s_beta[threadIdx.x] = beta[c];
   }
   __syncthreads();
