@@ -128,4 +128,30 @@ int fav_pnm_read_f32(const char *path, float *out, size_t capacity_floats, float
   }
   return FAV_OK;
 }
+
+// the raw payloads, for callers that convert on the GPU (fav_session_run_frame_bytes): the P5 / P6 bytes as stored
+// (interleaved RGB) and the .flo (u,v) pairs as stored; sizes are returned and validated against the capacity
+int fav_pnm_read_u8(const char *path, unsigned char *out, size_t capacity_bytes, int *W, int *H, int *C) {
+  if (!path || !out || !W || !H || !C) { fav::set_error("fav_pnm_read_u8: null argument"); return FAV_ERR_INVALID; }
+  File fl(path);
+  if (!fl.f) { fav::set_error("Could not open %s", path); return FAV_ERR_IO; }
+  int rc = pnm_header(fl.f, path, W, H, C);
+  if (rc != FAV_OK) return rc;
+  const size_t n = (size_t)*W * *H * *C;
+  if (n > capacity_bytes) { fav::set_error("%s: %dx%dx%d image does not fit the caller's buffer", path, *W, *H, *C); return FAV_ERR_IO; }
+  if (fread(out, 1, n, fl.f) != n) { fav::set_error("%s: truncated PNM payload", path); return FAV_ERR_IO; }
+  return FAV_OK;
+}
+
+int fav_flo_read_raw(const char *path, float *out_uv_pairs, size_t capacity_floats, int *W, int *H) {
+  if (!path || !out_uv_pairs || !W || !H) { fav::set_error("fav_flo_read_raw: null argument"); return FAV_ERR_INVALID; }
+  File fl(path);
+  if (!fl.f) { fav::set_error("Could not open %s", path); return FAV_ERR_IO; }
+  int rc = flo_header(fl.f, path, W, H);
+  if (rc != FAV_OK) return rc;
+  const size_t n = 2 * (size_t)*W * *H;
+  if (n > capacity_floats) { fav::set_error("%s: %dx%d flow does not fit the caller's buffer (%zu floats)", path, *W, *H, capacity_floats); return FAV_ERR_IO; }
+  if (fread(out_uv_pairs, sizeof(float), n, fl.f) != n) { fav::set_error("%s: truncated .flo payload", path); return FAV_ERR_IO; }
+  return FAV_OK;
+}
 }

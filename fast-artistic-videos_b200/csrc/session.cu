@@ -25,10 +25,13 @@ struct fav_session {
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
   struct InSet {
     float *content = nullptr, *flow = nullptr, *flow_fw = nullptr, *cert_raw = nullptr, *cert = nullptr;
+    unsigned char *rgb8 = nullptr, *cert8 = nullptr;  // file payloads (fav_session_run_frame_bytes), allocated on first use
+    float *flo_uv = nullptr;
     cudaEvent_t uploaded = nullptr, consumed = nullptr;
     bool used = false;
   } in[2];
   float *out[2] = {nullptr, nullptr};
+  unsigned char *rows8[2] = {nullptr, nullptr};  // Sub-filtered PNG scanlines of out[i] (fav_session_run_frame_bytes)
   cudaEvent_t computed[2] = {nullptr, nullptr}, downloaded[2] = {nullptr, nullptr};
   static constexpr int kDoneRing = 64;  // per-frame completion events for host threads (fav_session_frame_done)
   cudaEvent_t done[kDoneRing] = {};
@@ -46,6 +49,51 @@ static int s_alloc(fav_session *s, float **p, size_t n) {
   *p = (float *)d;
   return FAV_OK;
 }
+
+namespace {
+// ---- file payloads <-> planes (f-2): what image.load / flowFile.load / image.save do on the host in the reference
+// (fast_artistic_video.lua:95,103,161; flowFileLoader.lua:28-34), moved behind the copy engines.  Same fp32 operations as the
+// host readers of flo_io.cpp and the quantisation of video_pipeline.cu, so files and frames are bit-identical either way.
+__global__ void __launch_bounds__(256) decode_bytes_kernel(const unsigned char *__restrict__ rgb, const float2 *__restrict__ flo,
+                                                           const unsigned char *__restrict__ cert8, int invert,
+                                                           float *__restrict__ content, float *__restrict__ flow,
+                                                           float *__restrict__ cert, int64_t HW) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= HW) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) content[c * HW + i] = __fdiv_rn((float)rgb[3 * i + c], 255.0f);  // image.load: byte / 255
+  if (flo) {
+    const float2 f = __ldg(flo + i);  // .flo payload: (u, v) pairs; the loader returns [dy = v, dx = u] (flowFileLoader.lua:31-32)
+    flow[i] = f.y; flow[HW + i] = f.x;
+  }
+  if (cert8) {
+    float c = __fdiv_rn((float)cert8[i], 255.0f);
+    if (invert) c = __fsub_rn(1.0f, c);  // -invert_occlusion (fast_artistic_video.lua:105-107)
+    cert[i] = c;
+  }
+}
+
+__device__ __forceinline__ int quantize_u8(float v) {  // image.save: clamp to [0,1], x255, round
+  v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+  v = floorf(__fadd_rn(__fmul_rn(v, 255.0f), 0.5f));
+  return (int)(v < 0.f ? 0.f : (v > 255.f ? 255.f : v));
+}
+
+// rows: H x (1 + 3W) bytes = PNG scanlines, filter type 1 (Sub) -- ready for deflate
+__global__ void __launch_bounds__(256) encode_rows_kernel(const float *__restrict__ out, unsigned char *__restrict__ rows, int H, int W) {
+  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int64_t HW = (int64_t)H * W;
+  unsigned char *dst = rows + (int64_t)y * (1 + 3 * (int64_t)W);
+  if (x == 0) dst[0] = 1;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float *src = out + c * HW + (int64_t)y * W;
+    const int q = quantize_u8(src[x]), pq = x > 0 ? quantize_u8(src[x - 1]) : 0;
+    dst[1 + 3 * x + c] = (unsigned char)(q - pq);
+  }
+}
+}  // namespace
 
 extern "C" {
 
@@ -173,6 +221,69 @@ int fav_session_run_next_image_flows(fav_session_t *s, const float *content_host
                                      const float *flow_fw_uv_host, int min_filter_r, int border_mode, float *out_host) {
   FAV_REQUIRE(flow_bw_uv_host && flow_fw_uv_host, "fav_session_run_next_image_flows: null flow");
   return session_step(s, 2, content_host, flow_bw_uv_host, flow_fw_uv_host, nullptr, min_filter_r, border_mode, out_host);
+}
+
+// One frame from FILE PAYLOADS: rgb_hwc = the P6 payload (H*W*3 bytes), flo_uv = the .flo payload (H*W (u,v) float pairs) and
+// cert8 = the P5 payload of the certainty (both NULL for the first frame / a single image); png_rows_host receives
+// H*(1+3W) bytes of Sub-filtered PNG scanlines of the stylized frame.  The byte <-> float conversions run on the copy
+// streams (decode after the H2D, encode before the D2H), the compute stream runs exactly what fav_session_run_next_image runs.
+int fav_session_run_frame_bytes(fav_session_t *s, const unsigned char *rgb_hwc, const float *flo_uv, const unsigned char *cert8,
+                                int invert_occlusion, int min_filter_r, int border_mode, unsigned char *png_rows_host) {
+  FAV_REQUIRE(s && rgb_hwc && png_rows_host, "fav_session_run_frame_bytes: null argument");
+  FAV_REQUIRE((flo_uv != nullptr) == (cert8 != nullptr), "fav_session_run_frame_bytes: flow and certainty come together");
+  const bool first = flo_uv == nullptr;
+  FAV_REQUIRE(first || s->have_prev, "fav_session_run_frame_bytes: no previous frame");
+  FAV_REQUIRE(min_filter_r == 0 || ((min_filter_r & 1) && min_filter_r <= 15), "occlusions_min_filter must be odd <= 15");
+  const int H = s->H, W = s->W;
+  const size_t HW = (size_t)H * W, row_bytes = (size_t)H * (1 + 3 * (size_t)W);
+  const int si = (int)(s->frame & 1), so = si;
+  fav_session::InSet &in = s->in[si];
+  if (!in.rgb8) {
+    for (int i = 0; i < 2; ++i) {
+      void *d = nullptr;
+      FAV_TRY(check_cuda(cudaMalloc(&d, 3 * HW), "cudaMalloc(session bytes)")); s->allocs.push_back(d); s->in[i].rgb8 = (unsigned char *)d;
+      FAV_TRY(check_cuda(cudaMalloc(&d, HW), "cudaMalloc(session bytes)")); s->allocs.push_back(d); s->in[i].cert8 = (unsigned char *)d;
+      FAV_TRY(check_cuda(cudaMalloc(&d, row_bytes), "cudaMalloc(session bytes)")); s->allocs.push_back(d); s->rows8[i] = (unsigned char *)d;
+      FAV_TRY(s_alloc(s, &s->in[i].flo_uv, 2 * HW));
+    }
+  }
+  // ---- H2D + decode
+  if (in.used) FAV_TRY(check_cuda(cudaStreamWaitEvent(s->s_h2d, in.consumed, 0), "cudaStreamWaitEvent"));
+  FAV_TRY(check_cuda(cudaMemcpyAsync(in.rgb8, rgb_hwc, 3 * HW, cudaMemcpyHostToDevice, s->s_h2d), "H2D rgb"));
+  if (!first) {
+    FAV_TRY(check_cuda(cudaMemcpyAsync(in.flo_uv, flo_uv, 2 * HW * 4, cudaMemcpyHostToDevice, s->s_h2d), "H2D flo"));
+    FAV_TRY(check_cuda(cudaMemcpyAsync(in.cert8, cert8, HW, cudaMemcpyHostToDevice, s->s_h2d), "H2D cert"));
+  }
+  decode_bytes_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, s->s_h2d>>>(in.rgb8, first ? nullptr : (const float2 *)in.flo_uv,
+                                                                        first ? nullptr : in.cert8, invert_occlusion, in.content,
+                                                                        in.flow, in.cert_raw, (int64_t)HW);
+  FAV_TRY(post_launch("decode_bytes"));
+  FAV_TRY(check_cuda(cudaEventRecord(in.uploaded, s->s_h2d), "cudaEventRecord"));
+  // ---- compute
+  FAV_TRY(check_cuda(cudaStreamWaitEvent(s->s_comp, in.uploaded, 0), "cudaStreamWaitEvent"));
+  if (s->out_used[so]) FAV_TRY(check_cuda(cudaStreamWaitEvent(s->s_comp, s->downloaded[so], 0), "cudaStreamWaitEvent"));
+  FAV_TRY(check_cuda(cudaEventRecord(s->t0, s->s_comp), "cudaEventRecord"));
+  if (first) {
+    FAV_TRY(fav_run_image(s->net_img ? s->net_img : s->net, in.content, nullptr, H, W, s->out[so], s->s_comp));
+  } else {
+    FAV_TRY(fav_run_next_image_flows(s->net, in.content, s->out[so ^ 1], in.flow, nullptr, in.cert_raw, nullptr, nullptr, H, W,
+                                     min_filter_r, border_mode, s->out[so], s->s_comp));
+  }
+  FAV_TRY(check_cuda(cudaEventRecord(s->t1, s->s_comp), "cudaEventRecord"));
+  FAV_TRY(check_cuda(cudaEventRecord(in.consumed, s->s_comp), "cudaEventRecord"));
+  FAV_TRY(check_cuda(cudaEventRecord(s->computed[so], s->s_comp), "cudaEventRecord"));
+  in.used = true;
+  // ---- encode + D2H (out[so] is read by the next frame's warp as well: reads only, no ordering needed between them)
+  FAV_TRY(check_cuda(cudaStreamWaitEvent(s->s_d2h, s->computed[so], 0), "cudaStreamWaitEvent"));
+  encode_rows_kernel<<<dim3((unsigned)((W + 255) / 256), (unsigned)H), 256, 0, s->s_d2h>>>(s->out[so], s->rows8[so], H, W);
+  FAV_TRY(post_launch("encode_rows"));
+  FAV_TRY(check_cuda(cudaMemcpyAsync(png_rows_host, s->rows8[so], row_bytes, cudaMemcpyDeviceToHost, s->s_d2h), "D2H rows"));
+  FAV_TRY(check_cuda(cudaEventRecord(s->downloaded[so], s->s_d2h), "cudaEventRecord"));
+  FAV_TRY(check_cuda(cudaEventRecord(s->done[s->frame % fav_session::kDoneRing], s->s_d2h), "cudaEventRecord"));
+  s->out_used[so] = true;
+  s->have_prev = true;
+  s->frame++;
+  return FAV_OK;
 }
 
 // the stylized frame of call number `frame_index` (0-based count of run_* calls on this session) has landed in its out_host

@@ -2,14 +2,15 @@
 // host-buffer session (session.cu).  The reference decodes, uploads, stylizes, downloads and encodes one frame after the other
 // (image.load / flowFile.load in interpreted Lua, image.save); at B200 speeds that host work bounds the frame rate by two
 // orders of magnitude.  Here:
-//   decoder threads   frame PPM -> fp32 planes / 255, certainty PGM -> fp32 / 255, Middlebury .flo -> (dy,dx) planes, straight
-//                     into PINNED ring slots (cudaHostAlloc); the wait-for-file protocol of the flow / occlusion producers
+//   decoder threads   read the PAYLOADS of frame PPM, certainty PGM and Middlebury .flo straight into PINNED ring slots
+//                     (cudaHostAlloc); byte -> fp32 / 255, 1 - cert, (u,v) -> (dy,dx) planes happen on the GPU behind the H2D
+//                     copy (session.cu: decode_bytes_kernel); the wait-for-file protocol of the flow / occlusion producers
 //                     (utils.lua:74-80) and the [fmt] / {fmt} filename patterns (fast_artistic_video.lua:70-77) are kept
 //   calling thread    only enqueues frames on the session (3 CUDA streams inside: H2D / compute / D2H)
 //   completer thread  waits for the session's per-frame completion events in order (fav_session_frame_done)
-//   encoder threads   quantise a landed frame like image.save (clamp, x255, round) straight into Sub-filtered scanlines and
-//                     write "<prefix>-%05d.png" (fast_artistic_video.lua:161) with zlib; any PNG decoder returns the same
-//                     pixels as the synchronous driver's files
+//   encoder threads   deflate the landed Sub-filtered scanlines (quantised like image.save -- clamp, x255, round -- on the GPU
+//                     before the D2H copy: session.cu: encode_rows_kernel) and write "<prefix>-%05d.png"
+//                     (fast_artistic_video.lua:161); any PNG decoder returns the same pixels as the synchronous driver's files
 // FAV_PIPE_STATS=1 prints where the host time went.
 // Host code only (no kernels); compiled by nvcc for the CUDA runtime calls.
 #include <zlib.h>
@@ -103,32 +104,11 @@ int write_png(const std::string &path, const unsigned char *raw, size_t raw_byte
   return ok ? FAV_OK : FAV_ERR_IO;
 }
 
-// image.save's quantisation (clamp to [0,1], x255, round; the same fp32 operations as the synchronous driver) of planar fp32
-// rows, written as Sub-filtered PNG scanlines
-void quantize_filter_rows(const float *planes, size_t HW, int W, int H, unsigned char *raw) {
-  for (int y = 0; y < H; ++y) {
-    unsigned char *dst = raw + (size_t)y * (1 + 3 * (size_t)W);
-    *dst++ = 1;
-    for (int c = 0; c < 3; ++c) {
-      const float *src = planes + (size_t)c * HW + (size_t)y * W;
-      unsigned char pv = 0;
-      for (int x = 0; x < W; ++x) {
-        float v = src[x];
-        v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
-        v = floorf(v * 255.0f + 0.5f);
-        const unsigned char q = (unsigned char)(v < 0.f ? 0.f : (v > 255.f ? 255.f : v));
-        dst[3 * x + c] = (unsigned char)(q - pv);
-        pv = q;
-      }
-    }
-  }
-}
-
 inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-struct Slot {
-  float *content = nullptr, *flow = nullptr, *cert = nullptr, *out = nullptr;  // pinned
-  int state = 0;  // 0 free, 1 decoded, 2 in flight on the GPU
+struct Slot {  // pinned; file payloads in, PNG scanlines out (the byte <-> float conversions happen on the GPU)
+  unsigned char *rgb = nullptr, *cert = nullptr, *rows = nullptr;
+  float *flo = nullptr;
 };
 
 }  // namespace
@@ -157,14 +137,15 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
   if (n == 0) return FAV_OK;
   const size_t HW = (size_t)H * W;
   std::vector<Slot> slots(depth);
+  const size_t row_bytes = (size_t)H * (1 + 3 * (size_t)W);
   auto free_slots = [&]() {
-    for (Slot &s : slots) { cudaFreeHost(s.content); cudaFreeHost(s.flow); cudaFreeHost(s.cert); cudaFreeHost(s.out); }
+    for (Slot &s : slots) { cudaFreeHost(s.rgb); cudaFreeHost(s.flo); cudaFreeHost(s.cert); cudaFreeHost(s.rows); }
   };
   for (Slot &s : slots)
-    if (cudaHostAlloc((void **)&s.content, 3 * HW * 4, cudaHostAllocDefault) != cudaSuccess ||
-        cudaHostAlloc((void **)&s.flow, 2 * HW * 4, cudaHostAllocDefault) != cudaSuccess ||
-        cudaHostAlloc((void **)&s.cert, HW * 4, cudaHostAllocDefault) != cudaSuccess ||
-        cudaHostAlloc((void **)&s.out, 3 * HW * 4, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc((void **)&s.rgb, 3 * HW, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&s.flo, 2 * HW * 4, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&s.cert, HW, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&s.rows, row_bytes, cudaHostAllocDefault) != cudaSuccess) {
       (void)cudaGetLastError();
       free_slots();
       set_error("fav_video_pipeline_run: cannot allocate %d pinned frame slots", depth);
@@ -193,7 +174,7 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
   };
   const std::string in_pat(input_pattern), flow_pat(flow_pattern), occ_pat(occlusions_pattern), out_prefix(output_prefix);
 
-  std::atomic<long long> t_decode{0}, t_quant{0}, t_png{0}, t_enc_wait{0}, t_dec_wait{0}, t_enq_wait{0};  // microseconds, all threads
+  std::atomic<long long> t_decode{0}, t_png{0}, t_enc_wait{0}, t_dec_wait{0}, t_enq_wait{0};  // microseconds, all threads
   auto us = [](double a, double b) { return (long long)((b - a) * 1e6); };
   auto decoder = [&]() {
     for (;;) {
@@ -207,16 +188,19 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
         if (err != FAV_OK) return;
       }
       const double w1 = now_s();
-      int rc = fav_pnm_read_f32(format_index(in_pat, i).c_str(), s.content, 3 * HW, 255.0f);
+      int w = 0, h = 0, c = 0;
+      const std::string frame_name = format_index(in_pat, i);
+      int rc = fav_pnm_read_u8(frame_name.c_str(), s.rgb, 3 * HW, &w, &h, &c);
+      if (rc == FAV_OK && (w != W || h != H || c != 3)) { fail(FAV_ERR_IO, frame_name + ": not a " + std::to_string(W) + "x" + std::to_string(H) + " P6 image"); return; }
       if (rc == FAV_OK && i > 1) {
         const std::string cert_name = format_flow_name(occ_pat, i - 1, i), flow_name = format_flow_name(flow_pat, i - 1, i);
         if (!wait_for_file(cert_name)) return;  // func_load_cert :99-103
-        rc = fav_pnm_read_f32(cert_name.c_str(), s.cert, HW, 255.0f);
-        if (rc == FAV_OK && invert_occlusion)
-          for (size_t k = 0; k < HW; ++k) s.cert[k] = 1.0f - s.cert[k];
+        rc = fav_pnm_read_u8(cert_name.c_str(), s.cert, HW, &w, &h, &c);
+        if (rc == FAV_OK && (w != W || h != H || c != 1)) { fail(FAV_ERR_IO, cert_name + ": size / type mismatch"); return; }
         if (rc == FAV_OK) {
           if (!wait_for_file(flow_name)) return;
-          rc = fav_flo_read(flow_name.c_str(), s.flow, 2 * HW, 0);
+          rc = fav_flo_read_raw(flow_name.c_str(), s.flo, 2 * HW, &w, &h);
+          if (rc == FAV_OK && (w != W || h != H)) { fail(FAV_ERR_IO, flow_name + ": size mismatch"); return; }
         }
       }
       if (rc != FAV_OK) { fail(rc, fav_last_error()); return; }
@@ -226,8 +210,7 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
     }
   };
   auto encoder = [&]() {
-    const size_t raw_bytes = (size_t)H * (1 + 3 * (size_t)W);
-    std::vector<unsigned char> raw(raw_bytes), z, file;
+    std::vector<unsigned char> z, file;
     for (;;) {
       const int i = next_encode.fetch_add(1);
       if (i > n) return;
@@ -239,14 +222,12 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
       }
       const double w1 = now_s();
       const Slot &s = slots[(i - 1) % depth];
-      quantize_filter_rows(s.out, HW, W, H, raw.data());
-      const double w2 = now_s();
       char name[4096];
       snprintf(name, sizeof(name), "%s-%05d.png", out_prefix.c_str(), i);
-      if (write_png(name, raw.data(), raw_bytes, W, H, png_level, z, file) != FAV_OK) { fail(FAV_ERR_IO, std::string("cannot write ") + name); return; }
+      if (write_png(name, s.rows, row_bytes, W, H, png_level, z, file) != FAV_OK) { fail(FAV_ERR_IO, std::string("cannot write ") + name); return; }
       { std::lock_guard<std::mutex> lk(mu); ready[i] = 4; }
       cv_free.notify_all();
-      t_enc_wait += us(w0, w1); t_quant += us(w1, w2); t_png += us(w2, now_s());
+      t_enc_wait += us(w0, w1); t_png += us(w1, now_s());
     }
   };
   // frames complete in order: ONE thread waits on the session's per-frame events (dozens of encoder threads blocking in the
@@ -278,8 +259,8 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
       if (err != FAV_OK) break;
     }
     Slot &s = slots[(i - 1) % depth];
-    const int rc = i == 1 ? fav_session_run_image(sess, s.content, s.out)
-                          : fav_session_run_next_image(sess, s.content, s.flow, s.cert, min_filter_r, FAV_BORDER_PER_TAP, s.out);
+    const int rc = fav_session_run_frame_bytes(sess, s.rgb, i == 1 ? nullptr : s.flo, i == 1 ? nullptr : s.cert, invert_occlusion,
+                                               min_filter_r, FAV_BORDER_PER_TAP, s.rows);
     if (rc != FAV_OK) { fail(rc, fav_last_error()); break; }
     { std::lock_guard<std::mutex> lk(mu); ready[i] = 2; }
     cv_enq.notify_all();
@@ -291,9 +272,9 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
   if (seconds) *seconds = dt;
   if (getenv("FAV_PIPE_STATS"))  // where the host time went: per-frame averages over all worker threads
     fprintf(stderr, "{\"pipeline_stats\": {\"frames\": %d, \"seconds\": %.4f, \"decode_ms\": %.2f, \"decode_wait_slot_ms\": %.2f, "
-            "\"quantize_filter_ms\": %.2f, \"deflate_write_ms\": %.2f, \"encode_wait_frame_ms\": %.2f, \"enqueue_wait_decode_ms\": %.2f, "
+            "\"deflate_write_ms\": %.2f, \"encode_wait_frame_ms\": %.2f, \"enqueue_wait_decode_ms\": %.2f, "
             "\"n_decode\": %d, \"n_encode\": %d, \"depth\": %d, \"png_level\": %d}}\n",
-            n, dt, t_decode / 1e3 / n, t_dec_wait / 1e3 / n, t_quant / 1e3 / n, t_png / 1e3 / n, t_enc_wait / 1e3 / n,
+            n, dt, t_decode / 1e3 / n, t_dec_wait / 1e3 / n, t_png / 1e3 / n, t_enc_wait / 1e3 / n,
             t_enq_wait / 1e3 / n, n_decode, n_encode, depth, png_level);
   if (err != FAV_OK) { set_error("fav_video_pipeline_run: %s", err_msg.c_str()); return err; }
   return FAV_OK;

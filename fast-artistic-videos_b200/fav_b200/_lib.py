@@ -68,6 +68,8 @@ SIGNATURES = {
     "fav_flo_read": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int]),
     "fav_pnm_read_header": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fav_pnm_read_f32": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_float]),
+    "fav_pnm_read_u8": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "fav_flo_read_raw": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fav_net_create": (C.c_int, [C.c_char_p, C.c_char_p, C.c_float, C.c_int, C.POINTER(C.c_void_p)]),
     "fav_net_destroy": (None, [C.c_void_p]),
     "fav_net_num_params": (C.c_int, [C.c_void_p]),
@@ -91,6 +93,7 @@ SIGNATURES = {
     "fav_session_run_next_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fav_session_run_next_image_flows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fav_session_frame_done": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int]),
+    "fav_session_run_frame_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fav_video_pipeline_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "fav_session_sync": (C.c_int, [C.c_void_p]),

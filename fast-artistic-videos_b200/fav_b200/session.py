@@ -49,6 +49,14 @@ class Session:
                                                              _hp(flow_fw_uv_host), int(min_filter_r), border_mode,
                                                              _hp(out_host)))
 
+    def run_frame_bytes(self, rgb_hwc, flo_uv, cert8, rows_out, invert_occlusion=False, min_filter_r=7,
+                        border_mode=_lib.BORDER_PER_TAP):
+        """One frame from file payloads (uint8 HWC frame, float32 [H,W,2] (u,v) flow, uint8 certainty; the last two None for
+        the first frame); rows_out: uint8 [H, 1+3W] receives the Sub-filtered PNG scanlines of the stylized frame."""
+        bp = lambda a: None if a is None else C.c_void_p(a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data)
+        _lib.check(_lib.lib.fav_session_run_frame_bytes(self._h, bp(rgb_hwc), bp(flo_uv), bp(cert8), 1 if invert_occlusion else 0,
+                                                        int(min_filter_r), border_mode, bp(rows_out)))
+
     def frame_done(self, frame_index: int, wait: bool = True) -> bool:
         """The output of the frame_index-th run_* call (0-based) has landed in its host buffer."""
         rc = _lib.lib.fav_session_frame_done(self._h, int(frame_index), 1 if wait else 0)

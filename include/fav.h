@@ -162,6 +162,11 @@ FAV_API int fav_flo_read(const char *path, float *out_host, size_t capacity_floa
  * (consistencyChecker/CTensor.h:888-936, '#' comment lines honoured). */
 FAV_API int fav_pnm_read_header(const char *path, int *W, int *H, int *C);
 FAV_API int fav_pnm_read_f32(const char *path, float *out_host, size_t capacity_floats, float divisor);
+/* f-2  the RAW payloads for callers that convert on the GPU (fav_session_run_frame_bytes): the P5 / P6 bytes as stored
+ * (interleaved RGB; what image.load decodes, fast_artistic_video.lua:95,103) and the .flo (u,v) pairs as stored
+ * (flowFileLoader.lua:28-34).  Sizes are returned and validated against the caller's capacity. */
+FAV_API int fav_pnm_read_u8(const char *path, unsigned char *out_host, size_t capacity_bytes, int *W, int *H, int *C);
+FAV_API int fav_flo_read_raw(const char *path, float *out_uv_pairs_host, size_t capacity_floats, int *W, int *H);
 
 /* ---------------------------------------------------------------------------------------------
  * a-N*  the stylization network                fast_artistic_video/models_video.lua:55-140
@@ -259,6 +264,15 @@ FAV_API int fav_session_run_next_image_flows(fav_session_t *s, const float *cont
  * buffer (wait != 0 blocks; wait == 0 polls: FAV_OK / FAV_ERR_INVALID "still in flight").  Lets encoder threads consume
  * frames while later ones are still being enqueued (file-driven pipeline, fav_b200/video.py). */
 FAV_API int fav_session_frame_done(fav_session_t *s, uint64_t frame_index, int wait);
+/* f-2  one frame from FILE PAYLOADS (what image.load / flowFile.load / func_load_cert / image.save do on the host,
+ * fast_artistic_video.lua:95-110,161): rgb_hwc = P6 payload (H*W*3 bytes), flo_uv = .flo payload (H*W (u,v) pairs),
+ * cert8 = P5 payload of the certainty (both NULL for the first frame); png_rows_host receives H*(1+3W) bytes = the stylized
+ * frame quantised like image.save as Sub-filtered PNG scanlines (ready for deflate).  Byte <-> float conversions run on the
+ * GPU behind the copies (same fp32 operations as the host readers: results are bit-identical); the compute stream runs exactly
+ * what fav_session_run_next_image runs.  Completion: fav_session_frame_done. */
+FAV_API int fav_session_run_frame_bytes(fav_session_t *s, const unsigned char *rgb_hwc, const float *flo_uv,
+                                        const unsigned char *cert8, int invert_occlusion, int min_filter_r, int border_mode,
+                                        unsigned char *png_rows_host);
 /* f-2  the file-driven frame loop (fast_artistic_video.lua:93-170) as a native pipeline around this session: decoder threads
  * (frame PPM, certainty PGM, .flo -> pinned ring slots; [fmt]/{fmt} patterns :70-77; wait-for-file protocol utils.lua:74-80),
  * the calling thread enqueues frames, encoder threads wait per frame and write "<output_prefix>-%05d.png" (:161; zlib level

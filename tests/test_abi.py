@@ -138,3 +138,34 @@ def test_pnm_readers(tmp_path):
     _lib.check(_lib.lib.fav_pnm_read_f32(pg.encode(), outg.ctypes.data_as(C.c_void_p), outg.size, C.c_float(1.0)))
     assert np.array_equal(outg[0], g.astype(np.float32))
     assert _lib.lib.fav_pnm_read_f32(pg.encode(), outg.ctypes.data_as(C.c_void_p), 5, C.c_float(1.0)) == _lib.FAV_ERR_IO
+
+
+def test_raw_payload_readers(tmp_path):
+    """fav_pnm_read_u8 / fav_flo_read_raw: the payloads as stored (for the GPU-side conversions of
+    fav_session_run_frame_bytes), sizes returned, capacity enforced, hostile headers rejected."""
+    import ctypes as C
+    import struct
+
+    from fav_b200 import _lib, synth
+
+    H, W = 9, 14
+    img = synth.make_frame(H, W, 2)
+    p = str(tmp_path / "f.ppm")
+    synth.write_ppm(p, img)
+    u8 = np.clip(np.rint(img * 255.0), 0, 255).astype(np.uint8)  # CHW
+    out = np.zeros((H, W, 3), np.uint8)
+    w_, h_, c_ = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(_lib.lib.fav_pnm_read_u8(p.encode(), out.ctypes.data_as(C.c_void_p), out.size, C.byref(w_), C.byref(h_), C.byref(c_)))
+    assert (w_.value, h_.value, c_.value) == (W, H, 3) and np.array_equal(out, u8.transpose(1, 2, 0))
+    assert _lib.lib.fav_pnm_read_u8(p.encode(), out.ctypes.data_as(C.c_void_p), out.size - 1, C.byref(w_), C.byref(h_), C.byref(c_)) == _lib.FAV_ERR_IO
+    uv = synth.make_backward_flow(H, W, 3)
+    pf = str(tmp_path / "b.flo")
+    synth.write_flo(pf, uv)
+    raw = np.zeros((H, W, 2), np.float32)
+    _lib.check(_lib.lib.fav_flo_read_raw(pf.encode(), raw.ctypes.data_as(C.c_void_p), raw.size, C.byref(w_), C.byref(h_)))
+    assert (w_.value, h_.value) == (W, H) and np.array_equal(raw[..., 0], uv[0]) and np.array_equal(raw[..., 1], uv[1])
+    assert _lib.lib.fav_flo_read_raw(pf.encode(), raw.ctypes.data_as(C.c_void_p), raw.size - 1, C.byref(w_), C.byref(h_)) == _lib.FAV_ERR_IO
+    open(str(tmp_path / "huge.flo"), "wb").write(struct.pack("<fii", 202021.25, 1 << 30, 1 << 30) + b"\0" * 64)
+    assert _lib.lib.fav_flo_read_raw(str(tmp_path / "huge.flo").encode(), raw.ctypes.data_as(C.c_void_p), raw.size, C.byref(w_), C.byref(h_)) == _lib.FAV_ERR_IO
+    open(str(tmp_path / "trunc.ppm"), "wb").write(b"P6\n%d %d\n255\n" % (W, H) + b"\0" * 10)
+    assert _lib.lib.fav_pnm_read_u8(str(tmp_path / "trunc.ppm").encode(), out.ctypes.data_as(C.c_void_p), out.size, C.byref(w_), C.byref(h_), C.byref(c_)) == _lib.FAV_ERR_IO

@@ -210,6 +210,45 @@ def test_session_host_buffer_loop_matches_device_api(net):
     assert torch.equal(o2, outs[1])
 
 
+def test_session_file_payload_path_matches_float_path(net):
+    """fav_session_run_frame_bytes (P6 / P5 / .flo payloads in, Sub-filtered PNG scanlines out; byte <-> float conversions on the
+    GPU) == the host-side conversions of the float path (image.load's byte/255, -invert_occlusion, image.save's rounding)."""
+    from fav_b200 import session
+
+    H, W = 96, 128
+    rng = np.random.default_rng(5)
+    rgb = [torch.from_numpy(rng.integers(0, 256, (H, W, 3), dtype=np.uint8)).pin_memory() for _ in range(3)]
+    cert8 = [torch.from_numpy(((rng.uniform(size=(H, W)) > 0.2) * 255).astype(np.uint8)).pin_memory() for _ in range(3)]
+    flo = [torch.from_numpy(np.ascontiguousarray(synth.make_backward_flow(H, W, i + 2).transpose(1, 2, 0))).pin_memory() for i in range(3)]
+    for invert in (False, True):
+        sb, sf = session.Session(net, H, W), session.Session(net, H, W)
+        rows = [torch.zeros((H, 1 + 3 * W), dtype=torch.uint8).pin_memory() for _ in range(3)]
+        outs = [torch.empty((3, H, W)).pin_memory() for _ in range(3)]
+        for i in range(3):
+            sb.run_frame_bytes(rgb[i], flo[i] if i else None, cert8[i] if i else None, rows[i], invert_occlusion=invert)
+            content = (rgb[i].permute(2, 0, 1).float() / 255.0).contiguous().pin_memory()
+            if i == 0:
+                sf.run_image(content, outs[i])
+            else:
+                cert = cert8[i].float() / 255.0
+                if invert:
+                    cert = 1.0 - cert
+                lua_flow = torch.stack([flo[i][..., 1], flo[i][..., 0]]).contiguous().pin_memory()  # (dy, dx), flowFileLoader.lua:31-32
+                sf.run_next_image(content, lua_flow, cert.contiguous().pin_memory(), outs[i], 7)
+        assert sb.frame_done(2) and sf.frame_done(2)
+        sb.sync(); sf.sync()
+        for i in range(3):
+            q = torch.floor(outs[i].clamp(0, 1) * 255.0 + 0.5).clamp(0, 255).to(torch.uint8).permute(1, 2, 0).reshape(H, 3 * W)  # image.save
+            r = rows[i]
+            assert bool((r[:, 0] == 1).all())
+            sub = r[:, 1:].to(torch.int16)
+            recon = torch.zeros((H, 3 * W), dtype=torch.int16)
+            for x in range(W):  # undo the Sub filter (bytes, modulo 256)
+                prev = recon[:, 3 * (x - 1):3 * x] if x else 0
+                recon[:, 3 * x:3 * x + 3] = (sub[:, 3 * x:3 * x + 3] + prev) % 256
+            assert torch.equal(recon.to(torch.uint8), q), (invert, i)
+
+
 def test_full_size_720p_properties(net):
     """BASELINE.json config 2 size.  The fp64 oracle needs ~10 s per 720p frame on a few cores, so one frame is checked
     against it and the rest through properties: determinism, and invariance of frame 1 to the (masked) prior."""
