@@ -44,8 +44,9 @@ ARCHS = {"default": "c9s1-32,d64,d128,R128,R128,R128,R128,R128,u64,u32,c9s1-3",
 POOL = 8  # distinct input frames cycled: 8 x 29.5 MB of inputs per rank > 126 MB L2
 CONV_GFLOP_720P = 274.3  # logical-channel conv FLOPs per 720p frame, default arch (variant u)
 FRONT_BYTES_PER_PX = 64  # fused temporal-input kernel, all-fp32 I/O
-NCU_RES_CONV_DRAM_BYTES = 40013056 + 1452288  # one residual conv launch, ncu --set full (profiles/r01_conv_tc_res_v8.ncu-rep)
-NCU_FRONT_DRAM_BYTES = 33188608 + 271872      # temporal_input_kernel @720p (profiles/r01_temporal_input_v6.ncu-rep)
+NCU_RES_CONV_DRAM_BYTES = 34215000 + 1113000  # mean of the 10 residual conv_res_kernel launches of one frame, ncu --set full (profiles/r02_frame_raw.csv.gz)
+NCU_FRONT_DRAM_BYTES = 33185280 + 586240      # temporal_input_kernel @720p (profiles/r02_frame_raw.csv.gz)
+NCU_STAGE_DRAM_BYTES = 37158400 + 1045760      # temporal_stage_kernel<1,0> @720p (profiles/r02_frame_raw.csv.gz)
 
 
 WORKLOAD = "1280x720 clip (BASELINE.json configs[1]), candy (seeded random-init weights), one step = one frame of run_next_image"
@@ -419,12 +420,12 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor",
-                         "kernel": "conv_tc_kernel, residual-block launches (128->128 3x3; 10 of the %d conv launches per " % n_conv_launch +
+                         "kernel": "conv_res_kernel, residual-block launches (128->128 3x3; 10 of the %d conv launches per " % n_conv_launch +
                                    "frame, the largest share of the step; the second conv of each block also normalises its input on load)",
                          "achieved": res_tfs, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": res_tfs / pk["tf_sust"],
                          "traffic": NCU_RES_CONV_DRAM_BYTES,
-                         "traffic_source": "profiles/r01_conv_tc_res_v8.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum, "
-                                           "one launch; algorithmic bytes of that launch 68.5 MB: the raw output stays in L2)",
+                         "traffic_source": "profiles/r02_frame_raw.csv.gz (dram__bytes_read.sum + dram__bytes_write.sum, mean of the 10 "
+                                           "launches of one frame; algorithmic bytes per launch 68.5 MB: the planar raw output stays in L2)",
                          "peak_source": pk["src"] + ", bf16 sustained (kernel timed inside the step)",
                          "algorithmic_flop_per_launch": res_flop / max(1, res_n), "us_per_launch": 1e3 * res_ms / max(1, res_n),
                          "launches_timed": res_n,
@@ -436,12 +437,14 @@ def run_ours(args):
             "roofline_stage": {"bound": "hbm", "kernel": "temporal_stage_kernel<false,0> (the whole temporal stage in one launch: "
                                "occlusion test from the flow pair + 7x7 min filter + warp + mask + preprocess + concat)",
                                "achieved": stage_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": stage_gbs / pk["hbm"],
-                               "bytes_per_launch": 68 * H * W, "ms": stage_ms, "traffic": None,
+                               "bytes_per_launch": 68 * H * W, "ms": stage_ms, "traffic": NCU_STAGE_DRAM_BYTES,
+                               "traffic_source": "profiles/r02_frame_raw.csv.gz (37.2 MB read = the input planes; the packed operand it "
+                                                 "writes stays in L2); not memory bound: the occlusion test's mixed float/double chain",
                                "timing": f"{nf} launches in one CUDA graph, inputs cycle through {POOL} frames, best of 5 replays"},
             "roofline_front": {"bound": "hbm", "kernel": "temporal_input_kernel (fused warp+mask+preprocess+concat)",
                                "achieved": front_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": front_gbs / pk["hbm"],
                                "traffic": NCU_FRONT_DRAM_BYTES,
-                               "traffic_source": "profiles/r01_temporal_input_v6.ncu-rep (33.2 MB read = exactly the input planes; "
+                               "traffic_source": "profiles/r02_frame_raw.csv.gz (33.2 MB read = exactly the input planes; "
                                                  "the 25.8 MB written stay in the 126 MB L2)",
                                "bytes_per_launch": FRONT_BYTES_PER_PX * H * W, "ms": front_ms},
             "roofline_warp": None if not warp else {

@@ -221,12 +221,18 @@ def test_session_file_payload_path_matches_float_path(net):
     cert8 = [torch.from_numpy(((rng.uniform(size=(H, W)) > 0.2) * 255).astype(np.uint8)).pin_memory() for _ in range(3)]
     flo = [torch.from_numpy(np.ascontiguousarray(synth.make_backward_flow(H, W, i + 2).transpose(1, 2, 0))).pin_memory() for i in range(3)]
     for invert in (False, True):
-        sb, sf = session.Session(net, H, W), session.Session(net, H, W)
+        sb = session.Session(net, H, W)
         rows = [torch.zeros((H, 1 + 3 * W), dtype=torch.uint8).pin_memory() for _ in range(3)]
         outs = [torch.empty((3, H, W)).pin_memory() for _ in range(3)]
         for i in range(3):
             sb.run_frame_bytes(rgb[i], flo[i] if i else None, cert8[i] if i else None, rows[i], invert_occlusion=invert)
+        assert sb.frame_done(2)
+        sb.sync()  # one net = one set of activation buffers: the two sessions must not overlap
+        sf = session.Session(net, H, W)
+        keep = []
+        for i in range(3):
             content = (rgb[i].permute(2, 0, 1).float() / 255.0).contiguous().pin_memory()
+            keep.append(content)
             if i == 0:
                 sf.run_image(content, outs[i])
             else:
@@ -234,9 +240,11 @@ def test_session_file_payload_path_matches_float_path(net):
                 if invert:
                     cert = 1.0 - cert
                 lua_flow = torch.stack([flo[i][..., 1], flo[i][..., 0]]).contiguous().pin_memory()  # (dy, dx), flowFileLoader.lua:31-32
-                sf.run_next_image(content, lua_flow, cert.contiguous().pin_memory(), outs[i], 7)
-        assert sb.frame_done(2) and sf.frame_done(2)
-        sb.sync(); sf.sync()
+                cert = cert.contiguous().pin_memory()
+                keep += [lua_flow, cert]
+                sf.run_next_image(content, lua_flow, cert, outs[i], 7)
+        assert sf.frame_done(2)
+        sf.sync()
         for i in range(3):
             q = torch.floor(outs[i].clamp(0, 1) * 255.0 + 0.5).clamp(0, 255).to(torch.uint8).permute(1, 2, 0).reshape(H, 3 * W)  # image.save
             r = rows[i]
