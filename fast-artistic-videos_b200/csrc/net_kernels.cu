@@ -5,15 +5,11 @@
 //   in_apply        : normalise (+ReLU) (+ShaveImage(2) skip add) -> next operand    models_video.lua:41-53,121-130
 //   unpack_operand  : operand -> fp32 NCHW (per-layer parity checks)
 //   conv_simt       : direct convolution on CUDA cores, same I/O as the tcgen05 kernel (bring-up comparator)
-#include <atomic>
-
 #include "conv.cuh"
-#include "tc_common.cuh"
 
 namespace fav {
 
 constexpr int kStatRows = 8;
-constexpr int kAsMaxC = 256;  // channels of the streaming apply kernel's statistics table
 constexpr int kApplyIter = 4;  // pixels per thread in the apply kernels: amortises the per-block finalisation
 
 __device__ __forceinline__ void load_join8(const uint4 *hi_src, const uint4 *lo_src, float v[8]) {
@@ -172,14 +168,9 @@ __global__ void __launch_bounds__(128) in_apply_kernel(RawTensor raw, const doub
   }
 }
 
-int launch_in_apply_stream(const RawTensor &raw, const double *sums, const float *gamma, const float *beta, float eps, int relu,
-                           const Operand *skip, int shave, const Operand &dst, cudaStream_t st);
-
 int launch_in_apply(const RawTensor &raw, const double *sums, const float *gamma, const float *beta, float eps, int relu,
                     const Operand *skip, int shave, const Operand &dst, cudaStream_t st) {
   // pixels per thread: amortises the per-block finalisation against registers (occupancy); FAV_APPLY_ITER = 2|3|4 for A/B timing
-  static const bool stream = getenv("FAV_APPLY_OLD") == nullptr;  // A/B timing switch
-  if (stream && raw.C <= kAsMaxC && raw.C % 8 == 0) return launch_in_apply_stream(raw, sums, gamma, beta, eps, relu, skip, shave, dst, st);
   static const int forced = getenv("FAV_APPLY_ITER") ? atoi(getenv("FAV_APPLY_ITER")) : 0;
   const int iter = forced >= 2 && forced <= 4 ? forced : kApplyIter;
   dim3 grid(ceil_div(raw.W, 128 * iter), raw.H, raw.C / 8);
@@ -194,144 +185,11 @@ int launch_in_apply(const RawTensor &raw, const double *sums, const float *gamma
   return post_launch("in_apply");
 }
 
-// ---- in_apply, streaming version ----------------------------------------------------------------------------------------
-// The per-thread-load version above is latency bound (ncu, profiles/r02_frame_details: 4.4 resident warps per scheduler, one
-// eligible; 21 us for 68 L2-resident MB): every block pays load latency -> finalisation -> compute -> store drain in sequence
-// and only ~5 small blocks per SM overlap.  Here the loads are decoupled from the arithmetic: persistent blocks (2 per SM), one
-// producer thread streams work items -- (row y, channel block cb, 512-pixel segment) = the raw rows of 8 channels + the skip
-// operand's hi / lo rows -- into a 3-stage shared-memory ring with cp.async.bulk (rows of the planar / quad raw layouts and of
-// the operand layout are contiguous), 8 consumer warps normalise / add / split and store the next operand directly.  ~100 KB of
-// loads in flight per SM without a register spent on them; the statistics are finalised once per block for all channels.
-constexpr int kAsSeg = 512, kAsStages = 3, kAsConsumers = 256, kAsThreads = kAsConsumers + 32;
-constexpr int kAsRawBytes = kAsSeg * 32, kAsSkipBytes = kAsSeg * 16;  // 8 channels x fp32 | 8 channels x fp16 (hi) / (lo)
-constexpr int kAsStageBytes = kAsRawBytes + 2 * kAsSkipBytes;
-struct ApplyShared {
-  uint64_t full[kAsStages], empty[kAsStages];
-  float mean[kAsMaxC], scale[kAsMaxC], beta[kAsMaxC];
-};
-constexpr size_t kAsSmemBytes = (size_t)kAsStages * kAsStageBytes + sizeof(ApplyShared);
-
-__global__ void __launch_bounds__(kAsThreads, 2) in_apply_stream_kernel(RawTensor raw, const double *__restrict__ sums,
-                                                                        const float *__restrict__ gamma,
-                                                                        const float *__restrict__ beta, double inv_count,
-                                                                        double eps, int relu, Operand skip, int has_skip,
-                                                                        int shave, Operand dst, int nseg, int nitems) {
-  extern __shared__ __align__(128) uint8_t as_smem[];
-  ApplyShared *sh = reinterpret_cast<ApplyShared *>(as_smem + (size_t)kAsStages * kAsStageBytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kAsStages; ++i) { mbar_init(&sh->full[i], 1); mbar_init(&sh->empty[i], kAsConsumers / 32); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int c = threadIdx.x; c < raw.C; c += kAsThreads) {
-    in_finalize(sums[c], sums[raw.C + c], inv_count, eps, gamma[c], sh->mean[c], sh->scale[c]);
-    sh->beta[c] = beta[c];
-  }
-  __syncthreads();
-  const int Cb = raw.C / 8;
-  if (warp == kAsConsumers / 32) {
-    // ---- producer
-    if (lane == 0) {
-      int s = 0, ph = 0;
-      for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-        const int seg = it % nseg, cb = (it / nseg) % Cb, y = it / (nseg * Cb);
-        const int x0 = seg * kAsSeg, npx = min(kAsSeg, raw.W - x0);
-        mbar_wait(&sh->empty[s], ph ^ 1);
-        uint8_t *st = as_smem + (size_t)s * kAsStageBytes;
-        if (raw.planar) {
-          const uint32_t rb = (uint32_t)((npx + 3) & ~3) * 4u;  // whole 16-byte units (the row pitch is a multiple of 16 floats)
-          mbar_arrive_expect_tx(&sh->full[s], 8u * rb + (has_skip ? 2u * (uint32_t)npx * 16u : 0u));
-          const float *p0 = raw.p + raw.offp(cb * 8, y, x0);
-          const int64_t plane = (int64_t)raw.Hp * raw.Wp;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) bulk_g2s(st + i * (kAsSeg * 4), p0 + i * plane, rb, &sh->full[s]);
-        } else {
-          const uint32_t rb = (uint32_t)npx * 16u;
-          mbar_arrive_expect_tx(&sh->full[s], 2u * rb + (has_skip ? 2u * rb : 0u));
-          const float4 *rp = reinterpret_cast<const float4 *>(raw.p);
-          bulk_g2s(st, rp + raw.off4(y, 2 * cb, x0), rb, &sh->full[s]);
-          bulk_g2s(st + kAsSeg * 16, rp + raw.off4(y, 2 * cb + 1, x0), rb, &sh->full[s]);
-        }
-        if (has_skip) {  // ConcatTable{conv_block, ShaveImage(2)} -> CAddTable (models_video.lua:41-53)
-          const int64_t so = skip.off16(skip.padT + y + shave, cb, skip.padL + x0 + shave);
-          bulk_g2s(st + kAsRawBytes, reinterpret_cast<const uint4 *>(skip.hi) + so, (uint32_t)npx * 16u, &sh->full[s]);
-          bulk_g2s(st + kAsRawBytes + kAsSkipBytes, reinterpret_cast<const uint4 *>(skip.lo) + so, (uint32_t)npx * 16u, &sh->full[s]);
-        }
-        if (++s == kAsStages) { s = 0; ph ^= 1; }
-      }
-    }
-    return;
-  }
-  // ---- consumers: thread = pixel (x, x + 256) of the segment, all 8 channels of the block
-  int s = 0, ph = 0;
-  for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-    const int seg = it % nseg, cb = (it / nseg) % Cb, y = it / (nseg * Cb);
-    const int x0 = seg * kAsSeg, npx = min(kAsSeg, raw.W - x0);
-    float tm[8], ts[8], tb[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { tm[i] = sh->mean[cb * 8 + i]; ts[i] = sh->scale[cb * 8 + i]; tb[i] = sh->beta[cb * 8 + i]; }
-    mbar_wait(&sh->full[s], ph);
-    const uint8_t *st = as_smem + (size_t)s * kAsStageBytes;
-#pragma unroll
-    for (int k = 0; k < kAsSeg / kAsConsumers; ++k) {
-      const int x = k * kAsConsumers + threadIdx.x;
-      if (x < npx) {
-        float v[8];
-        if (raw.planar) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = reinterpret_cast<const float *>(st)[i * kAsSeg + x];
-        } else {
-          const float4 a = reinterpret_cast<const float4 *>(st)[x], b = reinterpret_cast<const float4 *>(st + kAsSeg * 16)[x];
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float t = (v[i] - tm[i]) * ts[i] + tb[i];
-          v[i] = relu ? fmaxf(t, 0.f) : t;
-        }
-        if (has_skip) {
-          const uint4 h = reinterpret_cast<const uint4 *>(st + kAsRawBytes)[x], l = reinterpret_cast<const uint4 *>(st + kAsRawBytes + kAsSkipBytes)[x];
-          const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {  // same arithmetic as load_join8
-            v[2 * i] += __half2float(__ushort_as_half((unsigned short)(hw[i] & 0xffff))) +
-                        __half2float(__ushort_as_half((unsigned short)(lw[i] & 0xffff)));
-            v[2 * i + 1] += __half2float(__ushort_as_half((unsigned short)(hw[i] >> 16))) +
-                            __half2float(__ushort_as_half((unsigned short)(lw[i] >> 16)));
-          }
-        }
-        const int64_t o = dst.off16(dst.padT + y, cb, dst.padL + x0 + x);
-        split_store8(v, reinterpret_cast<uint4 *>(dst.hi) + o, reinterpret_cast<uint4 *>(dst.lo) + o);
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sh->empty[s]);
-    if (++s == kAsStages) { s = 0; ph ^= 1; }
-  }
-}
-
-int launch_in_apply_stream(const RawTensor &raw, const double *sums, const float *gamma, const float *beta, float eps, int relu,
-                           const Operand *skip, int shave, const Operand &dst, cudaStream_t st) {
-  static std::atomic<uint64_t> attr_set{0};  // per-device function attribute
-  static std::atomic<int> sm_count[64];
-  int dev = 0;
-  FAV_TRY(check_cuda(cudaGetDevice(&dev), "cudaGetDevice"));
-  const uint64_t bit = 1ull << (dev & 63);
-  if (!(attr_set.load(std::memory_order_acquire) & bit)) {
-    FAV_TRY(check_cuda(cudaFuncSetAttribute(in_apply_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAsSmemBytes),
-                       "cudaFuncSetAttribute(in_apply_stream)"));
-    int n = 0;
-    FAV_TRY(check_cuda(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute"));
-    sm_count[dev & 63].store(n);
-    attr_set.fetch_or(bit, std::memory_order_release);
-  }
-  const int nseg = ceil_div(raw.W, kAsSeg), nitems = nseg * (raw.C / 8) * raw.H;
-  const int grid = std::min(nitems, 2 * sm_count[dev & 63].load());
-  Operand sk = skip ? *skip : Operand();
-  in_apply_stream_kernel<<<grid, kAsThreads, kAsSmemBytes, st>>>(raw, sums, gamma, beta, 1.0 / ((double)raw.H * raw.W), (double)eps,
-                                                                 relu, sk, skip ? 1 : 0, shave, dst, nseg, nitems);
-  return post_launch("in_apply_stream");
-}
+// (Tried and removed, DESIGN.md 9: a streaming version of in_apply -- persistent blocks, one producer thread feeding a 3-stage
+// shared-memory ring with cp.async.bulk row copies, 8 consumer warps -- on the theory that the kernel is latency bound by its
+// register-held loads.  Measured: residual layers 20.8 us vs 21-23 us, wide layers SLOWER (53.6 vs 50.0, 47.5 vs 41.2 us),
+// 915 vs 924 frames/s.  Neither the issue slots (packed conversions: -35 % instructions, same time) nor the loads in flight
+// bound this kernel.)
 
 // ---- nn.SpatialUpSamplingNearest(s) -> InstanceNormalization -> ReLU on an OPERAND (arch token UX) ---------------
 // models_video.lua:94-98,121-130.  Statistics of a nearest-upsampled tensor equal those of its source, so the sums

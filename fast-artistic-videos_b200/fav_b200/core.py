@@ -47,9 +47,18 @@ def load_model(path_or_style: str, arch: str = synth.DEFAULT_ARCH, in_dim: int =
     if path_or_style.endswith(".t7"):  # torch.load(path).model (core.lua:39-47)
         from . import t7
 
-        t7_arch, state, tanh_c, _pad = t7.load_checkpoint(path_or_style)
+        geo = {}
+        try:
+            t7_arch, state, tanh_c, pad = t7.load_checkpoint(path_or_style, geo)
+        except t7.GeometryError as e:  # a padding_type / module layout this implementation does not run
+            raise _lib.FavError(_lib.FAV_ERR_UNSUPPORTED, str(e)) from None
         cin = int(next(v for k, v in state.items() if k == "l0.weight").shape[1])
-        return models_video.StyleNet(t7_arch, tanh_constant=tanh_c, in_dim=cin).load_state(state)
+        net = models_video.StyleNet(t7_arch, geo["padding_type"], tanh_constant=tanh_c, in_dim=cin)
+        want = synth.reflect_start_pad(synth.parse_arch(t7_arch, cin), geo["padding_type"])
+        if pad != want:  # the file's SpatialReflectionPadding must be the one the arch implies (train_video.lua:319-324)
+            raise _lib.FavError(_lib.FAV_ERR_UNSUPPORTED, f"{path_or_style}: SpatialReflectionPadding({pad}) in the checkpoint, "
+                                f"the arch '{t7_arch}' with padding_type {geo['padding_type']} implies {want}")
+        return net.load_state(state)
     style = path_or_style.split(":", 1)[-1]
     return models_video.synthetic_model(style, arch, in_dim)
 

@@ -132,11 +132,27 @@ def _mods(m) -> List:
     return [mods[k] for k in sorted(mods)]
 
 
-def model_to_state(model) -> Tuple[str, Dict[str, np.ndarray], float, int]:
+class GeometryError(ValueError):
+    """The checkpoint's module tree does not have the geometry build_model would give its arch string."""
+
+
+def model_to_state(model, geometry: dict = None) -> Tuple[str, Dict[str, np.ndarray], float, int]:
     """Walk the checkpoint's nn.Sequential exactly as models_video.build_model lays it out (models_video.lua:55-140,
     plus the lazily inserted SpatialReflectionPadding, train_video.lua:319-324) and return
-    (arch string, {name: array}, tanh_constant, reflect_pad)."""
+    (arch string, {name: array}, tanh_constant, reflect_pad).  `geometry`, if given, receives what the file says about
+    padding: 'padding_type' ('reflect-start' | 'zero', inferred from the residual blocks: pad-0 convs + ShaveImage vs pad-1
+    convs + Identity, models_video.lua:21-53), 'has_reflect_pad', and every conv's (name, padW, padW implied by its token);
+    a layout build_model cannot produce for these two padding types raises GeometryError instead of being run with a
+    different geometry."""
     toks, state, tanh_c, pad = [], {}, 150.0, 0
+    geo = geometry if geometry is not None else {}
+    geo.update(padding_type=None, has_reflect_pad=False, conv_pads=[])
+
+    def check_pad(name, m, implied):
+        pw, ph = int(m.get("padW", 0)), int(m.get("padH", m.get("padW", 0)))
+        geo["conv_pads"].append((name, pw, implied))
+        if pw != implied or ph != implied:
+            raise GeometryError(f".t7 model: {name} has padding {pw}x{ph}, its arch token implies {implied}")
     mods = _mods(model)
     i = 0
 
@@ -165,16 +181,23 @@ def model_to_state(model) -> Tuple[str, Dict[str, np.ndarray], float, int]:
         i += 1
         if c == "SpatialReflectionPadding":
             pad = int(m["pad_l"])
+            if not (i == 1 and pad == int(m["pad_r"]) == int(m["pad_t"]) == int(m["pad_b"])):
+                raise GeometryError(".t7 model: only the leading symmetric SpatialReflectionPadding of padding_type "
+                                    "'reflect-start' is supported (train_video.lua:319-324)")
+            geo["has_reflect_pad"] = True
         elif c == "SpatialConvolution":
             k, s = int(m["kW"]), int(m["dW"])
             if k == 3 and s == 2 and int(m["padW"]) == 1:
                 toks.append(f"d{int(m['nOutputPlane'])}")
             else:
                 toks.append(f"c{k}s{s}-{int(m['nOutputPlane'])}")
+            check_pad(name, m, 1 if toks[-1][0] == "d" else (k - 1) // 2)  # models_video.lua:65-80,90-93
             conv_params(name, m, False)
             take_norm_relu(name)
         elif c == "SpatialFullConvolution":
-            toks.append(f"u{int(m['nOutputPlane'])}")
+            k, s = int(m["kW"]), int(m["dW"])
+            toks.append(f"u{int(m['nOutputPlane'])}" if (k == 3 and s == 2) else f"f{k}s{s}-{int(m['nOutputPlane'])}")
+            check_pad(name, m, (k - 1) // 2)  # :81-89,99-102
             conv_params(name, m, True)
             take_norm_relu(name)
         elif c == "SpatialUpSamplingNearest":
@@ -186,6 +209,16 @@ def model_to_state(model) -> Tuple[str, Dict[str, np.ndarray], float, int]:
             convs = [b for b in block if _cls(b) == "SpatialConvolution"]
             norms = [b for b in block if _cls(b) == "InstanceNormalization"]
             assert len(convs) == 2 and len(norms) == 2, "unexpected residual block layout"
+            extra = [_cls(b) for b in block if _cls(b) not in ("SpatialConvolution", "InstanceNormalization", "ReLU")]
+            skip = _cls(_mods(concat)[1]) if len(_mods(concat)) > 1 else None
+            rp = int(convs[0].get("padW", 0))
+            ptype = "reflect-start" if (rp == 0 and skip == "ShaveImage") else ("zero" if (rp == 1 and skip == "Identity") else None)
+            if extra or ptype is None or (geo["padding_type"] not in (None, ptype)):
+                raise GeometryError(f".t7 model: residual block {name} (conv padding {rp}, skip {skip}, extra modules {extra}) is not "
+                                    "a padding_type 'reflect-start' or 'zero' block (models_video.lua:21-53)")
+            geo["padding_type"] = ptype
+            for cn, cm in ((name + ".c1", convs[0]), (name + ".c2", convs[1])):
+                check_pad(cn, cm, rp)
             toks.append(f"R{int(convs[0]['nOutputPlane'])}")
             conv_params(name + ".c1", convs[0], False); in_params(name + ".n1", norms[0])
             conv_params(name + ".c2", convs[1], False); in_params(name + ".n2", norms[1])
@@ -197,13 +230,17 @@ def model_to_state(model) -> Tuple[str, Dict[str, np.ndarray], float, int]:
             pass  # identity in forward (TotalVariation.lua:12-15)
         else:
             raise ValueError(f".t7 model: unsupported module {m.torch_type}")
+    if geo["padding_type"] is None:
+        geo["padding_type"] = "reflect-start" if geo["has_reflect_pad"] else "zero"
+    if geo["has_reflect_pad"] != (geo["padding_type"] == "reflect-start" and pad > 0) and any(t[0] in "RC" for t in toks):
+        raise GeometryError(".t7 model: the leading SpatialReflectionPadding and the residual blocks' padding disagree")
     return ",".join(toks), state, tanh_c, pad
 
 
-def load_checkpoint(path: str):
+def load_checkpoint(path: str, geometry: dict = None):
     ck = load(path)
     model = ck["model"] if isinstance(ck, dict) and "model" in ck else ck
-    return model_to_state(model)
+    return model_to_state(model, geometry)
 
 
 # ---- writer (tests) ---------------------------------------------------------------------------------------------------
@@ -255,8 +292,10 @@ class _Writer:
 
 
 def write_checkpoint(path: str, arch: str, state: Dict[str, np.ndarray], tanh_constant: float = 150.0,
-                     reflect_pad: int = 40) -> None:
-    """Serialise a state dict as the `{model = nn.Sequential{...}}` table train_video.lua:507-541 saves."""
+                     reflect_pad: int = 40, padding_type: str = "reflect-start") -> None:
+    """Serialise a state dict as the `{model = nn.Sequential{...}}` table train_video.lua:507-541 saves
+    (padding_type 'reflect-start': leading reflection pad, pad-0 residual convs + ShaveImage; 'zero': pad-1 residual convs +
+    Identity, models_video.lua:21-53)."""
     from . import synth
 
     def seq(mods, cls="nn.Sequential"):
@@ -271,8 +310,9 @@ def write_checkpoint(path: str, arch: str, state: Dict[str, np.ndarray], tanh_co
         return T7Object("nn.InstanceNormalization", {"weight": state[name + ".weight"], "bias": state[name + ".bias"],
                                                       "eps": 1e-5, "nOutput": int(state[name + ".weight"].size)})
 
-    mods = [T7Object("nn.SpatialReflectionPadding", {"pad_l": reflect_pad, "pad_r": reflect_pad, "pad_t": reflect_pad,
-                                                     "pad_b": reflect_pad})]
+    zero = padding_type == "zero"
+    mods = [] if zero else [T7Object("nn.SpatialReflectionPadding", {"pad_l": reflect_pad, "pad_r": reflect_pad, "pad_t": reflect_pad,
+                                                                     "pad_b": reflect_pad})]
     for i, s in enumerate(synth.parse_arch(arch)):
         n = f"l{i}"
         if s["kind"] == "conv":
@@ -282,9 +322,11 @@ def write_checkpoint(path: str, arch: str, state: Dict[str, np.ndarray], tanh_co
         elif s["kind"] == "up":
             mods.append(T7Object("nn.SpatialUpSamplingNearest", {"scale_factor": s["scale"]}))
         elif s["kind"] == "res":
-            block = seq([conv(n + ".c1", s["cin"], s["cout"], 3, 1, 0), inorm(n + ".n1"), T7Object("nn.ReLU", {"inplace": True}),
-                         conv(n + ".c2", s["cout"], s["cout"], 3, 1, 0), inorm(n + ".n2")])
-            mods.append(seq([seq([block, T7Object("nn.ShaveImage", {"size": 2})], "nn.ConcatTable"), T7Object("nn.CAddTable", {})]))
+            rp = 1 if zero else 0
+            block = seq([conv(n + ".c1", s["cin"], s["cout"], 3, 1, rp), inorm(n + ".n1"), T7Object("nn.ReLU", {"inplace": True}),
+                         conv(n + ".c2", s["cout"], s["cout"], 3, 1, rp), inorm(n + ".n2")])
+            skip = T7Object("nn.Identity", {}) if zero else T7Object("nn.ShaveImage", {"size": 2})
+            mods.append(seq([seq([block, skip], "nn.ConcatTable"), T7Object("nn.CAddTable", {})]))
         if s["in_norm"]:
             mods.append(inorm(n + ".n"))
         if s["relu"]:
@@ -292,6 +334,6 @@ def write_checkpoint(path: str, arch: str, state: Dict[str, np.ndarray], tanh_co
     mods += [T7Object("nn.Tanh", {}), T7Object("nn.MulConstant", {"constant_scalar": tanh_constant}),
              T7Object("nn.TotalVariation", {"strength": 1e-6})]
     w = _Writer()
-    w.obj({"opt": {"arch": arch, "padding_type": "reflect-start"}, "iter": 60000, "model": seq(mods)})
+    w.obj({"opt": {"arch": arch, "padding_type": padding_type}, "iter": 60000, "model": seq(mods)})
     with open(path, "wb") as f:
         f.write(bytes(w.b))
