@@ -15,6 +15,7 @@
 // Host code only (no kernels); compiled by nvcc for the CUDA runtime calls.
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -71,31 +72,70 @@ void png_chunk(std::vector<unsigned char> &out, const char type[4], const unsign
   if (n) out.insert(out.end(), data, data + n);
   put_be32(out, (uint32_t)crc32(0, out.data() + start, (uInt)(n + 4)));
 }
-// 8-bit RGB PNG (colour type 2, no interlace) from scanlines that are already Sub-filtered (filter byte 1 + 3W bytes per row).
-// level 0 = stored; level 1 = zlib level 1 with Z_RLE (what libpng recommends for filtered rows when speed matters: on a
-// stylized 720p frame 32 ms instead of 72 ms at the same size); level >= 2 = that zlib level with Z_FILTERED.
-int write_png(const std::string &path, const unsigned char *raw, size_t raw_bytes, int W, int H, int level,
-              std::vector<unsigned char> &z, std::vector<unsigned char> &out) {
+// 8-bit PNG (colour type 2 RGB or 0 gray, no interlace) from scanlines that are already Sub-filtered (filter byte 1 + C*W bytes
+// per row).  level 0 = stored; level 1 = zlib level 1 with Z_RLE (what libpng recommends for filtered rows when speed matters:
+// on a stylized 720p frame 32 ms instead of 72 ms at the same size); level >= 2 = that zlib level with Z_FILTERED.
+// nthreads > 1: the rows are cut into bands that are deflated concurrently as raw streams ending in a full flush (the last one
+// in Z_FINISH) and concatenated behind one zlib header, the Adler-32 of the whole image combined from the bands' -- the
+// 12288 x 2048 cube-map strips of the VR driver take seconds on one core.
+int deflate_band(const unsigned char *raw, size_t n, int level, bool last, std::vector<unsigned char> &z, uLong *adler) {
   z_stream zs;
   memset(&zs, 0, sizeof(zs));
-  if (deflateInit2(&zs, level, Z_DEFLATED, 15, 9, level <= 1 ? Z_RLE : Z_FILTERED) != Z_OK) return FAV_ERR_IO;
-  z.resize(deflateBound(&zs, (uLong)raw_bytes));
-  zs.next_in = const_cast<unsigned char *>(raw); zs.avail_in = (uInt)raw_bytes;
+  if (deflateInit2(&zs, level, Z_DEFLATED, -15, 9, level <= 1 ? Z_RLE : Z_FILTERED) != Z_OK) return FAV_ERR_IO;
+  z.resize(deflateBound(&zs, (uLong)n) + 16);
+  zs.next_in = const_cast<unsigned char *>(raw); zs.avail_in = (uInt)n;
   zs.next_out = z.data(); zs.avail_out = (uInt)z.size();
-  const int zrc = deflate(&zs, Z_FINISH);
-  const size_t zn = zs.total_out;
+  const int zrc = deflate(&zs, last ? Z_FINISH : Z_FULL_FLUSH);
+  const bool ok = last ? zrc == Z_STREAM_END : (zrc == Z_OK && zs.avail_in == 0 && zs.avail_out > 0);
+  z.resize(zs.total_out);
   deflateEnd(&zs);
-  if (zrc != Z_STREAM_END) return FAV_ERR_IO;
+  *adler = adler32(adler32(0L, Z_NULL, 0), raw, (uInt)n);
+  return ok ? FAV_OK : FAV_ERR_IO;
+}
+
+int write_png_rows(const std::string &path, const unsigned char *raw, int W, int H, int C, int level, int nthreads,
+                   std::vector<unsigned char> &out) {
+  const size_t row = 1 + (size_t)C * W;
+  const int max_bands = (int)std::max<size_t>(1, (row * H) / (1u << 20));  // >= 1 MiB of scanlines per band
+  const int nb = std::max(1, std::min(std::min(nthreads, H), max_bands));
+  std::vector<std::vector<unsigned char>> z(nb);
+  std::vector<uLong> adl(nb);
+  std::vector<size_t> len(nb);
+  std::vector<int> rc(nb, FAV_OK);
+  auto band = [&](int b) {
+    const int y0 = (int)((int64_t)H * b / nb), y1 = (int)((int64_t)H * (b + 1) / nb);
+    len[b] = (size_t)(y1 - y0) * row;
+    rc[b] = deflate_band(raw + (size_t)y0 * row, len[b], level, b == nb - 1, z[b], &adl[b]);
+  };
+  if (nb == 1) {
+    band(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int b = 0; b < nb; ++b) th.emplace_back(band, b);
+    for (std::thread &t : th) t.join();
+  }
+  size_t zn = 2 + 4;
+  uLong adler = adl[0];
+  for (int b = 0; b < nb; ++b) {
+    if (rc[b] != FAV_OK) return rc[b];
+    zn += z[b].size();
+    if (b) adler = adler32_combine(adler, adl[b], (z_off_t)len[b]);
+  }
   out.clear();
   out.reserve(zn + 64);
   const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
   out.insert(out.end(), sig, sig + 8);
   std::vector<unsigned char> ihdr;
   put_be32(ihdr, (uint32_t)W); put_be32(ihdr, (uint32_t)H);
-  const unsigned char tail[5] = {8, 2, 0, 0, 0};
+  const unsigned char tail[5] = {8, (unsigned char)(C == 3 ? 2 : 0), 0, 0, 0};
   ihdr.insert(ihdr.end(), tail, tail + 5);
   png_chunk(out, "IHDR", ihdr.data(), ihdr.size());
-  png_chunk(out, "IDAT", z.data(), zn);
+  put_be32(out, (uint32_t)zn);  // IDAT: zlib header, the bands, Adler-32
+  const size_t start = out.size();
+  out.insert(out.end(), {'I', 'D', 'A', 'T', 0x78, 0x01});
+  for (int b = 0; b < nb; ++b) out.insert(out.end(), z[b].begin(), z[b].end());
+  put_be32(out, (uint32_t)adler);
+  put_be32(out, (uint32_t)crc32(crc32(0L, Z_NULL, 0), out.data() + start, (uInt)(out.size() - start)));
   png_chunk(out, "IEND", nullptr, 0);
   FILE *f = fopen(path.c_str(), "wb");
   if (!f) return FAV_ERR_IO;
@@ -117,6 +157,38 @@ struct Slot {  // pinned; file payloads in, PNG scanlines out (the byte <-> floa
 using namespace fav;
 
 extern "C" {
+
+// image.save(path, img) for an 8-bit image that is already quantised: pixels = H x W x C bytes (C = 3 RGB or 1 gray, interleaved);
+// Sub-filters the rows and writes the PNG with `nthreads` concurrent deflate bands (fast_artistic_video.lua:161,
+// fast_artistic_video_vr.lua:541-556 write 8-bit PNGs through the `image` rock; any decoder returns the same pixels).
+int fav_png_write(const char *path, const unsigned char *pixels, int W, int H, int C, int png_level, int nthreads) {
+  FAV_REQUIRE(path && pixels && W > 0 && H > 0 && (C == 1 || C == 3), "fav_png_write: bad argument");
+  FAV_REQUIRE((uint64_t)W * C * (uint64_t)H < (1ull << 31), "fav_png_write: image too large for one IDAT chunk");
+  png_level = png_level < 0 ? 1 : (png_level > 9 ? 9 : png_level);
+  const size_t row = 1 + (size_t)C * W;
+  std::vector<unsigned char> raw(row * H), file;
+  const int nt = nthreads < 1 ? 1 : (nthreads > 64 ? 64 : nthreads);
+  auto filter = [&](int y0, int y1) {
+    for (int y = y0; y < y1; ++y) {
+      unsigned char *dst = raw.data() + (size_t)y * row;
+      const unsigned char *src = pixels + (size_t)y * C * W;
+      *dst++ = 1;
+      for (int i = 0; i < C * W; ++i) dst[i] = (unsigned char)(src[i] - (i >= C ? src[i - C] : 0));
+    }
+  };
+  if (nt == 1 || H < 64) {
+    filter(0, H);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(filter, (int)((int64_t)H * t / nt), (int)((int64_t)H * (t + 1) / nt));
+    for (std::thread &t : th) t.join();
+  }
+  if (write_png_rows(path, raw.data(), W, H, C, png_level, nt, file) != FAV_OK) {
+    set_error("fav_png_write: cannot write %s", path);
+    return FAV_ERR_IO;
+  }
+  return FAV_OK;
+}
 
 // Runs the whole clip; blocks until the last PNG is on disk.  Frames are <input_pattern % i>, i = 1..; the loop ends at
 // num_frames or at the first missing frame file (func_load_image returning nil, fast_artistic_video.lua:93-97).
@@ -210,7 +282,7 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
     }
   };
   auto encoder = [&]() {
-    std::vector<unsigned char> z, file;
+    std::vector<unsigned char> file;
     for (;;) {
       const int i = next_encode.fetch_add(1);
       if (i > n) return;
@@ -224,7 +296,7 @@ int fav_video_pipeline_run(fav_session_t *sess, int H, int W, const char *input_
       const Slot &s = slots[(i - 1) % depth];
       char name[4096];
       snprintf(name, sizeof(name), "%s-%05d.png", out_prefix.c_str(), i);
-      if (write_png(name, s.rows, row_bytes, W, H, png_level, z, file) != FAV_OK) { fail(FAV_ERR_IO, std::string("cannot write ") + name); return; }
+      if (write_png_rows(name, s.rows, W, H, 3, png_level, 1, file) != FAV_OK) { fail(FAV_ERR_IO, std::string("cannot write ") + name); return; }
       { std::lock_guard<std::mutex> lk(mu); ready[i] = 4; }
       cv_free.notify_all();
       t_enc_wait += us(w0, w1); t_png += us(w1, now_s());

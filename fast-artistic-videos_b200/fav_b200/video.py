@@ -46,7 +46,17 @@ def getFormatedFlowFileName(pattern: str, fromIndex: int, toIndex: int) -> str:
 
 
 def load_image(path: str, channels: int) -> torch.Tensor:
-    """image.load(path, channels): float [0,1], CxHxW."""
+    """image.load(path, channels): float [0,1], CxHxW.  Binary PPM / PGM files (what the reference's pipelines produce,
+    run-deepflow.sh / makeOptFlow.sh) go through the native reader (byte / 255 in fp32, as image.load); anything else
+    through PIL."""
+    if path.lower().endswith((".ppm", ".pgm", ".pnm")):
+        import ctypes as C
+
+        w_, h_, c_ = C.c_int(), C.c_int(), C.c_int()
+        if _lib.lib.fav_pnm_read_header(path.encode(), C.byref(w_), C.byref(h_), C.byref(c_)) == _lib.FAV_OK and c_.value == channels:
+            out = np.empty((channels, h_.value, w_.value), np.float32)
+            _lib.check(_lib.lib.fav_pnm_read_f32(path.encode(), out.ctypes.data_as(C.c_void_p), out.size, C.c_float(255.0)))
+            return torch.from_numpy(out)
     from PIL import Image
 
     im = Image.open(path).convert("RGB" if channels == 3 else "L")
@@ -54,11 +64,44 @@ def load_image(path: str, channels: int) -> torch.Tensor:
     return torch.from_numpy(a.transpose(2, 0, 1).copy() if channels == 3 else a[None].copy())
 
 
-def save_image(path: str, img: torch.Tensor) -> None:
-    from PIL import Image
+_SAVE_POOL = None
+_SAVE_PENDING = []
 
-    a = (img.detach().clamp(0, 1) * 255.0 + 0.5).floor().clamp(0, 255).byte().cpu().numpy().transpose(1, 2, 0)
-    Image.fromarray(a).save(path)
+
+def save_image(path: str, img: torch.Tensor, background: bool = False) -> None:
+    """image.save(path, img): clamp to [0,1], x255, round -> 8-bit PNG.  Quantised on the tensor's device, encoded by the
+    native writer (fav_png_write: Sub filter, zlib level 1 + Z_RLE, concurrent deflate bands -- the cube-map strips of the VR
+    driver are 12288 x 2048).  background=True returns after the device->host copy and encodes on a worker thread
+    (flush_saves() waits); the pixels any PNG decoder returns are the same either way."""
+    import ctypes as C
+
+    a = (img.detach().clamp(0, 1) * 255.0 + 0.5).floor().clamp(0, 255).byte()
+    if a.dim() == 2:
+        a = a[None]
+    a = a.permute(1, 2, 0).contiguous().cpu().numpy()
+    H, W, Cn = a.shape
+    if Cn not in (1, 3):
+        raise _lib.FavError(_lib.FAV_ERR_INVALID, f"save_image: {Cn} channels")
+    nthreads = max(1, min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+
+    def write():
+        _lib.check(_lib.lib.fav_png_write(path.encode(), a.ctypes.data_as(C.c_void_p), W, H, Cn, 1, nthreads))
+
+    if not background:
+        write()
+        return
+    global _SAVE_POOL
+    if _SAVE_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _SAVE_POOL = ThreadPoolExecutor(max_workers=3)
+    _SAVE_PENDING.append(_SAVE_POOL.submit(write))
+
+
+def flush_saves() -> None:
+    """Wait for the background PNG writes (and surface their errors)."""
+    while _SAVE_PENDING:
+        _SAVE_PENDING.pop(0).result()
 
 
 class Driver:

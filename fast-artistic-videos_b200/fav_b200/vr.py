@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib, core, flowFileLoader, utils, vr_helper
-from .video import load_image, save_image
+from .video import flush_saves, load_image, save_image
 
 PROC_ORDER = [6, 1, 2, 5, 3, 4]  # :103
 
@@ -223,14 +223,14 @@ class VRDriver:
         if opt.out_equi:
             strip = torch.cat([sides[1], sides[2], sides[3], sides[4], rotate180(sides[5]), rotate180(sides[6])], 2)
             res["equi"] = utils.warp_image(strip.contiguous(), self.equi_map)
-            save_image("%s-%05d_equi.png" % (opt.output_prefix, file_idx), res["equi"])
+            save_image("%s-%05d_equi.png" % (opt.output_prefix, file_idx), res["equi"], background=True)
         if opt.out_cubemap:
             # :548-553: {oversize+1, hplus-oversize} index the MEDIAN-FILTERED face (already 2*(r//2) smaller), so each
             # face comes out (hplus - overlap + 2*(r//2)) wide -- the reference's own (asymmetric) crop, kept as is
             crop = lambda t: t[:, oh:self.hplus - oh, ow:self.wplus - ow]
             res["cubemap"] = torch.cat([crop(sides[4]), crop(sides[1]), rotate90(crop(sides[5])), rotateMinus90(crop(sides[6])),
                                         crop(sides[3]), crop(sides[2])], 2)
-            save_image("%s-%05d_cubemap.png" % (opt.output_prefix, file_idx), res["cubemap"])
+            save_image("%s-%05d_cubemap.png" % (opt.output_prefix, file_idx), res["cubemap"], background=True)
         self.outputs[file_idx] = res
 
 
@@ -253,6 +253,7 @@ def main(argv=None, model_vid=None):
     core.run_fast_neural_video(opt, d.func_load_image, d.func_load_cert, None, d.func_make_last_frame_warped,
                                d.func_is_single_image, d.func_save_image, model_vid=model_vid)
     torch.cuda.synchronize()
+    flush_saves()  # the PNGs of a VR frame are encoded on worker threads while the next frame's faces are stylized
     return d
 
 

@@ -264,6 +264,10 @@ FAV_API int fav_session_run_next_image_flows(fav_session_t *s, const float *cont
  * buffer (wait != 0 blocks; wait == 0 polls: FAV_OK / FAV_ERR_INVALID "still in flight").  Lets encoder threads consume
  * frames while later ones are still being enqueued (file-driven pipeline, fav_b200/video.py). */
 FAV_API int fav_session_frame_done(fav_session_t *s, uint64_t frame_index, int wait);
+/* f-2  image.save of an already quantised 8-bit image (fast_artistic_video.lua:161, fast_artistic_video_vr.lua:541-556):
+ * pixels = H x W x C bytes (C = 3 RGB | 1 gray, interleaved) -> PNG (Sub filter; png_level 0 stored, 1 zlib level 1 + Z_RLE,
+ * >= 2 that zlib level), deflated in nthreads concurrent bands.  HOST side. */
+FAV_API int fav_png_write(const char *path, const unsigned char *pixels, int W, int H, int C, int png_level, int nthreads);
 /* f-2  one frame from FILE PAYLOADS (what image.load / flowFile.load / func_load_cert / image.save do on the host,
  * fast_artistic_video.lua:95-110,161): rgb_hwc = P6 payload (H*W*3 bytes), flo_uv = .flo payload (H*W (u,v) pairs),
  * cert8 = P5 payload of the certainty (both NULL for the first frame); png_rows_host receives H*(1+3W) bytes = the stylized

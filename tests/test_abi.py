@@ -169,3 +169,25 @@ def test_raw_payload_readers(tmp_path):
     assert _lib.lib.fav_flo_read_raw(str(tmp_path / "huge.flo").encode(), raw.ctypes.data_as(C.c_void_p), raw.size, C.byref(w_), C.byref(h_)) == _lib.FAV_ERR_IO
     open(str(tmp_path / "trunc.ppm"), "wb").write(b"P6\n%d %d\n255\n" % (W, H) + b"\0" * 10)
     assert _lib.lib.fav_pnm_read_u8(str(tmp_path / "trunc.ppm").encode(), out.ctypes.data_as(C.c_void_p), out.size, C.byref(w_), C.byref(h_), C.byref(c_)) == _lib.FAV_ERR_IO
+
+
+def test_png_writer_round_trip(tmp_path):
+    """fav_png_write (image.save of an 8-bit image): decoded by an independent PNG reader (PIL) the pixels are identical, for one
+    band and for concurrent deflate bands, RGB and gray, every compression mode."""
+    import ctypes as C
+
+    from PIL import Image
+
+    from fav_b200 import _lib
+
+    rng = np.random.default_rng(3)
+    for (H, W, Cn, nt, lvl) in [(7, 5, 3, 1, 1), (64, 33, 1, 4, 1), (1100, 1000, 3, 3, 1), (300, 200, 3, 4, 0), (300, 200, 3, 3, 6)]:
+        yy, xx = np.mgrid[0:H, 0:W]
+        img = np.stack([(128 + 100 * np.sin(xx / 37 + c) * np.cos(yy / 23) + rng.normal(0, 12, (H, W))).clip(0, 255) for c in range(Cn)], -1)
+        img = np.ascontiguousarray(img.astype(np.uint8))
+        p = str(tmp_path / "a.png")
+        _lib.check(_lib.lib.fav_png_write(p.encode(), img.ctypes.data_as(C.c_void_p), W, H, Cn, lvl, nt))
+        back = np.asarray(Image.open(p))
+        assert np.array_equal(back if Cn == 3 else back[..., None], img), (H, W, Cn, nt, lvl)
+    assert _lib.lib.fav_png_write(str(tmp_path / "no" / "dir.png").encode(), img.ctypes.data_as(C.c_void_p), W, H, Cn, 1, 1) == _lib.FAV_ERR_IO
+    assert _lib.lib.fav_png_write(b"x.png", img.ctypes.data_as(C.c_void_p), W, H, 2, 1, 1) == _lib.FAV_ERR_INVALID
