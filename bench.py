@@ -505,20 +505,33 @@ def run_cfg3(args):
     net = models_video.synthetic_model("candy", ARCHS[args.arch])
     state = {}
     host = {}
+    from fav_b200 import utils as fav_utils
+
+    bytes_mode = args.payload == "bytes"
     fr = np.stack([synth.make_frame(Hc, Wc, i + 1) for i in range(PO)])
-    bw = np.stack([synth.checker_to_lua(synth.make_backward_flow(Hc, Wc, i + 2)) for i in range(PO)])  # (dy,dx), flowFileLoader.lua:31-32
     fw = np.stack([synth.make_forward_flow(Hc, Wc, i + 2) for i in range(PO)])
-    dpool = {k: torch.from_numpy(v).to(dev) for k, v in (("fr", fr), ("bw", bw), ("fw", fw))}  # compute-only leg (every rank)
+    if bytes_mode:
+        # what the files hold: 8-bit frames (P6 payload, HWC) and the backward .flo payload ((u,v) pairs); converted on the owner GPU
+        fr = np.ascontiguousarray(np.clip(np.rint(fr * 255.0), 0, 255).astype(np.uint8).transpose(0, 2, 3, 1))
+        bw = np.stack([np.ascontiguousarray(synth.make_backward_flow(Hc, Wc, i + 2).transpose(1, 2, 0)) for i in range(PO)])
+        out_shape, out_dtype = (Hc, 1 + 3 * Wc), torch.uint8  # image.save's 8-bit pixels as Sub-filtered PNG scanlines
+    else:
+        bw = np.stack([synth.checker_to_lua(synth.make_backward_flow(Hc, Wc, i + 2)) for i in range(PO)])  # (dy,dx), flowFileLoader.lua:31-32
+        out_shape, out_dtype = (3, Hc, Wc), torch.float32
+    pool = (("fr", fr), ("bw", bw), ("fw", fw))
+    in_shapes = [tuple(v.shape[1:]) for _, v in pool]
+    in_dtypes = [torch.from_numpy(v[:1]).dtype for _, v in pool]
+    dpool = {k: torch.from_numpy(v).to(dev) for k, v in pool}  # compute-only leg (every rank)
     if rank == 0:
-        host = {k: torch.from_numpy(v).pin_memory() for k, v in (("fr", fr), ("bw", bw), ("fw", fw))}
-        out_host = [torch.empty((CH, 3, Hc, Wc)).pin_memory() for _ in range(NC)]
+        host = {k: torch.from_numpy(v).pin_memory() for k, v in pool}
+        out_host = [torch.empty((CH,) + out_shape, dtype=out_dtype).pin_memory() for _ in range(NC)]
 
     def load_chunk(c, f0, f1):
         # H2D straight from the pinned decoded pool into a device chunk (no host-side staging copy)
         idx = [(c + i) % PO for i in range(f0, f1)]
         res = []
         for k in ("fr", "bw", "fw"):
-            buf = torch.empty((len(idx),) + tuple(host[k].shape[1:]), device=dev)
+            buf = torch.empty((len(idx),) + tuple(host[k].shape[1:]), dtype=host[k].dtype, device=dev)
             for i, j in enumerate(idx):
                 buf[i].copy_(host[k][j], non_blocking=True)
             res.append(buf)
@@ -528,12 +541,16 @@ def run_cfg3(args):
         fr_, bw_, fw_ = inputs
         outs = []
         for i in range(fr_.shape[0]):
-            if f0 + i == 0:
-                prev = net.run_image(fr_[i])
+            if bytes_mode:
+                content, flow, _ = fav_utils.bytes_to_planes(fr_[i], bw_[i])
             else:
-                prev = net.run_next_image_flows(fr_[i], state[c], bw_[i], fw_[i], None, 7)
+                content, flow = fr_[i], bw_[i]
+            if f0 + i == 0:
+                prev = net.run_image(content)
+            else:
+                prev = net.run_next_image_flows(content, state[c], flow, fw_[i], None, 7)
             state[c] = prev
-            outs.append(prev)
+            outs.append(fav_utils.planes_to_png_rows(prev) if bytes_mode else prev)
         return torch.stack(outs)
 
     def store_chunk(c, f0, out):
@@ -556,8 +573,8 @@ def run_cfg3(args):
         return e0.elapsed_time(e1) * 1e-3, st
 
     def run(nf):
-        return timed(lambda: clips.stream_clips(NC, nf, CH, [(3, Hc, Wc), (2, Hc, Wc), (2, Hc, Wc)], (3, Hc, Wc), load_chunk,
-                                                process_chunk, store_chunk, device=dev))
+        return timed(lambda: clips.stream_clips(NC, nf, CH, in_shapes, out_shape, load_chunk, process_chunk, store_chunk, device=dev,
+                                                in_dtypes=in_dtypes, out_dtype=out_dtype))
 
     def run_compute_only(nf):
         """the same clips and frame loops with every input already resident on the owning GPU: what the data plane costs
@@ -587,7 +604,8 @@ def run_cfg3(args):
     t_max, tc_max = float(tt[0]), float(tt[1])
     if rank == 0:
         clocks = sampler.stop(tw0, tw1)
-        per_frame_in = (3 + 2 + 2) * Hc * Wc * 4
+        per_frame_in = sum(int(np.prod(v.shape[1:])) * v.itemsize for _, v in pool)
+        per_frame_out = int(np.prod(out_shape)) * (1 if bytes_mode else 4)
         line = {"metric": "stylized frames/sec, 8 independent 1920x1080 clips (BASELINE.json configs[2])", "value": NC * F / t_max,
                 "unit": "frames/s", "n_gpus": world, "steps": F, "warmup": 2 * CH, "ms_per_step": 1e3 * t_max / F,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -595,8 +613,12 @@ def run_cfg3(args):
                 "config": {"workload": "8 x 1920x1080 clips, candy (synthetic weights), one step = one frame of EVERY clip",
                            "arch": ARCHS[args.arch], "frames_per_clip": F, "chunk": CH,
                            "parallelism": f"clips round-robin over {world} GPU(s); rank 0 scatters inputs / gathers outputs (NCCL p2p)"},
-                "data_plane": {"source": "rank 0 pinned host memory (fp32 frames + bw/fw flow)", "bytes_in_per_frame": per_frame_in,
-                               "bytes_out_per_frame": 3 * Hc * Wc * 4, "nccl_bytes_sent_rank0": st["bytes_in"],
+                "data_plane": {"payload": args.payload,
+                               "source": "rank 0 pinned host memory: " + ("8-bit frames as the files hold them + backward .flo payload + forward "
+                                         "flow planes; byte->float / (u,v)->(dy,dx) on the owning GPU (fav_bytes_to_planes); results return as "
+                                         "8-bit Sub-filtered PNG scanlines (fav_planes_to_png_rows = image.save's quantisation)" if bytes_mode
+                                         else "fp32 frames + bw/fw flow, fp32 stylized frames back"),
+                               "bytes_in_per_frame": per_frame_in, "bytes_out_per_frame": per_frame_out, "nccl_bytes_sent_rank0": st["bytes_in"],
                                "compute_only_frames_per_s": NC * F / tc_max, "compute_only_ms_per_step": 1e3 * tc_max / F,
                                "data_plane_exposed_share": max(0.0, 1.0 - tc_max / t_max),
                                "streams": "uploads + NCCL on a transfer stream, D2H of results on a third, frame loops on the compute stream",
@@ -621,6 +643,9 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3"],
                     help="cfg2 = BASELINE.json configs[1] (the metric: 1280x720 clip, default); cfg3 = configs[2]: 8 x 1080p clips "
                          "with the NCCL scatter / gather of frames inside the timed region")
+    ap.add_argument("--payload", default="bytes", choices=["bytes", "fp32"],
+                    help="cfg3 only: what travels from rank 0 to the owning GPU and back: the 8-bit pixels the files hold (converted on "
+                         "the GPU; default) or decoded fp32 tensors")
     ap.add_argument("--arch", default="default", choices=list(ARCHS),
                     help="default = train_video.lua:21 (u64,u32); paper = README.md:256 (U2,c3s1-64,U2)")
     args = ap.parse_args()

@@ -223,6 +223,26 @@ int fav_session_run_next_image_flows(fav_session_t *s, const float *content_host
   return session_step(s, 2, content_host, flow_bw_uv_host, flow_fw_uv_host, nullptr, min_filter_r, border_mode, out_host);
 }
 
+// The two conversions as device-pointer entry points (multi-GPU data plane: frames travel as the 8-bit pixels the files hold and
+// are converted on the GPU that owns the clip).  Any of flo_uv / cert8 (and their outputs) may be NULL.
+int fav_bytes_to_planes(const unsigned char *rgb_hwc, const float *flo_uv, const unsigned char *cert8, int invert_occlusion,
+                        float *content, float *flow, float *cert, int H, int W, void *stream) {
+  FAV_REQUIRE(rgb_hwc && content && H > 0 && W > 0, "fav_bytes_to_planes: bad argument");
+  FAV_REQUIRE((flo_uv == nullptr) == (flow == nullptr) && (cert8 == nullptr) == (cert == nullptr), "fav_bytes_to_planes: input / output mismatch");
+  FAV_TRY(require_device());
+  const int64_t HW = (int64_t)H * W;
+  decode_bytes_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rgb_hwc, (const float2 *)flo_uv, cert8, invert_occlusion,
+                                                                                  content, flow, cert, HW);
+  return post_launch("decode_bytes");
+}
+
+int fav_planes_to_png_rows(const float *rgb_planes, unsigned char *rows, int H, int W, void *stream) {
+  FAV_REQUIRE(rgb_planes && rows && H > 0 && W > 0, "fav_planes_to_png_rows: bad argument");
+  FAV_TRY(require_device());
+  encode_rows_kernel<<<dim3((unsigned)((W + 255) / 256), (unsigned)H), 256, 0, (cudaStream_t)stream>>>(rgb_planes, rows, H, W);
+  return post_launch("encode_rows");
+}
+
 // One frame from FILE PAYLOADS: rgb_hwc = the P6 payload (H*W*3 bytes), flo_uv = the .flo payload (H*W (u,v) float pairs) and
 // cert8 = the P5 payload of the certainty (both NULL for the first frame / a single image); png_rows_host receives
 // H*(1+3W) bytes of Sub-filtered PNG scanlines of the stylized frame.  The byte <-> float conversions run on the copy

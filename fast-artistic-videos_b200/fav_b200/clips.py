@@ -76,11 +76,13 @@ def gather_clips(local: Dict[int, torch.Tensor], shapes: List[tuple], dst: int =
 # of chunk k+1 (inputs) and k-1 (outputs) fly while chunk k is processed.
 # ---------------------------------------------------------------------------------------------------------------------
 def stream_clips(num_clips, n_frames, chunk, in_shapes, out_shape, load_chunk, process_chunk, store_chunk, src=0, device=None,
-                 dtype=torch.float32):
+                 dtype=torch.float32, in_dtypes=None, out_dtype=None):
     """in_shapes: per-frame shapes of the input tensors of a clip, e.g. [(3,H,W), (2,H,W), (2,H,W)]; out_shape e.g. (3,H,W).
     load_chunk(clip, f0, f1) -> list of tensors [f1-f0, *shape] (rank src only; host or device; moved to `device`),
     process_chunk(clip, f0, inputs) -> tensor [f1-f0, *out_shape] on `device` (owner ranks, called in frame order),
     store_chunk(clip, f0, out) (rank src only).  Returns dict(comm_wait_s, steps, bytes_in, bytes_out) of this rank.
+    in_dtypes / out_dtype: element types of the travelling tensors when they are not all `dtype` (e.g. uint8 frames as the
+    files hold them, uint8 PNG scanlines back).
 
     On a CUDA device three streams are used: the caller's current stream runs process_chunk only; a transfer stream carries
     the uploads of load_chunk and the NCCL sends / receives (so chunk k+1 travels while chunk k is processed); a third stream
@@ -89,6 +91,8 @@ def stream_clips(num_clips, n_frames, chunk, in_shapes, out_shape, load_chunk, p
     import time
 
     rank, world = dist.get_rank(), dist.get_world_size()
+    in_dtypes = list(in_dtypes) if in_dtypes is not None else [dtype] * len(in_shapes)
+    out_dtype = out_dtype if out_dtype is not None else dtype
     nsteps = (n_frames + chunk - 1) // chunk
     mine = [c for c in range(num_clips) if owner(c, world) == rank]
     span = lambda k: (k * chunk, min(n_frames, (k + 1) * chunk))
@@ -129,7 +133,7 @@ def stream_clips(num_clips, n_frames, chunk, in_shapes, out_shape, load_chunk, p
                                 stats["bytes_in"] += t.numel() * t.element_size()
                             inbuf[(c, k)] = ts  # keep alive until the send completes
                     elif rank == o:
-                        ts = [torch.empty((f1 - f0,) + tuple(s), dtype=dtype, device=device) for s in in_shapes]
+                        ts = [torch.empty((f1 - f0,) + tuple(s), dtype=dt, device=device) for s, dt in zip(in_shapes, in_dtypes)]
                         for t in ts:
                             ops.append(dist.P2POp(dist.irecv, t, src))
                         inbuf[(c, k)] = ts
@@ -146,7 +150,7 @@ def stream_clips(num_clips, n_frames, chunk, in_shapes, out_shape, load_chunk, p
                         ops.append(dist.P2POp(dist.isend, t, src))
                         stats["bytes_out"] += t.numel() * t.element_size()
                     elif rank == src:
-                        t = torch.empty((f1 - f0,) + tuple(out_shape), dtype=dtype, device=device)
+                        t = torch.empty((f1 - f0,) + tuple(out_shape), dtype=out_dtype, device=device)
                         ops.append(dist.P2POp(dist.irecv, t, o))
                         outbuf[(c, kk)] = t
             return dist.batch_isend_irecv(ops) if ops else []

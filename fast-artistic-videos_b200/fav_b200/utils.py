@@ -45,6 +45,28 @@ def temporal_loss(prev_stylized: torch.Tensor, stylized: torch.Tensor, flow: tor
     return float(acc.item()) / (3.0 * H * W)
 
 
+def bytes_to_planes(rgb_hwc: torch.Tensor, flo_uv: torch.Tensor = None, cert8: torch.Tensor = None, invert_occlusion: bool = False):
+    """Device-side image.load / flowFile.load / func_load_cert: uint8 [H,W,3] -> float [3,H,W] = byte / 255, float [H,W,2] (u,v)
+    pairs -> [2,H,W] = (dy,dx), uint8 [H,W] -> float [1,H,W] = byte / 255 (1 - that with invert_occlusion).  One kernel."""
+    H, W = rgb_hwc.shape[:2]
+    assert rgb_hwc.dtype == torch.uint8 and rgb_hwc.is_contiguous()
+    content = torch.empty((3, H, W), dtype=torch.float32, device=rgb_hwc.device)
+    flow = torch.empty((2, H, W), dtype=torch.float32, device=rgb_hwc.device) if flo_uv is not None else None
+    cert = torch.empty((1, H, W), dtype=torch.float32, device=rgb_hwc.device) if cert8 is not None else None
+    _lib.check(_lib.lib.fav_bytes_to_planes(_lib.dptr(rgb_hwc), _lib.dptr(flo_uv.contiguous() if flo_uv is not None else None),
+                                            _lib.dptr(cert8.contiguous() if cert8 is not None else None), 1 if invert_occlusion else 0,
+                                            _lib.dptr(content), _lib.dptr(flow), _lib.dptr(cert), H, W, _lib.stream_ptr()))
+    return content, flow, cert
+
+
+def planes_to_png_rows(img: torch.Tensor) -> torch.Tensor:
+    """Device-side image.save quantisation: float [3,H,W] -> uint8 [H, 1+3W] Sub-filtered PNG scanlines (filter byte 1)."""
+    H, W = img.shape[-2:]
+    rows = torch.empty((H, 1 + 3 * W), dtype=torch.uint8, device=img.device)
+    _lib.check(_lib.lib.fav_planes_to_png_rows(_lib.dptr(img.contiguous()), _lib.dptr(rows), H, W, _lib.stream_ptr()))
+    return rows
+
+
 def file_exists(name: str) -> bool:  # utils.lua:68-71
     return os.path.isfile(name)
 

@@ -268,6 +268,13 @@ FAV_API int fav_session_frame_done(fav_session_t *s, uint64_t frame_index, int w
  * pixels = H x W x C bytes (C = 3 RGB | 1 gray, interleaved) -> PNG (Sub filter; png_level 0 stored, 1 zlib level 1 + Z_RLE,
  * >= 2 that zlib level), deflated in nthreads concurrent bands.  HOST side. */
 FAV_API int fav_png_write(const char *path, const unsigned char *pixels, int W, int H, int C, int png_level, int nthreads);
+/* f-2 / (e)  the conversions of image.load / flowFile.load / func_load_cert / image.save (fast_artistic_video.lua:95-110,161;
+ * flowFileLoader.lua:28-34) on DEVICE buffers: rgb_hwc H*W*3 bytes -> content [3,H,W] = byte / 255; flo_uv H*W (u,v) pairs ->
+ * flow [2,H,W] = (dy,dx); cert8 H*W bytes -> cert [H,W] = byte / 255 (1 - that with invert_occlusion); and a stylized frame
+ * [3,H,W] -> H*(1+3W) bytes of Sub-filtered PNG scanlines quantised like image.save.  flo_uv/flow and cert8/cert may be NULL. */
+FAV_API int fav_bytes_to_planes(const unsigned char *rgb_hwc, const float *flo_uv, const unsigned char *cert8, int invert_occlusion,
+                                float *content, float *flow, float *cert, int H, int W, void *stream);
+FAV_API int fav_planes_to_png_rows(const float *rgb_planes, unsigned char *rows, int H, int W, void *stream);
 /* f-2  one frame from FILE PAYLOADS (what image.load / flowFile.load / func_load_cert / image.save do on the host,
  * fast_artistic_video.lua:95-110,161): rgb_hwc = P6 payload (H*W*3 bytes), flo_uv = .flo payload (H*W (u,v) pairs),
  * cert8 = P5 payload of the certainty (both NULL for the first frame); png_rows_host receives H*(1+3W) bytes = the stylized

@@ -265,3 +265,32 @@ def test_full_size_properties_720p(fav):
     zf = torch.zeros((2, H, W), device="cuda")
     r0 = fav.consistencyChecker.check(zf, zf)  # zero flow is consistent except where x2/y2 leave the frame (:107)
     assert bool((r0[: H - 1, : W - 1] == 255).all()) and bool((r0[H - 1] == 0).all()) and bool((r0[:, W - 1] == 0).all())
+
+
+@pytest.mark.gpu
+def test_byte_conversions_on_device():
+    """fav_bytes_to_planes / fav_planes_to_png_rows == image.load's byte/255, flowFile.load's (u,v)->(dy,dx), -invert_occlusion and
+    image.save's clamp-x255-round, bit for bit."""
+    import torch
+
+    from fav_b200 import utils
+
+    H, W = 50, 68
+    g = torch.Generator().manual_seed(3)
+    rgb = torch.randint(0, 256, (H, W, 3), generator=g, dtype=torch.uint8).cuda()
+    flo = (torch.rand((H, W, 2), generator=g) * 8 - 4).cuda()
+    c8 = (torch.randint(0, 2, (H, W), generator=g, dtype=torch.uint8) * 255).cuda()
+    for inv in (False, True):
+        content, flow, cert = utils.bytes_to_planes(rgb, flo, c8, invert_occlusion=inv)
+        assert torch.equal(content, rgb.permute(2, 0, 1).float() / 255.0)
+        assert torch.equal(flow[0], flo[..., 1]) and torch.equal(flow[1], flo[..., 0])
+        want = c8.float() / 255.0
+        assert torch.equal(cert[0], 1.0 - want if inv else want)
+    content, flow, cert = utils.bytes_to_planes(rgb)
+    assert flow is None and cert is None
+    img = (torch.rand((3, H, W), generator=g) * 1.4 - 0.2).cuda()
+    rows = utils.planes_to_png_rows(img)
+    q = torch.floor(img.clamp(0, 1) * 255.0 + 0.5).clamp(0, 255).to(torch.int16).permute(1, 2, 0)  # [H,W,3]
+    sub = q.clone()
+    sub[:, 1:] -= q[:, :-1]
+    assert bool((rows[:, 0] == 1).all()) and torch.equal(rows[:, 1:], (sub % 256).to(torch.uint8).reshape(H, 3 * W))
