@@ -195,6 +195,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = utils.bind_host_to_gpu_numa(local)  # before any pinned allocation: host buffers in the GPU's NUMA node
     if world > 1:
         # NCCL prints its version banner on STDOUT at communicator creation; the contract is ONE JSON line on stdout,
         # so fd 1 points at stderr until the final print.
@@ -419,6 +420,7 @@ def run_ours(args):
                             "mask + min filter + warp + net on the GPU, stylized frame back to pinned host memory"},
             "gpu_launches": launches,
             "clocks": clocks,
+            "host": {"gpu_numa_binding": numa},
             "roofline": {"bound": "tensor",
                          "kernel": "conv_res_kernel, residual-block launches (128->128 3x3; 10 of the %d conv launches per " % n_conv_launch +
                                    "frame, the largest share of the step; the second conv of each block also normalises its input on load)",
@@ -492,6 +494,9 @@ def run_cfg3(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from fav_b200 import utils as fav_utils
+
+    numa = fav_utils.bind_host_to_gpu_numa(local)  # before any pinned allocation: host buffers in the GPU's NUMA node
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)  # NCCL banner must not reach stdout
@@ -505,8 +510,6 @@ def run_cfg3(args):
     net = models_video.synthetic_model("candy", ARCHS[args.arch])
     state = {}
     host = {}
-    from fav_b200 import utils as fav_utils
-
     bytes_mode = args.payload == "bytes"
     fr = np.stack([synth.make_frame(Hc, Wc, i + 1) for i in range(PO)])
     fw = np.stack([synth.make_forward_flow(Hc, Wc, i + 2) for i in range(PO)])
@@ -589,6 +592,14 @@ def run_cfg3(args):
             return None
         return timed(body)
 
+    h2d_gbps = None
+    if rank == 0:  # what this box's PCIe link delivers from pinned memory (256 MB, outside the timed region)
+        probe_h, probe_d = torch.empty(64 << 20, dtype=torch.float32).pin_memory(), torch.empty(64 << 20, dtype=torch.float32, device=dev)
+        probe_d.copy_(probe_h, non_blocking=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); probe_d.copy_(probe_h, non_blocking=True); e1.record(); torch.cuda.synchronize()
+        h2d_gbps = probe_h.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        del probe_h, probe_d
     run(2 * CH)  # warm-up: plans, graphs, NCCL connections
     sampler = ClockSampler(local)
     if rank == 0:
@@ -622,7 +633,8 @@ def run_cfg3(args):
                                "compute_only_frames_per_s": NC * F / tc_max, "compute_only_ms_per_step": 1e3 * tc_max / F,
                                "data_plane_exposed_share": max(0.0, 1.0 - tc_max / t_max),
                                "streams": "uploads + NCCL on a transfer stream, D2H of results on a third, frame loops on the compute stream",
-                               "rank0_h2d_GBps_needed": NC * F * per_frame_in / t_max / 1e9,
+                               "rank0_h2d_GBps_needed": NC * F * per_frame_in / t_max / 1e9, "rank0_h2d_GBps_probe": h2d_gbps,
+                               "gpu_numa_binding": numa,
                                "limit": "every input byte crosses rank 0's single PCIe link (H2D) before NVLink: the scatter is "
                                         "bound by that link, not by NVLink / NVSwitch"},
                 "clocks": clocks}

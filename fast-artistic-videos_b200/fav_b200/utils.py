@@ -67,6 +67,33 @@ def planes_to_png_rows(img: torch.Tensor) -> torch.Tensor:
     return rows
 
 
+def bind_host_to_gpu_numa(device_index: int = 0) -> dict:
+    """Restrict this process (threads created later inherit it) to the CPUs of the NUMA node the GPU hangs off, BEFORE pinned
+    buffers are allocated: first-touch then places them in that node's memory and host<->device copies do not cross the
+    socket interconnect.  Returns what was found / done; a box without NUMA information is left alone."""
+    info = dict(numa_node=None, cpus_before=None, cpus_after=None)
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cur = os.sched_getaffinity(0)
+        info["cpus_before"] = len(cur)
+        both = cur & cpus
+        if both:
+            os.sched_setaffinity(0, both)
+        info["cpus_after"] = len(os.sched_getaffinity(0))
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    return info
+
+
 def file_exists(name: str) -> bool:  # utils.lua:68-71
     return os.path.isfile(name)
 

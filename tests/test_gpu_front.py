@@ -282,10 +282,11 @@ def test_byte_conversions_on_device():
     c8 = (torch.randint(0, 2, (H, W), generator=g, dtype=torch.uint8) * 255).cuda()
     for inv in (False, True):
         content, flow, cert = utils.bytes_to_planes(rgb, flo, c8, invert_occlusion=inv)
-        assert torch.equal(content, rgb.permute(2, 0, 1).float() / 255.0)
+        # expectations on the CPU: IEEE division (torch's CUDA division by a scalar multiplies by the reciprocal)
+        assert torch.equal(content.cpu(), rgb.cpu().permute(2, 0, 1).float() / 255.0)
         assert torch.equal(flow[0], flo[..., 1]) and torch.equal(flow[1], flo[..., 0])
-        want = c8.float() / 255.0
-        assert torch.equal(cert[0], 1.0 - want if inv else want)
+        want = c8.cpu().float() / 255.0
+        assert torch.equal(cert[0].cpu(), 1.0 - want if inv else want)
     content, flow, cert = utils.bytes_to_planes(rgb)
     assert flow is None and cert is None
     img = (torch.rand((3, H, W), generator=g) * 1.4 - 0.2).cuda()
