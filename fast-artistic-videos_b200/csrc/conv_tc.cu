@@ -316,7 +316,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t a_stage16 = (uint32_t)job.stage16;
     const uint32_t *steps32 = reinterpret_cast<const uint32_t *>(job.steps);
     const uint32_t drow = dual ? (uint32_t)(warp - 6) : 0u;  // dual issue: this warp's accumulator row
-    const bool two = false;  // (mt = 2 units are split between the two issuing warps)
     // NOTE: no runtime integer division / modulo on this warp: ~150 cycles each on the issue path (measured with
     // tools/mma_bench.cu); ring positions are wrap counters.
     uint32_t sa = 0, aph = 0, tl = 0, sb = 0, bph = 0;
@@ -327,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const bool tr = job.trace && warp == 6 && lane == 0 && tl < (uint32_t)kTraceUnits;
       long long tr_a = 0, tr_b = 0;
       if (tr) trace_put(job, 8 + 8 * (int)tl, clock64());
-      const uint32_t d0 = tmem_base + as * 256u + drow * 128u, d1 = d0 + 128u;
+      const uint32_t d0 = tmem_base + as * 256u + drow * 128u;
       if (job.rf_R) {
         // ===== row-fold issue loop (conv.cuh): patch row iy feeds output rows r_min..r_max in ONE MMA per K step =====
         const int KH = job.rf_kh, R = job.rf_R;
@@ -421,78 +420,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (leader) tc_commit(&sh->t_full[as]);
         continue;
       }
-      uint32_t accumulate = 0, sc = 0;  // sc: K-step counter of the unit (K-split parity)
-      const bool dbg_nowait = job.dbg & 16, dbg_one = job.dbg & 32;
+      // ===== generic issue loop.  The issuing warps are INSTRUCTION bound on the narrow layers (ncu source counters, d64: the
+      // two warps were busy in their own code all the time -- ~570 instructions per weight chunk in an unrolled, predicated
+      // step ladder, i-cache misses -- while the tensor pipe was 25 % active), so this is the leanest form: per chunk one
+      // divergent region holding a plain loop over the K steps, ~12 instructions per step around the three UTCHMMAs.
+      uint32_t acc = 0, sc = 0;  // acc: this warp's accumulator holds a partial sum; sc: K-step counter of the unit (K-split parity)
       for (int g = 0; g < ngroups; ++g) {
         long long tw = tr ? clock64() : 0;
-        if (!dbg_nowait) mbar_wait(&sh->a_full[sa], aph);
+        mbar_wait(&sh->a_full[sa], aph);
         tc_fence_after();
         if (tr) { const long long now = clock64(); tr_a += now - tw; if (g == 0) trace_put(job, 8 + 8 * (int)tl + 1, now); }
         const uint32_t a_hi16 = (smem_u32(a_base + sa * 2 * a_stage_bytes) >> 4) + (dual_rows ? drow * a_tile16 : 0u), a_lo16 = a_hi16 + a_stage16;
-        int sidx = 0;
+        uint32_t sidx = 0;
         for (int c = 0; c < nchunks; ++c) {
           // ring: slot sb, phase bph.  resident: slot = chunk index, filled once (parity 0 stays satisfied afterwards)
-          if ((!job.b_resident || tl == 0) && !dbg_nowait) {  // resident weights are complete after the first tile
+          if (!job.b_resident || tl == 0) {  // resident weights are complete after the first tile
             const long long tw2 = tr ? clock64() : 0;
             mbar_wait(&sh->b_full[sb], job.b_resident ? 0u : bph);
             tc_fence_after();
             if (tr) tr_b += clock64() - tw2;
           }
           const uint32_t bh = (smem_u32(b_base + sb * chunk_bytes) >> 4) | ((uint32_t)Npad << 16);  // LBO = Npad * 16 B
-          if (Npad >= 128) {
-            // wide MMAs (>= 64 cycles each): one divergent region per K step is cheap enough and measured fastest
-            for (int st = 0; st < spc; ++st, ++sidx) {
-              const uint32_t dls = steps32[sidx];
-              const uint32_t bs = bh + (uint32_t)st * b_step16;
+          if (leader) {
+            uint32_t bs = bh;
+            for (uint32_t st = 0; st < (uint32_t)spc; ++st, bs += b_step16) {
+              if (ksplit && ((sc + st) & 1u) != drow) continue;  // K-split: alternate steps, one accumulator per warp
+              const uint32_t dls = steps32[sidx + st];
               const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + dls), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + dls);
               const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | bs, bd_lo = ((uint64_t)desc_hi << 32) | (bs + b_lo16);
-              const bool mine = !ksplit || ((sc + (uint32_t)st) & 1u) == drow;
-              if (leader && mine) {
-                tc_mma_f16(d0, ad_hi, bd_hi, idesc, accumulate);
-                if (!dbg_one) {
-                tc_mma_f16(d0, ad_lo, bd_hi, idesc, 1);
-                tc_mma_f16(d0, ad_hi, bd_lo, idesc, 1);
-                }
-                if (two) {  // second output row: same weights, patch shifted by one row
-                  tc_mma_f16(d1, ad_hi + a_tile16, bd_hi, idesc, accumulate);
-                  if (!dbg_one) {
-                  tc_mma_f16(d1, ad_lo + a_tile16, bd_hi, idesc, 1);
-                  tc_mma_f16(d1, ad_hi + a_tile16, bd_lo, idesc, 1);
-                  }
-                }
-              }
-              if (mine) accumulate = 1;
+              tc_mma_f16(d0, ad_hi, bd_hi, idesc, acc);
+              tc_mma_f16(d0, ad_lo, bd_hi, idesc, 1);
+              tc_mma_f16(d0, ad_hi, bd_lo, idesc, 1);
+              acc = 1;
             }
-          } else {
-          // All descriptors of the chunk are formed first (uniform datapath), then the elected lane issues every MMA of
-            // the chunk inside ONE divergent region: a reconvergence point (BSYNC) between MMA groups makes the warp
-            // wait for the previous UTCHMMAs to leave the scoreboard and serialises them (~2x slower at small N,
-            // measured with FAV_DBG=16).  spc <= kMaxSpc, guarded by warp-uniform predicates.
-            if (leader) {
-#pragma unroll
-              for (int st = 0; st < kMaxSpc; ++st) {
-                if (st < spc && (!ksplit || ((sc + (uint32_t)st) & 1u) == drow)) {
-                  const uint32_t bs = bh + (uint32_t)st * b_step16;
-                  const uint32_t dls = steps32[sidx + st];
-                  const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + dls), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + dls);
-                  const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | bs, bd_lo = ((uint64_t)desc_hi << 32) | (bs + b_lo16);
-                  tc_mma_f16(d0, ad_hi, bd_hi, idesc, accumulate);
-                  tc_mma_f16(d0, ad_lo, bd_hi, idesc, 1);
-                  tc_mma_f16(d0, ad_hi, bd_lo, idesc, 1);
-                  if (two) {  // second output row: same weights, patch shifted by one row
-                    tc_mma_f16(d1, ad_hi + a_tile16, bd_hi, idesc, accumulate);
-                    tc_mma_f16(d1, ad_lo + a_tile16, bd_hi, idesc, 1);
-                    tc_mma_f16(d1, ad_hi + a_tile16, bd_lo, idesc, 1);
-                  }
-                  accumulate = 1;
-                }
-              }
-            }
-            sidx += spc;
+            if (!job.b_resident) tc_commit(&sh->b_empty[sb]);  // frees the weight slot when the MMAs retire
           }
-          if (!ksplit || spc >= 2 || (sc & 1u) == drow) accumulate = 1;  // this warp issued at least one step of the chunk
+          sidx += (uint32_t)spc;
           sc += (uint32_t)spc;
-          if (!job.b_resident && leader) tc_commit(&sh->b_empty[sb]);  // frees the weight slot when the MMAs retire
           if (++sb == nslots) { sb = 0; bph ^= 1; }
         }
         if (leader) tc_commit(&sh->a_empty[sa]);  // frees the patch stage

@@ -353,6 +353,22 @@ extern "C" int emu_plan_info(int cin, int cout, int k, int stride, int pad, int 
 }
 
 
+extern "C" int emu_plan_detail(int cin, int cout, int k, int stride, int pad, int transposed, int adj, int H, int W, int *out16) {
+  ConvDef c;
+  init_conv_def(c, "emu", cin, cout, k, stride, pad, transposed != 0, adj);
+  build_phases(c);
+  Operand op = operand_geometry(cin, H, W, &c);
+  ConvPhase &ph = c.has_fold ? c.fold : c.phases[0];
+  if (!ph.pf && build_phase_tables(c, ph) != FAV_OK) return 1;
+  ConvJob j;
+  if (fill_conv_job(c, ph, op, j) != FAV_OK) return 2;
+  conv_tc_choose_slots(j);
+  const int v[16] = {j.ngroups, j.nchunks, j.spc, j.nrows, j.CbG, j.nseg, j.a_stages, j.b_slots, j.b_resident, j.stage16 * 16,
+                     j.chunk16 * 16, j.pslab16, j.tiles_x, j.ntiles, j.Npad, j.ksplit};
+  for (int i = 0; i < 16; ++i) out16[i] = v[i];
+  return 0;
+}
+
 // ---- conv_res.cu (swapped roles: weights = M operand, pixels = N operand, cost-balanced tile table) ---------------------
 // Emulates the kernel's addressing from the same host planner (conv_res_plan.hpp): bulk-copy sources, stage layout, the two
 // matrix descriptors per K step, accumulator rows / columns, planar output placement; checks it against a direct convolution
