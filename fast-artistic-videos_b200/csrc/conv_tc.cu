@@ -520,10 +520,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (valid) {
             float4 *rp = reinterpret_cast<float4 *>(job.raw) + (((int64_t)yo * job.raw_Cq + (c0 >> 2)) * job.raw_Wp + 2 * x);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              rp[(int64_t)q * job.raw_Wp] = make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]);
-              rp[(int64_t)q * job.raw_Wp + 1] = make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]);
-            }
+            for (int q = 0; q < 4; ++q)  // ONE 256-bit store per channel quad: whole 32-byte sectors (two float4 stores wrote each sector twice)
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(rp + (int64_t)q * job.raw_Wp), "f"(v0[4 * q]),
+                           "f"(v0[4 * q + 1]), "f"(v0[4 * q + 2]), "f"(v0[4 * q + 3]), "f"(v1[4 * q]), "f"(v1[4 * q + 1]),
+                           "f"(v1[4 * q + 2]), "f"(v1[4 * q + 3])
+                           : "memory");
           }
           if (job.stats && !(job.dbg & 64)) {
             float sv[16], sq[16];
