@@ -696,6 +696,12 @@ void conv_tc_choose_slots(ConvJob &job) {
       if (total <= kMaxB && tc_fixed_smem(t) + total * chunk <= budget) { job.a_stages = n; break; }
     }
   }
+  if (const char *e = getenv("FAV_ASTAGES")) {  // tuning knob: force the patch ring depth (weights take what is left)
+    const int n = atoi(e);
+    ConvJob t = job;
+    t.a_stages = n;
+    if (n >= 2 && n <= kMaxA && tc_fixed_smem(t) + 2 * chunk <= budget) job.a_stages = n;
+  }
   const size_t fixed = tc_fixed_smem(job);
   if (total <= kMaxB && fixed + total * chunk <= budget) {
     job.b_resident = 1;

@@ -116,6 +116,16 @@ int main() {
       {"M64 N256",                             {256, 0, 130, 8, 256, 8, 4096, 1, 4096, 0, 8, 0, 0, 64}},
       {"M64 N64",                              {64, 0, 130, 8, 64, 8, 4096, 1, 4096, 0, 8, 0, 0, 64}},
       {"M64 N128 two accumulators",            {128, 0, 130, 8, 128, 8, 4096, 0, 4096, 0, 8, 0, 4096, 64}},
+      // the narrow layers of conv_tc (r02): N = 64 / 128 with the patch strides of the stride-2 and transposed plans
+      {"N64  aligned",                         {64, 0, 128, 8, 64, 8, 4096, 1, 4096, 0, 8, 0, 2048}},
+      {"N64  A lbo130 +16B steps",             {64, 0, 130, 8, 64, 8, 4096, 1, 16, 0, 8, 0, 2048}},
+      {"N64  A lbo257 +16B steps (d64)",       {64, 0, 257, 8, 64, 8, 4096, 1, 16, 0, 8, 0, 2048}},
+      {"N64  A lbo257 +16B, two accumulators", {64, 0, 257, 8, 64, 8, 4096, 0, 16, 0, 8, 0, 2048}},
+      {"N64  A lbo257 commit/8 + ring wait",   {64, 0, 257, 8, 64, 8, 4096, 1, 16, 8, 8 | 1 | 4, 3, 2048}},
+      {"N64  A lbo257 commit/8, pollers",      {64, 0, 257, 8, 64, 8, 4096, 1, 16, 8, 8 | 1 | 4 | 16, 3, 2048}},
+      {"N128 A lbo257 +16B steps (d128)",      {128, 0, 257, 8, 128, 8, 4096, 1, 16, 0, 8, 0, 4096}},
+      {"N128 A lbo129 +16B steps (u32)",       {128, 0, 129, 8, 128, 8, 4096, 1, 16, 0, 8, 0, 4096}},
+      {"N128 A lbo129 commit/8 + ring wait",   {128, 0, 129, 8, 128, 8, 4096, 1, 16, 8, 8 | 1 | 4, 3, 4096}},
   };
   for (int g = 148; g <= 148; g += 147) {
     for (auto &e : cfgs) {
