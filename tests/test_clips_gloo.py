@@ -107,6 +107,36 @@ def _stream_worker(rank, world, port, q):
             q.put(ok)
         else:
             assert not got and st["bytes_out"] > 0
+        # byte payloads (bench.py --config cfg3 --payload bytes): uint8 frames travel, float flows, uint8 results come back
+        frames8 = (frames * 255).to(torch.uint8)
+        state.clear(); got.clear()
+
+        def load8(c, f0, f1):
+            return [frames8[c, f0:f1].clone(), flows[c, f0:f1].clone()]
+
+        def process8(c, f0, inputs):
+            fr, fl = inputs
+            assert fr.dtype == torch.uint8 and fl.dtype == torch.float32
+            outs = []
+            for i in range(fr.shape[0]):
+                prev = state.get(c, torch.zeros((3, H, W)))
+                prev = 0.5 * prev + fr[i].float() / 255.0 + fl[i].sum(0, keepdim=True)
+                state[c] = prev
+                outs.append((prev.clamp(0, 1) * 255.0 + 0.5).floor().to(torch.uint8))
+            return torch.stack(outs)
+
+        st = clips.stream_clips(n_clips, n_frames, chunk, [(3, H, W), (2, H, W)], (3, H, W), load8, process8, store_chunk,
+                                in_dtypes=[torch.uint8, torch.float32], out_dtype=torch.uint8)
+        if rank == 0:
+            ok = True
+            for c in range(n_clips):
+                prev = torch.zeros((3, H, W))
+                for i in range(n_frames):
+                    prev = 0.5 * prev + frames8[c, i].float() / 255.0 + flows[c, i].sum(0, keepdim=True)
+                    f0 = (i // chunk) * chunk
+                    want = (prev.clamp(0, 1) * 255.0 + 0.5).floor().to(torch.uint8)
+                    ok &= got[(c, f0)].dtype == torch.uint8 and bool(torch.equal(got[(c, f0)][i - f0], want))
+            q.put(ok)
     finally:
         dist.destroy_process_group()
 
@@ -122,7 +152,8 @@ def test_streaming_data_plane_world2_gloo():
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
-    assert q.get(timeout=5) is True
+    assert q.get(timeout=5) is True   # fp32 payloads
+    assert q.get(timeout=5) is True   # byte payloads
 
 
 def test_assign_clips_partitions():
