@@ -18,6 +18,7 @@ __device__ __forceinline__ void wait(uint64_t *bar, uint32_t parity) {
 }
 struct Cfg {
   int units, groups, chunks, spc, two;
+  int N;      // 0 = 128
   int flags;  // 1 wait+fence per chunk and per group, 2 commit per chunk, 4 per-chunk divergent region (else per step), 8 no LDC table
               // 16 one MMA of three
   uint32_t steps[32];
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(224, 1) bench(const __grid_constant__ Cfg c, l
   if (threadIdx.x < 32 || (dual && iw == 1)) {
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
-    const uint32_t N = 128;
+    const uint32_t N = c.N ? (uint32_t)c.N : 128u;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t desc_hi = 8u | (1u << 14);
     const uint32_t a_hi16 = smem_u32(smem) >> 4, a_lo16 = a_hi16 + (40960 >> 4), a_tile16 = 4 * 130;
@@ -62,14 +63,29 @@ __global__ void __launch_bounds__(224, 1) bench(const __grid_constant__ Cfg c, l
     uint32_t sb = 0;
     for (int u = 0; u < c.units; ++u) {
       const uint32_t d0 = tmem + (u & 1) * 256u + drow * 128u, d1 = d0 + 128u;
-      uint32_t acc = 0;
+      uint32_t acc = 0, sc = 0;
       for (int g = 0; g < c.groups; ++g) {
         if (c.flags & 1) { wait(&ready_bar, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
         int sidx = 0;
         for (int ch = 0; ch < c.chunks; ++ch) {
           if (c.flags & 1) { wait(&ready_bar, 0); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
           const uint32_t bh = ((smem_u32(smem + 100 * 1024) >> 4) + sb * 1024u) | (N << 16);
-          if (c.flags & 32) {
+          if (c.flags & 256) {
+            // the generic issue loop of conv_tc.cu as of round 2: plain loop in one divergent region per chunk; K-split (flag 128)
+            if (leader) {
+              uint32_t bs = bh;
+              for (uint32_t st = 0; st < (uint32_t)spc; ++st, bs += b_step16) {
+                if ((c.flags & 128) && ((sc + st) & 1u) != drow) continue;
+                const uint32_t dls = c.steps[sidx + st];
+                const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + dls), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + dls);
+                const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | bs, bd_lo = ((uint64_t)desc_hi << 32) | (bs + b_lo16);
+                mma(d0, ad_hi, bd_hi, idesc, acc);
+                if (!one) { mma(d0, ad_lo, bd_hi, idesc, 1); mma(d0, ad_hi, bd_lo, idesc, 1); }
+                acc = 1;
+              }
+            }
+            sidx += spc; sc += (uint32_t)spc;
+          } else if (c.flags & 32) {
             // slim descriptors: 64-bit invariant bases + one 64-bit add per descriptor
             const uint64_t A_HI = ((uint64_t)c.desc_hi_opaque << 32) | (a_hi16 + drow * a_tile16), A_LO = ((uint64_t)c.desc_hi_opaque << 32) | (a_lo16 + drow * a_tile16);
             const uint64_t BH = ((uint64_t)c.desc_hi_opaque << 32) | bh;
@@ -146,7 +162,7 @@ __global__ void __launch_bounds__(224, 1) bench(const __grid_constant__ Cfg c, l
 int main() {
   long long *d; cudaMalloc(&d, 148 * 8);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  struct { const char *name; int units, groups, chunks, spc, two, flags; } cfgs[] = {
+  struct { const char *name; int units, groups, chunks, spc, two, flags, N; } cfgs[] = {
       {"res: per-step region, waits, commits (kernel)", 4, 4, 9, 2, 1, 3},
       {"res: per-step region, no waits",                4, 4, 9, 2, 1, 2},
       {"res: per-step region, no waits/commits",        4, 4, 9, 2, 1, 0},
@@ -166,10 +182,20 @@ int main() {
       {"res: dual issue warps, slim",                   4, 4, 9, 2, 1, 3 | 32 | 64},
       {"res: dual issue warps, slim, one of three",     4, 4, 9, 2, 1, 3 | 32 | 64 | 16},
       {"mt1: slim",                                     8, 4, 9, 2, 0, 3 | 32},
+      // r02: the narrow layers of conv_tc (generic loop as of round 2 = flag 256; 128 = K-split; 64 = two issuing warps)
+      {"d64 : lean, ksplit, waits+commits",             17, 2, 3, 3, 0, 3 | 64 | 128 | 256, 64},
+      {"d64 : lean, ksplit, no waits",                  17, 2, 3, 3, 0, 2 | 64 | 128 | 256, 64},
+      {"d64 : lean, ksplit, no waits/commits",          17, 2, 3, 3, 0, 64 | 128 | 256, 64},
+      {"d64 : lean, one warp, waits+commits",           17, 2, 3, 3, 0, 3 | 256, 64},
+      {"d64 : lean, one warp, no waits/commits",        17, 2, 3, 3, 0, 256, 64},
+      {"d64 : lean, ksplit, one MMA of three",          17, 2, 3, 3, 0, 3 | 64 | 128 | 256 | 16, 64},
+      {"d128: lean, ksplit, waits+commits",             4, 4, 3, 3, 0, 3 | 64 | 128 | 256, 128},
+      {"d128: lean, ksplit, no waits/commits",          4, 4, 3, 3, 0, 64 | 128 | 256, 128},
+      {"d128: lean, one warp, waits+commits",           4, 4, 3, 3, 0, 3 | 256, 128},
   };
   for (auto &e : cfgs) {
     Cfg c{};
-    c.units = e.units; c.groups = e.groups; c.chunks = e.chunks; c.spc = e.spc; c.two = e.two; c.flags = e.flags;
+    c.units = e.units; c.groups = e.groups; c.chunks = e.chunks; c.spc = e.spc; c.two = e.two; c.flags = e.flags; c.N = e.N;
     for (int i = 0; i < 32; ++i) { c.steps[i] = (uint32_t)(i * 260 + (i % 3)) | (130u << 16); c.steps64[i] = c.steps[i]; }
     c.desc_hi_opaque = 8u | (1u << 14);
     if (e.spc == 4) c.chunks = 4;
