@@ -68,7 +68,6 @@ struct ConvJob {
   int pf;
   int pf_n[4], pf_col[4], pf_len16[4], pf_src16[4], pf_grp16, pf_cout;
   int ksplit;          // 1: two issuing warps take alternate K steps into two accumulators (columns +0 / +128)
-  int ksplit4;         // with ksplit, generic plans of <= 64 columns: FOUR issuing warps (6, 7, 12, 13), accumulators 64 columns apart
   // row-fold: per patch row iy (host-computed, keeps the issue loop free of index arithmetic): accumulator column of
   // the first output row it feeds, weight-row offset of its slice, instruction descriptors for all / old / new rows
   uint32_t rf_dcol[kMaxRfRows], rf_boff[kMaxRfRows], rf_idn_all[kMaxRfRows], rf_idn_acc[kMaxRfRows], rf_idn_new[kMaxRfRows],

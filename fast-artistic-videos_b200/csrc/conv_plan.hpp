@@ -485,10 +485,6 @@ static inline int fill_conv_job(const ConvDef &c, const ConvPhase &ph, const Ope
     const bool ok = j.mt == 1 || ph.rf_R;
     j.ksplit = (ok && cols <= 128 && (!ph.pf || ph.spc % 2 == 0) && !getenv("FAV_NO_KSPLIT")) ? 1 : 0;
     if (!ph.rf_R && !ph.pf && (int)ph.steps.size() * ph.nrg * ph.nchg < 2) j.ksplit = 0;
-    // one K step costs ~190 cycles of issue time per warp whatever its MMA count (tools/mma_bench3.cu): at <= 64 columns
-    // (144 cycles of tensor-pipe time per step) two issuing warps are not enough
-    j.ksplit4 = (j.ksplit && !ph.rf_R && !ph.pf && cols <= 64 && (int)ph.steps.size() * ph.nrg * ph.nchg >= 4 &&
-                 getenv("FAV_KSPLIT4")) ? 1 : 0;
   }
   if (ph.rf_R) {  // per-patch-row issue table (conv_tc.cu, row-fold loop)
     const int KH = j.rf_kh, R = j.rf_R, nblk = j.rf_nblk;

@@ -52,17 +52,9 @@ struct __align__(16) TcShared {
 };
 
 // accumulator columns [taddr, taddr+16) as floats; K-split jobs add the second issuing warp's partial sums (+128 columns)
-__device__ __forceinline__ void tmem_ld16_acc(uint32_t taddr, bool ksplit, bool ks4, float (&v)[16]) {
+__device__ __forceinline__ void tmem_ld16_acc(uint32_t taddr, bool ksplit, float (&v)[16]) {
   uint32_t r[16];
-  if (ks4) {  // four issuing warps: partial sums 64 columns apart
-    uint32_t q[16];
-    tmem_ld16x2(taddr, taddr + 64u, r, q);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
-    tmem_ld16x2(taddr + 128u, taddr + 192u, r, q);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r[i]) + __uint_as_float(q[i]);
-  } else if (ksplit) {
+  if (ksplit) {
     uint32_t q[16];
     tmem_ld16x2(taddr, taddr + 128u, r, q);
 #pragma unroll
@@ -141,8 +133,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   // accumulators (columns +0 / +128) that the epilogue adds.
   const bool dual_rows = job.mt == 2 && !job.rf_R && !job.pf, ksplit = job.ksplit != 0;
   const bool dual = dual_rows || ksplit;
-  const bool ks4 = job.ksplit4 != 0 && ksplit && !job.nl;  // four issuing warps: 6, 7, 12, 13 (12-14 are idle without norm-on-load)
-  const uint32_t nissue = ks4 ? 4u : (dual ? 2u : 1u);
+  const uint32_t nissue = dual ? 2u : 1u;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxA; ++i) { mbar_init(&sh->a_full[i], job.nl == 1 ? kNlWarps : (job.nl == 2 ? 4 : 1)); mbar_init(&sh->a_empty[i], nissue); }
     for (int i = 0; i < kMaxB; ++i) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], nissue); }
@@ -307,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
     __syncwarp();
-  } else if (warp == 6 || (warp == 7 && dual) || (ks4 && (warp == 12 || warp == 13))) {
+  } else if (warp == 6 || (warp == 7 && dual)) {
     // ===== MMA issuer: the whole warp runs the (warp-uniform) control flow so that descriptors live in uniform
     // registers and the UTCHMMAs issue back to back; one elected lane executes the tcgen05 instructions =====
     uint32_t leader;
@@ -324,8 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t a_tile16 = (uint32_t)(job.CbG * job.pslab16);  // mt = 2: second output row = one patch row lower
     const uint32_t a_stage16 = (uint32_t)job.stage16;
     const uint32_t *steps32 = reinterpret_cast<const uint32_t *>(job.steps);
-    const uint32_t drow = warp >= 12 ? (uint32_t)(warp - 10) : (dual ? (uint32_t)(warp - 6) : 0u);  // this warp's accumulator
-    const uint32_t kmask = ks4 ? 3u : 1u, acc_stride = ks4 ? 64u : 128u;
+    const uint32_t drow = dual ? (uint32_t)(warp - 6) : 0u;  // dual issue: this warp's accumulator row
     // NOTE: no runtime integer division / modulo on this warp: ~150 cycles each on the issue path (measured with
     // tools/mma_bench.cu); ring positions are wrap counters.
     uint32_t sa = 0, aph = 0, tl = 0, sb = 0, bph = 0;
@@ -336,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const bool tr = job.trace && warp == 6 && lane == 0 && tl < (uint32_t)kTraceUnits;
       long long tr_a = 0, tr_b = 0;
       if (tr) trace_put(job, 8 + 8 * (int)tl, clock64());
-      const uint32_t d0 = tmem_base + as * 256u + drow * acc_stride;
+      const uint32_t d0 = tmem_base + as * 256u + drow * 128u;
       if (job.rf_R) {
         // ===== row-fold issue loop (conv.cuh): patch row iy feeds output rows r_min..r_max in ONE MMA per K step =====
         const int KH = job.rf_kh, R = job.rf_R;
@@ -454,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (leader) {
             uint32_t bs = bh;
             for (uint32_t st = 0; st < (uint32_t)spc; ++st, bs += b_step16) {
-              if (ksplit && ((sc + st) & kmask) != drow) continue;  // K-split: every 2nd / 4th step, one accumulator per warp
+              if (ksplit && ((sc + st) & 1u) != drow) continue;  // K-split: alternate steps, one accumulator per warp
               const uint32_t dls = steps32[sidx + st];
               const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | (a_hi16 + dls), ad_lo = ((uint64_t)desc_hi << 32) | (a_lo16 + dls);
               const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | bs, bd_lo = ((uint64_t)desc_hi << 32) | (bs + b_lo16);
@@ -483,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int neg = job.nl == 1 ? 1 : 2;  // norm-on-load (8-producer mode): the second group works as patch producers
     const int px = wq * 32 + lane;
     const int nj = (Npad + 15) >> 4;
-    const bool ks = job.ksplit != 0, ks4e = job.ksplit4 != 0 && !job.nl;
+    const bool ks = job.ksplit != 0;
     float *exch = reinterpret_cast<float *>(sh + 1);  // x-fold exchange buffer [128][kExchPitch] / stats [2][128]
     float acc_s[8], acc_q[8];  // fused InstanceNorm statistics: this lane's channel (16*j + lane/2), all tiles
 #pragma unroll
@@ -569,7 +559,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         float *ex = exch + eg * (kTileM * kExchPitch);
         for (int c0 = 0; c0 < Npad; c0 += 16) {
           float r[16];
-          tmem_ld16_acc(taddr + (uint32_t)c0, ks, false, r);
+          tmem_ld16_acc(taddr + (uint32_t)c0, ks, r);
 #pragma unroll
           for (int i = 0; i < 16; ++i) ex[px * kExchPitch + c0 + i] = r[i];
         }
@@ -610,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (c0 >= Npad) break;
         if (neg == 2 && (nj >= 2 ? ((jc + t) & 1) : (t & 1)) != eg) continue;  // work split between the two epilogue groups
         float v[16];
-        tmem_ld16_acc(taddr + (uint32_t)c0, ks, ks4e, v);
+        tmem_ld16_acc(taddr + (uint32_t)c0, ks, v);
         if (job.final_mode == 0) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {

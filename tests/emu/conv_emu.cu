@@ -95,7 +95,6 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
     std::vector<uint16_t> st_hi((size_t)j.stage16 * 8), st_lo((size_t)j.stage16 * 8);
     std::vector<double> acc(j.rf_R ? (size_t)kTileM * 512 : (size_t)2 * kTileM * Npad);
     std::vector<double> acc2(acc.size());  // K-split: the second issuing warp's accumulator (TMEM columns +128)
-    std::vector<double> acc3(acc.size()), acc4(acc.size());  // 4-way K-split (ksplit4): warps 12 / 13
     if (j.ksplit && (j.rf_R ? j.rf_R * j.rf_nblk : Npad) > 128) { set_error("ksplit needs <= 128 columns"); return 10; }
     if (j.ksplit && j.mt != 1 && !j.rf_R) { set_error("ksplit with mt = 2"); return 10; }
     for (int tile = 0; tile < j.ntiles; ++tile) {
@@ -103,8 +102,7 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
       const double poison = (j.rf_R || j.ksplit) ? 1e30 : 0.0;  // stale TMEM must be overwritten, not accumulated
       std::fill(acc.begin(), acc.end(), poison);
       std::fill(acc2.begin(), acc2.end(), poison);
-      std::fill(acc3.begin(), acc3.end(), poison); std::fill(acc4.begin(), acc4.end(), poison);
-      bool first_w[4] = {true, true, true, true};  // K-split: first MMA of each issuing warp in the unit (accumulate = 0)
+      bool first_w[2] = {true, true};  // K-split: first MMA of each issuing warp in the unit (accumulate = 0)
       int sc = 0;                       // K-step counter of the unit
       for (int g = 0; g < j.ngroups; ++g) {
         // A producer
@@ -208,8 +206,8 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
           for (int st = 0; st < j.spc; ++st) {
             const KStep ks = j.steps[ch * j.spc + st];
             mma_count += 3 * j.mt;
-            const int w = j.ksplit ? ((sc + st) & (j.ksplit4 ? 3 : 1)) : 0;
-            std::vector<double> &accw = w == 0 ? acc : (w == 1 ? acc2 : (w == 2 ? acc3 : acc4));
+            const int w = j.ksplit ? ((sc + st) & 1) : 0;
+            std::vector<double> &accw = w ? acc2 : acc;
             if (j.ksplit && first_w[w]) { std::fill(accw.begin(), accw.end(), 0.0); first_w[w] = false; }
             for (int t = 0; t < j.mt; ++t)
             for (int m = 0; m < kTileM; ++m)
@@ -232,8 +230,7 @@ extern "C" int emu_conv_check(int cin, int cout, int k, int stride, int pad, int
       }
       // epilogue: K-split units add the second warp's accumulator
       if (j.ksplit)
-        for (size_t i = 0; i < acc.size(); ++i) acc[i] += acc2[i] + (j.ksplit4 ? acc3[i] + acc4[i] : 0.0);
-      if (j.ksplit4 && (Npad > 64 || j.rf_R || j.pf || j.mt != 1)) { set_error("ksplit4 needs a generic one-row plan of <= 64 columns"); return 10; }
+        for (size_t i = 0; i < acc.size(); ++i) acc[i] += acc2[i];
       // epilogue placement
       if (j.rf_R) {
         const int nblk = j.rf_nblk;
